@@ -1,0 +1,193 @@
+"""Generate the golden fixtures in this directory by running the UNMODIFIED reference.
+
+Run in the build container only (it needs /root/reference, which does not exist on the GPU box):
+
+    python tests/golden/make_golden.py
+
+The reference modules are imported read-only from /root/reference (the model path
+imports under torch 2.11 with /root/reference and /root/reference/keypoints on sys.path).  Weights
+come from ``oracle.init_state_dict`` (numpy PCG64 stream) and are *loaded into the reference
+modules* with load_state_dict(strict=True), so a fixture stores only inputs and the reference's
+outputs.  Everything is fp32 on CPU, torch deterministic single-thread.
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+sys.path[:0] = ['/root/reference', '/root/reference/keypoints']
+
+import warnings  # noqa: E402
+warnings.filterwarnings('ignore')
+
+from keypoints.models import transporter as ref_transporter  # noqa: E402
+from keypoints.models import knn as ref_knn, vgg as ref_vgg, keynet as ref_keynet  # noqa: E402
+from keypoints.models import functional as RF  # noqa: E402
+import tps as ref_tps  # noqa: E402
+import data_augments as ref_aug  # noqa: E402
+
+from oracle import keypoints_oracle as O  # noqa: E402
+
+torch.set_num_threads(1)
+torch.use_deterministic_algorithms(True)
+
+
+def npy(t):
+    return t.detach().cpu().numpy()
+
+
+def synth_images(rng, n, c, h, w, lo=0.0, hi=1.0):
+    """Smooth noise + bright rectangles (SURVEY 8d synthetic inputs), numpy stream."""
+    base = torch.from_numpy(rng.random((n, c, max(h // 8, 2), max(w // 8, 2))).astype('float32'))
+    x = torch.nn.functional.interpolate(base, size=(h, w), mode='bilinear', align_corners=False)
+    for i in range(n):
+        for _ in range(3):
+            y0, x0 = int(rng.integers(0, h - 4)), int(rng.integers(0, w - 4))
+            hh, ww = int(rng.integers(2, max(h // 4, 3))), int(rng.integers(2, max(w // 4, 3)))
+            x[i, :, y0:y0 + hh, x0:x0 + ww] = torch.from_numpy(rng.random(c).astype('float32')).view(c, 1, 1) * 0.5 + 0.5
+    return (x * (hi - lo) + lo).contiguous()
+
+
+def grad_summary(out, name, g):
+    """Full tensor when small, otherwise sum / abs-sum / strided sample."""
+    g = npy(g).astype('float32')
+    if g.size <= 40000:
+        out[f'grad/{name}'] = g
+    else:
+        flat = g.reshape(-1)
+        out[f'gradsum/{name}'] = np.array([flat.astype('float64').sum(), np.abs(flat).astype('float64').sum()])
+        out[f'gradsample/{name}'] = flat[::997].copy()
+
+
+def known_answers():
+    out = {}
+    for v in (1.0, 5.0, 100.0):                                   # tests/tests.py:11-17 style literal
+        hm = torch.zeros(1, 1, 5, 5); hm[0, 0, 2, 2] = v
+        out[f'peak5_center_{int(v)}/soft'] = npy(RF.spacial_softmax(hm))
+        out[f'peak5_center_{int(v)}/logsoft'] = npy(RF.spacial_logsoftmax(hm))
+    hm = torch.zeros(1, 1, 5, 5); hm[0, 0, 4, 4] = 5.0             # tests/tests.py:19-25
+    out['peak5_corner/soft'] = npy(RF.spacial_softmax(hm))
+    out['peak5_corner/logsoft'] = npy(RF.spacial_logsoftmax(hm))
+    hm = torch.zeros(1, 1, 16, 16); hm[0, 0, 0, 15] = 20.0         # tests/tests.py:239-240
+    k = RF.spacial_logsoftmax(hm)
+    out['coords16/k'] = npy(k)
+    out['coords16/g'] = npy(RF.gaussian_like_function(k, 16, 16))
+    c = torch.tensor([[0., 0], [1., 0], [1., 1], [0, 1]]).unsqueeze(0)   # tps.py:197-212
+    out['tps_identity/grid'] = npy(ref_tps.tps_grid(torch.zeros(1, 7, 2), c, (1, 1, 6, 3)))
+    np.savez_compressed(os.path.join(HERE, 'known_answers.npz'), **out)
+
+
+def functional_fixture():
+    rng = np.random.default_rng(11)
+    out = {}
+    heat = torch.from_numpy((rng.standard_normal((2, 3, 7, 9)) * 3).astype('float32')).requires_grad_(True)
+    k, (ph, pw) = RF.spacial_logsoftmax(heat, probs=True)
+    gk = torch.from_numpy(rng.standard_normal((2, 3, 2)).astype('float32'))
+    (k * gk).sum().backward()
+    out.update({'ssm/heat': npy(heat), 'ssm/k': npy(k), 'ssm/ph': npy(ph), 'ssm/pw': npy(pw), 'ssm/gk': npy(gk),
+                'ssm/dheat': npy(heat.grad)})
+    k2, (ph2, pw2) = RF.spacial_softmax(heat.detach(), probs=True)
+    out.update({'ssm/k_soft': npy(k2), 'ssm/ph_soft': npy(ph2)})
+    kp = torch.from_numpy(rng.random((2, 3, 2)).astype('float32')).requires_grad_(True)
+    m = RF.gaussian_like_function(kp, 6, 11)
+    gm = torch.from_numpy(rng.standard_normal((2, 3, 6, 11)).astype('float32'))
+    (m * gm).sum().backward()
+    out.update({'gauss/kp': npy(kp), 'gauss/m': npy(m), 'gauss/gm': npy(gm), 'gauss/dkp': npy(kp.grad)})
+    np.savez_compressed(os.path.join(HERE, 'functional.npz'), **out)
+
+
+def tps_fixture():
+    rng = np.random.default_rng(12)
+    out = {}
+    x = synth_images(rng, 3, 3, 20, 14)
+    theta = torch.from_numpy((rng.standard_normal((3, 7, 2)) * 0.05).astype('float32'))
+    ctrl = torch.from_numpy(rng.random((3, 4, 2)).astype('float32'))
+    rot = torch.from_numpy(((rng.random(3) * 2 - 1) * 0.1).astype('float32'))
+    out.update({'x': npy(x), 'theta': npy(theta), 'ctrl': npy(ctrl), 'rot': npy(rot)})
+    out['grid'] = npy(ref_tps.tps_grid(theta, ctrl, tuple(x.shape)))
+    out['tps'] = npy(ref_tps.tps_transform(x, theta, ctrl))
+    out['rot_out'] = npy(ref_tps.rotate_affine_grid_multi(x, rot))
+    theta_r = torch.from_numpy((rng.standard_normal((3, 6, 2)) * 0.05).astype('float32'))    # reduced form
+    out['theta_reduced'] = npy(theta_r)
+    out['grid_reduced'] = npy(ref_tps.tps_grid(theta_r, ctrl, tuple(x.shape)))
+    # the full augmentation with the reference's own RNG consumption order
+    torch.manual_seed(77)
+    x1, x2, mask = ref_aug.TpsAndRotate(4, 0.05, 0.1)(x, x)
+    out.update({'aug/x1': npy(x1), 'aug/x2': npy(x2), 'aug/mask': npy(mask)})
+    np.savez_compressed(os.path.join(HERE, 'tps.npz'), **out)
+
+
+def build_ref_keynet(model_type, cin, z, K):
+    """keynet.make is broken in the reference; assemble exactly what keynet.py:51-59 intends."""
+    nn = torch.nn
+    enc = ref_knn.Unit(cin, z, ref_vgg.make_layers(ref_vgg.vgg_cfg[model_type], nonlinearity=nn.LeakyReLU,
+                                                   nonlinearity_kwargs={'inplace': True}))
+    dec = ref_knn.Unit(z + K, cin, ref_vgg.make_layers(ref_vgg.decoder_cfg[model_type]))
+    kp = ref_knn.Unit(cin, K, ref_vgg.make_layers(ref_vgg.vgg_cfg[model_type], nonlinearity=nn.LeakyReLU,
+                                                  nonlinearity_kwargs={'inplace': True}))
+    return ref_keynet.KeyNet(enc, kp, ref_knn.GaussianLike(sigma=0.1), dec, init_weights=True)
+
+
+def model_fixture(name, kind, model_type, cin, z, K, n, h, w, seed, lo, hi, with_mask, adam=False):
+    rng = np.random.default_rng(seed)
+    if kind == 'transporter':
+        net = ref_transporter.make(model_type, cin, z, K)
+        ops = O.transporter_ops(model_type, cin, z, K)
+    else:
+        net = build_ref_keynet(model_type, cin, z, K)
+        ops = O.keynet_ops(model_type, cin, z, K)
+    sd = O.init_state_dict(ops, seed)
+    net.load_state_dict(sd, strict=True)
+    a = synth_images(rng, n, cin, h, w, lo, hi)
+    b = synth_images(rng, n, cin, h, w, lo, hi)
+    mask = None
+    if with_mask:
+        mask = (torch.from_numpy(rng.random((n, cin, h, w)).astype('float32')) > 0.2).float()
+    out = {'a': npy(a), 'b': npy(b), 'meta': np.array([cin, z, K, n, h, w, seed])}
+    if mask is not None:
+        out['mask'] = npy(mask)
+    optim = torch.optim.Adam(net.parameters(), lr=1e-4)
+    optim.zero_grad()
+    res = net(a, b)
+    loss = ((res[0] - b) ** 2 * mask).mean() if mask is not None else ((res[0] - b) ** 2).mean()
+    loss.backward()
+    names = ['x_hat', 'phi', 'k', 'm', 'p', 'heat', 'mask_s', 'mask_t'] if kind == 'transporter' else \
+            ['x_hat', 'z', 'k', 'm', 'p', 'heat']
+    for nm, r in zip(names, res):
+        if nm == 'p':
+            out['out/p_h'], out['out/p_w'] = npy(r[0]), npy(r[1])
+        else:
+            out[f'out/{nm}'] = npy(r)
+    out['loss'] = npy(loss)
+    for pname, p in net.named_parameters():
+        grad_summary(out, pname, p.grad)
+    new_sd = net.state_dict()
+    for key in new_sd:
+        if 'running_' in key or 'num_batches' in key:
+            out[f'stat/{key}'] = npy(new_sd[key])
+    if adam:
+        optim.step()
+        for pname, p in net.named_parameters():
+            out[f'adam/{pname}'] = npy(p)
+    np.savez_compressed(os.path.join(HERE, f'{name}.npz'), **out)
+    print(name, 'loss', float(loss), 'bytes', os.path.getsize(os.path.join(HERE, f'{name}.npz')))
+
+
+if __name__ == '__main__':
+    known_answers()
+    functional_fixture()
+    tps_fixture()
+    # BASELINE config 1 verbatim: Transporter Pong-grey 84x84 K=4 batch=2 (range [-1,1], datasets.py:292-295)
+    model_fixture('transporter_pong', 'transporter', 'VGG_PONG_LAYERNECK', 1, 16, 4, 2, 84, 84, 101, -1.0, 1.0,
+                  with_mask=False, adam=True)
+    # the F stacks (configs 3-5) at reduced spatial size; weights regenerate from the seed
+    model_fixture('keynet_F', 'keynet', 'F', 3, 64, 10, 2, 32, 32, 102, 0.0, 1.0, with_mask=True)
+    model_fixture('transporter_F', 'transporter', 'F', 3, 64, 6, 2, 32, 32, 103, 0.0, 1.0, with_mask=True)
+    # a pooled + upsampled small net (exercises 'M' right after in_block and 'U' chains)
+    model_fixture('keynet_pong_mu', 'keynet', 'VGG_PONG', 1, 8, 3, 3, 24, 16, 104, -1.0, 1.0, with_mask=False,
+                  adam=True)
+    print('done')

@@ -1,0 +1,127 @@
+"""Pins the CPU oracle (oracle/keypoints_oracle.py) to outputs of the reference itself
+(tests/golden/*.npz, produced by tests/golden/make_golden.py) and to the known answers derived from
+the reference tests' literals.  fp32 tolerance: 1e-5 relative-to-max
+(oracle and reference issue the same ATen ops, so most entries are bit-identical)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import keypoints_oracle as O
+
+torch.set_num_threads(1)      # the fixtures were made single-threaded; same reduction order -> same bits
+
+
+def bn_sibling(key, keys):
+    """For 'grad/<unit>.<block>.<i>.bias' return the key of the BatchNorm bias that follows the conv
+    (index i+1) if there is one.  The bias of a conv feeding train-mode BN has a mathematically zero
+    gradient (BN subtracts the batch mean); what the reference stores there is rounding noise, so it
+    is compared on the scale of the BN bias gradient instead of its own."""
+    if not key.endswith('.bias'):
+        return None
+    head, idx, _ = key.rsplit('.', 2)
+    sib = f'{head}.{int(idx) + 1}.bias'
+    return sib if sib in keys else None
+
+
+def close(a, b, tol=1e-5, name='', scale=None):
+    if isinstance(a, torch.Tensor):
+        a = a.detach().cpu().numpy()
+    a = np.asarray(a, dtype=np.float64); b = np.asarray(b, dtype=np.float64)
+    assert a.shape == b.shape, (name, a.shape, b.shape)
+    scale = max(np.abs(b).max(), 1e-12) if scale is None else scale
+    err = np.abs(a - b).max() / scale
+    assert err <= tol, f'{name}: rel-to-max err {err:.3e} > {tol}'
+
+
+def test_known_answers(golden):
+    g = golden('known_answers')
+    for v in (1, 5, 100):
+        hm = torch.zeros(1, 1, 5, 5); hm[0, 0, 2, 2] = float(v)
+        close(O.spatial_logsoftmax(hm)[0], g[f'peak5_center_{v}/logsoft'])
+        close(O.spatial_softmax(hm)[0], g[f'peak5_center_{v}/soft'])
+        close(O.spatial_logsoftmax(hm)[0], np.full((1, 1, 2), 0.5))
+    hm = torch.zeros(1, 1, 5, 5); hm[0, 0, 4, 4] = 5.0
+    close(O.spatial_logsoftmax(hm)[0], g['peak5_corner/logsoft'])
+    close(O.spatial_logsoftmax(hm)[0], np.full((1, 1, 2), 0.627881), tol=1e-5)
+    hm = torch.zeros(1, 1, 16, 16); hm[0, 0, 0, 15] = 20.0
+    k = O.spatial_logsoftmax(hm)[0]
+    close(k, g['coords16/k'])
+    close(k, np.array([[[0.432658, 0.567342]]]), tol=1e-5)
+    gm = O.gaussian_like(k, 16, 16)
+    close(gm, g['coords16/g'])
+    assert abs(float(gm.max()) - 0.099278) < 1e-5 and int(gm.argmax()) == 6 * 16 + 9
+    c = torch.tensor([[0., 0], [1., 0], [1., 1], [0, 1]]).unsqueeze(0)
+    grid = O.tps_grid(torch.zeros(1, 7, 2), c, (1, 1, 6, 3))
+    close(grid, g['tps_identity/grid'])
+    close(grid[0, :, :, 0], np.tile(np.array([-1., 0., 1.]), (6, 1)), tol=1e-6)
+    close(grid[0, :, :, 1], np.tile(np.linspace(-1, 1, 6)[:, None], (1, 3)), tol=1e-6)
+
+
+def test_functional(golden):
+    g = golden('functional')
+    heat = torch.from_numpy(g['ssm/heat']).requires_grad_(True)
+    k, (ph, pw) = O.spatial_logsoftmax(heat)
+    close(k, g['ssm/k']); close(ph, g['ssm/ph']); close(pw, g['ssm/pw'])
+    (k * torch.from_numpy(g['ssm/gk'])).sum().backward()
+    close(heat.grad, g['ssm/dheat'])
+    k2, (ph2, _) = O.spatial_softmax(heat.detach())
+    close(k2, g['ssm/k_soft']); close(ph2, g['ssm/ph_soft'])
+    kp = torch.from_numpy(g['gauss/kp']).requires_grad_(True)
+    m = O.gaussian_like(kp, 6, 11)
+    close(m, g['gauss/m'])
+    (m * torch.from_numpy(g['gauss/gm'])).sum().backward()
+    close(kp.grad, g['gauss/dkp'])
+
+
+def test_tps(golden):
+    g = golden('tps')
+    x, theta, ctrl, rot = (torch.from_numpy(g[k]) for k in ('x', 'theta', 'ctrl', 'rot'))
+    close(O.tps_grid(theta, ctrl, tuple(x.shape)), g['grid'], tol=2e-6)
+    close(O.tps_grid(torch.from_numpy(g['theta_reduced']), ctrl, tuple(x.shape)), g['grid_reduced'], tol=2e-6)
+    close(O.tps_transform(x, theta, ctrl), g['tps'], tol=2e-5)
+    close(O.rotate_affine_grid_multi(x, rot), g['rot_out'])
+    torch.manual_seed(77)                       # same RNG consumption order as data_augments.py:31,35
+    p1 = O.sample_perturb_params(3, 4, 0.05, 0.1)
+    p2 = O.sample_perturb_params(3, 4, 0.05, 0.1)
+    x1, x2, mask = O.tps_and_rotate(x, p1, p2)
+    close(x1, g['aug/x1'], tol=5e-5); close(x2, g['aug/x2'], tol=5e-5); close(mask, g['aug/mask'], tol=5e-5)
+
+
+MODELS = [('transporter_pong', 'transporter', 'VGG_PONG_LAYERNECK'), ('keynet_F', 'keynet', 'F'),
+          ('transporter_F', 'transporter', 'F'), ('keynet_pong_mu', 'keynet', 'VGG_PONG')]
+
+
+@pytest.mark.parametrize('name,kind,model_type', MODELS)
+def test_model_step(golden, name, kind, model_type):
+    g = golden(name)
+    cin, z, K, n, h, w, seed = (int(v) for v in g['meta'])
+    ops = O.transporter_ops(model_type, cin, z, K) if kind == 'transporter' else O.keynet_ops(model_type, cin, z, K)
+    sd = O.init_state_dict(ops, seed)
+    tr = O.OracleTrainer(kind, model_type, cin, z, K, sd)
+    a, b = torch.from_numpy(g['a']), torch.from_numpy(g['b'])
+    mask = torch.from_numpy(g['mask']) if 'mask' in g else None
+    loss, out = tr.step(a, b, mask)
+    names = ['x_hat', 'phi', 'k', 'm', 'p', 'heat', 'mask_s', 'mask_t'] if kind == 'transporter' else \
+            ['x_hat', 'z', 'k', 'm', 'p', 'heat']
+    tol = 2e-5
+    for nm, r in zip(names, out):
+        if nm == 'p':
+            close(r[0], g['out/p_h'], tol, 'p_h'); close(r[1], g['out/p_w'], tol, 'p_w')
+        else:
+            close(r, g[f'out/{nm}'], tol, nm)
+    close(loss, g['loss'], tol, 'loss')
+    for key in g:
+        if key.startswith('grad/'):
+            sib = bn_sibling(key, g)
+            close(sd[key[5:]].grad, g[key], 2e-4, key, scale=None if sib is None else np.abs(g[sib]).max())
+        elif key.startswith('gradsample/'):
+            close(sd[key[11:]].grad.reshape(-1)[::997], g[key], 2e-4, key)
+        elif key.startswith('stat/'):
+            close(sd[key[5:]], g[key], tol, key)
+        elif key.startswith('adam/'):
+            if bn_sibling('grad/' + key[5:], g) is not None:
+                # Adam normalises the rounding-noise gradient of a pre-BN conv bias to a +-lr step:
+                # the reference's value is noise-determined, only |step| <= lr is meaningful
+                close(sd[key[5:]], g[key], 1.0, key, scale=2.001e-4)
+            else:
+                close(sd[key[5:]], g[key], 0.02, key, scale=1e-4)      # within 2 % of one lr-sized step
