@@ -1,0 +1,335 @@
+// Keypoint bottleneck: marginal spatial soft-max -> K (y,x) keypoints, gaussian-like heat-map render,
+// Transporter feature transport ('max' combine), masked L2 loss — forward and closed-form backward.
+// All latency/HBM-bound: one block per (n,k) plane, warp-shuffle reductions, coalesced plane reads.
+#include "kp_common.cuh"
+
+namespace {
+
+template <typename F>
+int dispatch1(int dt, F&& f) {
+    if (dt == KP_F32) return f(float{});
+    if (dt == KP_BF16) return f(bf16{});
+    kp_set_error("bad dtype %d", dt);
+    return KP_ERR_ARG;
+}
+
+__device__ __forceinline__ float ruler(int i, int n) { return n > 1 ? (float)i / (float)(n - 1) : 0.f; }
+
+// block-wide sum of one float; every thread gets the result.  blockDim.x multiple of 32, <= 1024.
+__device__ float block_sum(float v, float* scratch) {
+    v = warp_sum(v);
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    __syncthreads();
+    if (lane == 0) scratch[wid] = v;
+    __syncthreads();
+    float t = (lane < nw) ? scratch[lane] : 0.f;
+    t = warp_sum(t);
+    return t;
+}
+
+// softmax of s[0:n] in place by one warp, returns expectation against ruler
+__device__ float warp_softmax_expect(float* s, int n, int lane) {
+    float mx = -INFINITY;
+    for (int i = lane; i < n; i += 32) mx = fmaxf(mx, s[i]);
+    mx = warp_max(mx);
+    float sum = 0.f;
+    for (int i = lane; i < n; i += 32) sum += expf(s[i] - mx);
+    sum = warp_sum(sum);
+    const float lse = mx + logf(sum);
+    float e = 0.f;
+    for (int i = lane; i < n; i += 32) {
+        float p = expf(s[i] - lse);        // exp(log_softmax), functional.py:11-14,44
+        s[i] = p;
+        e += p * ruler(i, n);
+    }
+    return warp_sum(e);
+}
+
+__global__ void __launch_bounds__(256) ssm_fwd_k(const float* __restrict__ heat, int h, int w, float* k, float* ph,
+                                                 float* pw) {
+    extern __shared__ float sm[];
+    float* a = sm;          // [h] row means
+    float* b = sm + h;      // [w] column means
+    const float* pl = heat + (long long)blockIdx.x * h * w;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    for (int i = wid; i < h; i += nw) {
+        float s = 0.f;
+        for (int j = lane; j < w; j += 32) s += pl[(long long)i * w + j];
+        s = warp_sum(s);
+        if (lane == 0) a[i] = s / (float)w;
+    }
+    for (int j = threadIdx.x; j < w; j += blockDim.x) {
+        float s = 0.f;
+        for (int i = 0; i < h; ++i) s += pl[(long long)i * w + j];
+        b[j] = s / (float)h;
+    }
+    __syncthreads();
+    if (wid == 0) {
+        float ky = warp_softmax_expect(a, h, lane);
+        if (lane == 0) k[blockIdx.x * 2 + 0] = ky;
+    } else if (wid == 1) {
+        float kx = warp_softmax_expect(b, w, lane);
+        if (lane == 0) k[blockIdx.x * 2 + 1] = kx;
+    }
+    __syncthreads();
+    if (ph) for (int i = threadIdx.x; i < h; i += blockDim.x) ph[(long long)blockIdx.x * h + i] = a[i];
+    if (pw) for (int j = threadIdx.x; j < w; j += blockDim.x) pw[(long long)blockIdx.x * w + j] = b[j];
+}
+
+// da_i = p_i (y_i - k_y) dk_y ; db_j likewise ; dheat[i,j] = da_i / w + db_j / h
+__global__ void __launch_bounds__(256) ssm_bwd_k(const float* __restrict__ dk, const float* __restrict__ k,
+                                                 const float* __restrict__ ph, const float* __restrict__ pw, int h,
+                                                 int w, float* dheat) {
+    extern __shared__ float sm[];
+    float* da = sm;
+    float* db = sm + h;
+    const long long pl = blockIdx.x;
+    const float ky = k[pl * 2], kx = k[pl * 2 + 1], gy = dk[pl * 2], gx = dk[pl * 2 + 1];
+    for (int i = threadIdx.x; i < h; i += blockDim.x) da[i] = ph[pl * h + i] * (ruler(i, h) - ky) * gy / (float)w;
+    for (int j = threadIdx.x; j < w; j += blockDim.x) db[j] = pw[pl * w + j] * (ruler(j, w) - kx) * gx / (float)h;
+    __syncthreads();
+    float* o = dheat + pl * h * w;
+    for (int e = threadIdx.x; e < h * w; e += blockDim.x) o[e] = da[e / w] + db[e % w];
+}
+
+__device__ __forceinline__ float gauss(float yi, float xj, float ky, float kx, float two_s2, float eps) {
+    float dy = yi - ky, dx = xj - kx;
+    return expf(-sqrtf(dy * dy + dx * dx + eps) / two_s2);
+}
+
+__global__ void __launch_bounds__(256) gaussian_fwd_k(const float* __restrict__ k, int h, int w, float two_s2,
+                                                      float eps, float* m) {
+    const long long pl = blockIdx.x;
+    const float ky = k[pl * 2], kx = k[pl * 2 + 1];
+    float* o = m + pl * h * w;
+    for (int e = threadIdx.x; e < h * w; e += blockDim.x) o[e] = gauss(ruler(e / w, h), ruler(e % w, w), ky, kx, two_s2, eps);
+}
+
+template <typename TG>
+__global__ void __launch_bounds__(256)
+gaussian_bwd_k(View<TG> dm, int pad, const float* __restrict__ k, const int* __restrict__ argmax, int K, int h, int w,
+               float two_s2, float eps, float* dk) {
+    __shared__ float scratch[32];
+    const int pl = blockIdx.x, n = pl / K, kk = pl % K;
+    const float ky = k[pl * 2], kx = k[pl * 2 + 1];
+    float sy = 0.f, sx = 0.f;
+    for (int e = threadIdx.x; e < h * w; e += blockDim.x) {
+        int i = e / w, j = e % w;
+        if (argmax && argmax[(long long)n * h * w + e] != kk) continue;
+        float g = 0.f;
+        {   // gradient at (i,j), replicate-pad border folded in
+            const int c = argmax ? 0 : kk;
+            if (!pad) {
+                g = to_f(*dm.at(n, i, j, c));
+            } else {
+                int ys[3], xs[3], ny = 0, nx = 0;
+                ys[ny++] = i + 1; if (i == 0) ys[ny++] = 0; if (i == h - 1) ys[ny++] = h + 1;
+                xs[nx++] = j + 1; if (j == 0) xs[nx++] = 0; if (j == w - 1) xs[nx++] = w + 1;
+                for (int a = 0; a < ny; ++a)
+                    for (int b = 0; b < nx; ++b) g += to_f(*dm.at(n, ys[a], xs[b], c));
+            }
+        }
+        float yi = ruler(i, h), xj = ruler(j, w);
+        float dy = yi - ky, dx = xj - kx;
+        float r = sqrtf(dy * dy + dx * dx + eps);
+        float mv = expf(-r / two_s2);
+        float t = g * mv / (two_s2 * r);
+        sy += t * dy;
+        sx += t * dx;
+    }
+    sy = block_sum(sy, scratch);
+    sx = block_sum(sx, scratch);
+    if (threadIdx.x == 0) { dk[pl * 2] = sy; dk[pl * 2 + 1] = sx; }
+}
+
+template <typename TP, typename TO>
+__global__ void __launch_bounds__(256)
+transport_fwd_k(View<TP> phi_s, View<TP> phi_t, const float* __restrict__ k_s, const float* __restrict__ k_t,
+                View<TO> out, int pad, float* mask_s, float* mask_t, int* argmax_t, int N, int h, int w, int C, int K,
+                float two_s2, float eps) {
+    const int PH = h + 2 * pad, PW = w + 2 * pad;
+    const long long total = (long long)N * PH * PW * C;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+         idx += (long long)gridDim.x * blockDim.x) {
+        int c = (int)(idx % C);
+        long long p = idx / C;
+        int px = (int)(p % PW);
+        long long r = p / PW;
+        int py = (int)(r % PH);
+        int n = (int)(r / PH);
+        int i = min(max(py - pad, 0), h - 1), j = min(max(px - pad, 0), w - 1);
+        float yi = ruler(i, h), xj = ruler(j, w);
+        float ms = -INFINITY, mt = -INFINITY;
+        int am = 0;
+        for (int q = 0; q < K; ++q) {
+            const float* ks_ = k_s + ((long long)n * K + q) * 2;
+            const float* kt_ = k_t + ((long long)n * K + q) * 2;
+            float a = gauss(yi, xj, ks_[0], ks_[1], two_s2, eps);
+            float b = gauss(yi, xj, kt_[0], kt_[1], two_s2, eps);
+            ms = fmaxf(ms, a);
+            if (b > mt) { mt = b; am = q; }          // first maximum wins, as torch.max(dim=1)
+        }
+        float ps = to_f(*phi_s.at(n, i, j, c)), pt = to_f(*phi_t.at(n, i, j, c));
+        from_f(out.at(n, py, px, c), ps * (1.f - ms) * (1.f - mt) + pt * mt);
+        if (c == 0 && py - pad == i && px - pad == j) {
+            long long e = ((long long)n * h + i) * w + j;
+            if (mask_s) mask_s[e] = ms;
+            if (mask_t) mask_t[e] = mt;
+            if (argmax_t) argmax_t[e] = am;
+        }
+    }
+}
+
+// one warp per pixel: dphi_t = dout * M_t ; dmask_t = sum_c dout (phi_t - phi_s (1 - M_s))
+template <typename TG, typename TP, typename TD>
+__global__ void __launch_bounds__(256)
+transport_bwd_k(View<TG> dout, int pad, View<TP> phi_s, View<TP> phi_t, const float* __restrict__ mask_s,
+                const float* __restrict__ mask_t, View<TD> dphi_t, float* dmask_t, int N, int h, int w, int C) {
+    const int lane = threadIdx.x & 31;
+    const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+    const long long P = (long long)N * h * w;
+    for (long long p = warp; p < P; p += nwarps) {
+        int j = (int)(p % w);
+        long long r = p / w;
+        int i = (int)(r % h);
+        int n = (int)(r / h);
+        float ms = mask_s[p], mt = mask_t[p];
+        int ys[3], xs[3], ny = 0, nx = 0;
+        if (pad) {
+            ys[ny++] = i + 1; if (i == 0) ys[ny++] = 0; if (i == h - 1) ys[ny++] = h + 1;
+            xs[nx++] = j + 1; if (j == 0) xs[nx++] = 0; if (j == w - 1) xs[nx++] = w + 1;
+        } else { ys[ny++] = i; xs[nx++] = j; }
+        float acc = 0.f;
+        for (int c = lane; c < C; c += 32) {
+            float g = 0.f;
+            for (int a = 0; a < ny; ++a)
+                for (int b = 0; b < nx; ++b) g += to_f(*dout.at(n, ys[a], xs[b], c));
+            float ps = to_f(*phi_s.at(n, i, j, c)), pt = to_f(*phi_t.at(n, i, j, c));
+            from_f(dphi_t.at(n, i, j, c), g * mt);
+            acc += g * (pt - ps * (1.f - ms));
+        }
+        acc = warp_sum(acc);
+        if (lane == 0) dmask_t[p] = acc;
+    }
+}
+
+__global__ void __launch_bounds__(256) l2_loss_k(const float* __restrict__ xhat, const float* __restrict__ target,
+                                                 const float* __restrict__ mask, long long numel, float gscale,
+                                                 double* loss_sum, float* dxhat) {
+    __shared__ float scratch[32];
+    float s = 0.f;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < numel;
+         i += (long long)gridDim.x * blockDim.x) {
+        float d = xhat[i] - target[i];
+        float mk = mask ? mask[i] : 1.f;
+        s += d * d * mk;
+        if (dxhat) dxhat[i] = 2.f * d * mk * gscale;
+    }
+    s = block_sum(s, scratch);
+    if (threadIdx.x == 0 && loss_sum) atomicAdd(loss_sum, (double)s);
+}
+
+static int grid_for(long long work, int block) {
+    long long g = (work + block - 1) / block;
+    long long cap = (long long)kp_sm_count() * 8;
+    if (g > cap) g = cap;
+    if (g < 1) g = 1;
+    return (int)g;
+}
+
+}  // namespace
+
+extern "C" int kp_spatial_softmax_fwd(kp_stream stream, const float* heat, int planes, int h, int w, float* k,
+                                      float* p_h, float* p_w) {
+    KP_CHECK_ARG(heat && k && planes > 0 && h > 0 && w > 0 && (h + w) * 4 <= 48 * 1024,
+                 "kp_spatial_softmax_fwd: bad arguments");
+    ssm_fwd_k<<<planes, 256, (h + w) * sizeof(float), (cudaStream_t)stream>>>(heat, h, w, k, p_h, p_w);
+    KP_LAUNCH_CHECK();
+    return KP_OK;
+}
+
+extern "C" int kp_spatial_softmax_bwd(kp_stream stream, const float* dk, const float* k, const float* p_h,
+                                      const float* p_w, int planes, int h, int w, float* dheat) {
+    KP_CHECK_ARG(dk && k && p_h && p_w && dheat && planes > 0 && h > 0 && w > 0 && (h + w) * 4 <= 48 * 1024,
+                 "kp_spatial_softmax_bwd: bad arguments");
+    ssm_bwd_k<<<planes, 256, (h + w) * sizeof(float), (cudaStream_t)stream>>>(dk, k, p_h, p_w, h, w, dheat);
+    KP_LAUNCH_CHECK();
+    return KP_OK;
+}
+
+extern "C" int kp_gaussian_fwd(kp_stream stream, const float* k, int planes, int h, int w, float sigma, float eps,
+                               float* m) {
+    KP_CHECK_ARG(k && m && planes > 0 && h > 0 && w > 0 && sigma > 0, "kp_gaussian_fwd: bad arguments");
+    gaussian_fwd_k<<<planes, 256, 0, (cudaStream_t)stream>>>(k, h, w, (float)(2.0 * (double)sigma * (double)sigma), eps, m);
+    KP_LAUNCH_CHECK();
+    return KP_OK;
+}
+
+extern "C" int kp_gaussian_bwd(kp_stream stream, const kp_view* dm, int pad, const float* k, const int32_t* argmax,
+                               int N, int K, int h, int w, float sigma, float eps, float* dk) {
+    KP_CHECK_ARG(dm && dm->ptr && k && dk && N > 0 && K > 0 && h > 0 && w > 0 && sigma > 0, "kp_gaussian_bwd: bad arguments");
+    const float two_s2 = (float)(2.0 * (double)sigma * (double)sigma);
+    return dispatch1(dm->dtype, [&](auto tg) -> int {
+        using TG = decltype(tg);
+        gaussian_bwd_k<TG><<<N * K, 256, 0, (cudaStream_t)stream>>>(make_view<TG>(dm), pad, k, argmax, K, h, w, two_s2,
+                                                                   eps, dk);
+        KP_LAUNCH_CHECK();
+        return KP_OK;
+    });
+}
+
+extern "C" int kp_transport_fwd(kp_stream stream, const kp_view* phi_s, const kp_view* phi_t, const float* k_s,
+                                const float* k_t, const kp_view* out, int pad, float* mask_s, float* mask_t,
+                                int32_t* argmax_t, int N, int h, int w, int C, int K, float sigma, float eps) {
+    KP_CHECK_ARG(phi_s && phi_t && out && phi_s->ptr && phi_t->ptr && out->ptr && k_s && k_t && N > 0 && h > 0 &&
+                     w > 0 && C > 0 && K > 0 && phi_s->dtype == phi_t->dtype,
+                 "kp_transport_fwd: bad arguments");
+    const float two_s2 = (float)(2.0 * (double)sigma * (double)sigma);
+    long long total = (long long)N * (h + 2 * pad) * (w + 2 * pad) * C;
+    int grid = grid_for(total, 256);
+    return dispatch1(phi_s->dtype, [&](auto tp) -> int {
+        return dispatch1(out->dtype, [&](auto to) -> int {
+            using TP = decltype(tp);
+            using TO = decltype(to);
+            transport_fwd_k<TP, TO><<<grid, 256, 0, (cudaStream_t)stream>>>(
+                make_view<TP>(phi_s), make_view<TP>(phi_t), k_s, k_t, make_view<TO>(out), pad, mask_s, mask_t, argmax_t,
+                N, h, w, C, K, two_s2, eps);
+            KP_LAUNCH_CHECK();
+            return KP_OK;
+        });
+    });
+}
+
+extern "C" int kp_transport_bwd(kp_stream stream, const kp_view* dout, int pad, const kp_view* phi_s,
+                                const kp_view* phi_t, const float* mask_s, const float* mask_t, const kp_view* dphi_t,
+                                float* dmask_t, int N, int h, int w, int C) {
+    KP_CHECK_ARG(dout && phi_s && phi_t && dphi_t && dout->ptr && phi_s->ptr && phi_t->ptr && dphi_t->ptr && mask_s &&
+                     mask_t && dmask_t && N > 0 && h > 0 && w > 0 && C > 0 && phi_s->dtype == phi_t->dtype,
+                 "kp_transport_bwd: bad arguments");
+    long long P = (long long)N * h * w;
+    int grid = grid_for(P * 32, 256);
+    return dispatch1(dout->dtype, [&](auto tg) -> int {
+        return dispatch1(phi_s->dtype, [&](auto tp) -> int {
+            return dispatch1(dphi_t->dtype, [&](auto td) -> int {
+                using TG = decltype(tg);
+                using TP = decltype(tp);
+                using TD = decltype(td);
+                transport_bwd_k<TG, TP, TD><<<grid, 256, 0, (cudaStream_t)stream>>>(
+                    make_view<TG>(dout), pad, make_view<TP>(phi_s), make_view<TP>(phi_t), mask_s, mask_t,
+                    make_view<TD>(dphi_t), dmask_t, N, h, w, C);
+                KP_LAUNCH_CHECK();
+                return KP_OK;
+            });
+        });
+    });
+}
+
+extern "C" int kp_l2_loss(kp_stream stream, const float* xhat, const float* target, const float* mask, int64_t numel,
+                          float gscale, double* loss_sum, float* dxhat) {
+    KP_CHECK_ARG(xhat && target && numel > 0, "kp_l2_loss: bad arguments");
+    l2_loss_k<<<grid_for(numel, 256 * 4), 256, 0, (cudaStream_t)stream>>>(xhat, target, mask, numel, gscale, loss_sum,
+                                                                         dxhat);
+    KP_LAUNCH_CHECK();
+    return KP_OK;
+}

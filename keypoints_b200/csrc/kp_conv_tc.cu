@@ -1,0 +1,525 @@
+// Convolutions on the Blackwell tensor cores: tcgen05.mma (kind::f16, bf16 x bf16 -> fp32 in TMEM),
+// operands staged by TMA with the 128-byte swizzle, mbarrier producer/consumer ring, warp-specialised
+// (warp 0 = TMA producer, warp 1 = TMEM owner + MMA issuer, warps 2-5 = epilogue).
+//
+// "Flat pixel" formulation.  Every activation lives in a replicate-padded NHWC buffer
+// [N][PH][PW][C] (PH = H+2, PW = W+2) which is also a 2-D matrix [Q = N*PH*PW pixels][C].  Because the
+// input and output share the row pitch PW, a 3x3 tap is a CONSTANT shift of the flat pixel index:
+//     out[q][co] = sum_t sum_ci in[q + shift_t][ci] * w[t][co][ci]
+// so the implicit-GEMM A tile of a tap is one plain 2-D TMA box (64 channels x 128 pixels) at row
+// q0 + shift_t, for any image width, and TMA's out-of-range zero fill covers both ends of the buffer.
+//   fprop : in = replicate-padded X, shift_t = ty*PW + tx, out = Y aligned top-left (rows with
+//           x >= W or y >= H are scratch and are masked out of the BatchNorm statistics).
+//   dgrad : in = dY stored interior-aligned with a ZERO border, shift_t' = (t'y-1)*PW + (t'x-1),
+//           weights flipped/transposed; every row of out = d(padded X) is valid.
+//   wgrad : dw[t][co][ci] = sum_q dY[q][co] * X[q + shift_t][ci]; both operands are "MN-major"
+//           (pixels = GEMM-K are the strided axis) which UMMA reads directly through MN-major
+//           shared-memory descriptors; split over pixel ranges, fp32 vector reductions into a
+//           staging gradient.
+#include "kp_common.cuh"
+#include <cuda.h>
+
+namespace {
+
+// ------------------------------------------------------------------------------------------------
+// PTX wrappers
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(bar), "r"(parity)
+            : "memory");
+    } while (!done);
+}
+__device__ __forceinline__ void fence_barrier_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* tm, int c0, int c1, uint32_t bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+        ::"r"(dst), "l"((uint64_t)tm), "r"(c0), "r"(c1), "r"(bar)
+        : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* tm) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)tm) : "memory");
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t smem_dst, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+        "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(pred));
+    return pred != 0;
+}
+__device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+// shared-memory matrix descriptor (sm_100 format, version 1), 128-byte swizzle
+//   K-major : rows of 128 B (64 bf16 of K), 8-row groups every SBO = 1024 B; LBO unused (1)
+//   MN-major: rows of 128 B (64 bf16 of M/N) per k, 8-k groups every SBO = 1024 B, next 64 M/N every LBO
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+    d |= (uint64_t)1 << 46;   // descriptor version (Blackwell)
+    d |= (uint64_t)2 << 61;   // SWIZZLE_128B
+    return d;
+}
+// instruction descriptor: D=f32, A=B=bf16, M=128
+__host__ __device__ constexpr uint32_t make_idesc(int n, int a_mn_major, int b_mn_major) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
+           ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+}
+
+constexpr int STAGE_A_BYTES = 128 * 128;   // 128 rows x 64 bf16
+
+struct ConvTcParams {
+    long long Q;
+    int Cin, Cout, taps;
+    int shift[9];
+    const float* bias;
+    bf16* out;
+    double* stats;
+    int PH, PW, VH, VW;
+};
+
+// ------------------------------------------------------------------------------------------------
+// fprop / dgrad: D[128 pixels][BN channels] = sum over (tap, 64-channel chunk) A[pix][ci] * B[co][ci]
+// ------------------------------------------------------------------------------------------------
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(192, 1)
+conv_tc_k(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const ConvTcParams p) {
+    constexpr int STAGE_B_BYTES = BN * 128;
+    constexpr int STAGE_BYTES = STAGE_A_BYTES + STAGE_B_BYTES;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* gen_base = smem_raw + (base - smem_u32(smem_raw));
+    const uint32_t bars = base + STAGES * STAGE_BYTES;          // full[S], empty[S], tmem_full
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gen_base + STAGES * STAGE_BYTES + 8 * (2 * STAGES + 1));
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long q0 = (long long)blockIdx.x * 128;
+    const int n0 = blockIdx.y * BN;
+    const int kchunks = p.Cin / 64;
+    const int num_kb = p.taps * kchunks;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmA);
+        tma_prefetch_desc(&tmB);
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(bars + 8 * s, 1);
+            mbar_init(bars + 8 * (STAGES + s), 1);
+        }
+        mbar_init(bars + 8 * (2 * STAGES), 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(smem_u32(tmem_slot), BN);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (elect_one()) {
+            for (int kb = 0; kb < num_kb; ++kb) {
+                const int s = kb % STAGES, ph = (kb / STAGES) & 1;
+                mbar_wait(bars + 8 * (STAGES + s), ph ^ 1);
+                const uint32_t full = bars + 8 * s;
+                mbar_expect_tx(full, STAGE_BYTES);
+                const int tap = kb / kchunks, kc = kb - tap * kchunks;
+                const uint32_t sa = base + s * STAGE_BYTES;
+                tma_load_2d(sa, &tmA, kc * 64, (int)(q0 + p.shift[tap]), full);
+                tma_load_2d(sa + STAGE_A_BYTES, &tmB, kc * 64, tap * p.Cout + n0, full);
+            }
+        }
+    } else if (warp == 1) {
+        if (elect_one()) {
+            constexpr uint32_t idesc = make_idesc(BN, 0, 0);
+            for (int kb = 0; kb < num_kb; ++kb) {
+                const int s = kb % STAGES, ph = (kb / STAGES) & 1;
+                mbar_wait(bars + 8 * s, ph);
+                tc_fence_after();
+                const uint32_t sa = base + s * STAGE_BYTES;
+                const uint64_t ad = make_desc(sa, 16, 1024), bd = make_desc(sa + STAGE_A_BYTES, 16, 1024);
+#pragma unroll
+                for (int k = 0; k < 4; ++k)       // UMMA_K = 16 bf16 = 32 bytes inside the 128-byte swizzled row
+                    umma_bf16(tmem_base, ad + 2 * k, bd + 2 * k, idesc, (kb | k) ? 1u : 0u);
+                umma_commit(bars + 8 * (STAGES + s));
+            }
+            umma_commit(bars + 8 * (2 * STAGES));
+        }
+    } else {
+        // epilogue: TMEM lane group of this warp = warp % 4
+        const int wq = warp & 3;
+        const int row = wq * 32 + lane;
+        const long long q = q0 + row;
+        bool valid = q < p.Q;
+        if (valid && p.stats) {
+            int x = (int)(q % p.PW);
+            int y = (int)((q / p.PW) % p.PH);
+            valid = x < p.VW && y < p.VH;
+        }
+        float* tile = reinterpret_cast<float*>(gen_base) + wq * (32 * 33);              // reuse pipeline smem
+        float* part = reinterpret_cast<float*>(gen_base) + 4 * 32 * 33 + wq * (2 * BN);  // per-warp column sums
+        mbar_wait(bars + 8 * (2 * STAGES), 0);
+        tc_fence_after();
+#pragma unroll 1
+        for (int c = 0; c < BN / 32; ++c) {
+            uint32_t r[32];
+            tmem_ld32(tmem_base + ((uint32_t)(wq * 32) << 16) + c * 32, r);
+            float v[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) + (p.bias ? p.bias[n0 + c * 32 + j] : 0.f);
+            if (q < p.Q) {
+                uint4* dst = reinterpret_cast<uint4*>(p.out + q * p.Cout + n0 + c * 32);
+#pragma unroll
+                for (int g = 0; g < 4; ++g) {
+                    uint4 u;
+                    __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) h[e] = __floats2bfloat162_rn(v[g * 8 + 2 * e], v[g * 8 + 2 * e + 1]);
+                    dst[g] = u;
+                }
+            }
+            if (p.stats) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) tile[lane * 33 + j] = valid ? v[j] : 0.f;
+                __syncwarp();
+                float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+                for (int rr = 0; rr < 32; ++rr) {
+                    float t = tile[rr * 33 + lane];
+                    s1 += t;
+                    s2 = fmaf(t, t, s2);
+                }
+                part[c * 32 + lane] = s1;
+                part[BN + c * 32 + lane] = s2;
+                __syncwarp();
+            }
+        }
+        if (p.stats) {
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            const float* pp = reinterpret_cast<float*>(gen_base) + 4 * 32 * 33;
+            for (int ch = (warp - 2) * 32 + lane; ch < BN; ch += 128) {
+                float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+                for (int w = 0; w < 4; ++w) { s1 += pp[w * 2 * BN + ch]; s2 += pp[w * 2 * BN + BN + ch]; }
+                atomicAdd(&p.stats[n0 + ch], (double)s1);
+                atomicAdd(&p.stats[p.Cout + n0 + ch], (double)s2);
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        __syncwarp();
+        tmem_dealloc(tmem_base, BN);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// wgrad: D[128 (M channels)][BN (N channels)] = sum over pixels A[pix][m] * B[pix + shift][n], MN-major
+// ------------------------------------------------------------------------------------------------
+struct WgradTcParams {
+    long long Q;            // flat pixels
+    long long kchunk;       // pixels per split (multiple of 64)
+    int splits;
+    int shiftA[9], shiftB[9];
+    int Mtot, Ntot;         // staging is [taps][Mtot][Ntot] fp32
+    float* stg;
+};
+
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(192, 1)
+wgrad_tc_k(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const WgradTcParams p) {
+    constexpr int BOX_BYTES = 64 * 128;            // 64 pixels x 64 channels bf16
+    constexpr int A_BYTES = 2 * BOX_BYTES;         // M = 128 channels
+    constexpr int B_BYTES = (BN / 64) * BOX_BYTES;
+    constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* gen_base = smem_raw + (base - smem_u32(smem_raw));
+    const uint32_t bars = base + STAGES * STAGE_BYTES;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gen_base + STAGES * STAGE_BYTES + 8 * (2 * STAGES + 1));
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int m0 = blockIdx.x * 128, n0 = blockIdx.y * BN;
+    const int tap = blockIdx.z / p.splits, split = blockIdx.z % p.splits;
+    const long long qbeg = (long long)split * p.kchunk;
+    long long qend = qbeg + p.kchunk;
+    if (qend > p.Q) qend = p.Q;
+    const int num_kb = qend > qbeg ? (int)((qend - qbeg + 63) / 64) : 0;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmA);
+        tma_prefetch_desc(&tmB);
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(bars + 8 * s, 1);
+            mbar_init(bars + 8 * (STAGES + s), 1);
+        }
+        mbar_init(bars + 8 * (2 * STAGES), 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(smem_u32(tmem_slot), BN);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (num_kb > 0) {
+        if (warp == 0) {
+            if (elect_one()) {
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    const int s = kb % STAGES, ph = (kb / STAGES) & 1;
+                    mbar_wait(bars + 8 * (STAGES + s), ph ^ 1);
+                    const uint32_t full = bars + 8 * s;
+                    mbar_expect_tx(full, STAGE_BYTES);
+                    const long long q = qbeg + (long long)kb * 64;
+                    const uint32_t sa = base + s * STAGE_BYTES;
+                    // NOTE: the last block of a split may run past qend into the next split's pixels; that
+                    // would double count, so splits are sized in whole 64-pixel blocks (kchunk % 64 == 0)
+                    // and only the global tail (>= Q, zero-filled by TMA) is ever partial.
+#pragma unroll
+                    for (int b = 0; b < 2; ++b)
+                        tma_load_2d(sa + b * BOX_BYTES, &tmA, m0 + b * 64, (int)(q + p.shiftA[tap]), full);
+#pragma unroll
+                    for (int b = 0; b < BN / 64; ++b)
+                        tma_load_2d(sa + A_BYTES + b * BOX_BYTES, &tmB, n0 + b * 64, (int)(q + p.shiftB[tap]), full);
+                }
+            }
+        } else if (warp == 1) {
+            if (elect_one()) {
+                constexpr uint32_t idesc = make_idesc(BN, 1, 1);
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    const int s = kb % STAGES, ph = (kb / STAGES) & 1;
+                    mbar_wait(bars + 8 * s, ph);
+                    tc_fence_after();
+                    const uint32_t sa = base + s * STAGE_BYTES;
+                    const uint64_t ad = make_desc(sa, BOX_BYTES, 1024), bd = make_desc(sa + A_BYTES, BOX_BYTES, 1024);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)   // UMMA_K = 16 pixels = two 8-row groups = 2048 bytes
+                        umma_bf16(tmem_base, ad + 128 * k, bd + 128 * k, idesc, (kb | k) ? 1u : 0u);
+                    umma_commit(bars + 8 * (STAGES + s));
+                }
+                umma_commit(bars + 8 * (2 * STAGES));
+            }
+        } else {
+            const int wq = warp & 3;
+            const int row = wq * 32 + lane;
+            mbar_wait(bars + 8 * (2 * STAGES), 0);
+            tc_fence_after();
+            float* dst_row = p.stg + ((long long)tap * p.Mtot + m0 + row) * p.Ntot + n0;
+#pragma unroll 1
+            for (int c = 0; c < BN / 32; ++c) {
+                uint32_t r[32];
+                tmem_ld32(tmem_base + ((uint32_t)(wq * 32) << 16) + c * 32, r);
+#pragma unroll
+                for (int g = 0; g < 8; ++g)
+                    red_add_v4(dst_row + c * 32 + g * 4, __uint_as_float(r[4 * g]), __uint_as_float(r[4 * g + 1]),
+                               __uint_as_float(r[4 * g + 2]), __uint_as_float(r[4 * g + 3]));
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        __syncwarp();
+        tmem_dealloc(tmem_base, BN);
+    }
+}
+
+// staging [t][a][b] -> dw_oihw[co][ci][t] (+=), a/b = (co,ci) or (ci,co)
+__global__ void wgrad_finalize_k(const float* __restrict__ stg, float* __restrict__ dw, int taps, int Cout, int Cin,
+                                 int CinStg, int m_is_cout) {
+    const long long total = (long long)Cout * Cin * taps;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        int t = (int)(i % taps);
+        long long r = i / taps;
+        int ci = (int)(r % Cin);
+        int co = (int)(r / Cin);
+        float v = m_is_cout ? stg[((long long)t * Cout + co) * CinStg + ci] : stg[((long long)t * CinStg + ci) * Cout + co];
+        dw[i] += v;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+    static EncodeTiledFn fn = nullptr;
+    if (fn) return fn;
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) != cudaSuccess ||
+        qres != cudaDriverEntryPointSuccess)
+        return nullptr;
+    fn = (EncodeTiledFn)ptr;
+    return fn;
+}
+
+// 2-D bf16 matrix [rows][cols] (cols contiguous), box = 64 cols x box_rows, 128-byte swizzle
+static int make_map(CUtensorMap* tm, const void* ptr, long long rows, long long cols, int box_rows) {
+    EncodeTiledFn enc = get_encode();
+    if (!enc) { kp_set_error("cuTensorMapEncodeTiled entry point not available"); return KP_ERR_CUDA; }
+    cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)cols * 2};
+    cuuint32_t box[2] = {64, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { kp_set_error("cuTensorMapEncodeTiled failed: %d (rows=%lld cols=%lld box=%d)", (int)r, rows, cols, box_rows); return KP_ERR_CUDA; }
+    return KP_OK;
+}
+
+template <int BN, int STAGES>
+static int launch_conv(cudaStream_t st, const CUtensorMap& a, const CUtensorMap& b, const ConvTcParams& p) {
+    constexpr int smem = STAGES * (STAGE_A_BYTES + BN * 128) + 8 * (2 * STAGES + 1) + 16 + 1024;
+    static bool attr_done = false;
+    if (!attr_done) {
+        KP_CUDA(cudaFuncSetAttribute(conv_tc_k<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        attr_done = true;
+    }
+    dim3 grid((unsigned)((p.Q + 127) / 128), (unsigned)(p.Cout / BN), 1);
+    conv_tc_k<BN, STAGES><<<grid, 192, smem, st>>>(a, b, p);
+    KP_LAUNCH_CHECK();
+    return KP_OK;
+}
+
+template <int BN, int STAGES>
+static int launch_wgrad(cudaStream_t st, const CUtensorMap& a, const CUtensorMap& b, const WgradTcParams& p, int taps) {
+    constexpr int smem = STAGES * (2 * 8192 + (BN / 64) * 8192) + 8 * (2 * STAGES + 1) + 16 + 1024;
+    static bool attr_done = false;
+    if (!attr_done) {
+        KP_CUDA(cudaFuncSetAttribute(wgrad_tc_k<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        attr_done = true;
+    }
+    dim3 grid((unsigned)(p.Mtot / 128), (unsigned)(p.Ntot / BN), (unsigned)(taps * p.splits));
+    wgrad_tc_k<BN, STAGES><<<grid, 192, smem, st>>>(a, b, p);
+    KP_LAUNCH_CHECK();
+    return KP_OK;
+}
+
+}  // namespace
+
+// in: bf16 [Q][Cin]; wt: bf16 [taps][Cout][Cin]; out: bf16 [Q][Cout]; shifts: host int[taps];
+// stats masked to rows with (q % PW) < VW && (q / PW % PH) < VH.
+extern "C" int kp_conv_tc(kp_stream stream, const void* in_bf16, int64_t Q, int Cin, const void* wt_bf16, int taps,
+                          const int32_t* shifts, const float* bias, void* out_bf16, int Cout, double* stats, int PH,
+                          int PW, int VH, int VW) {
+    KP_CHECK_ARG(in_bf16 && wt_bf16 && out_bf16 && shifts && Q > 0 && Q < (1LL << 31) - 4096 && taps >= 1 && taps <= 9 &&
+                     Cin % 64 == 0 && Cout % 64 == 0 && Cin > 0 && Cout > 0,
+                 "kp_conv_tc: unsupported shape Q=%lld Cin=%d Cout=%d taps=%d", (long long)Q, Cin, Cout, taps);
+    KP_CHECK_ARG(!stats || (PH > 0 && PW > 0), "kp_conv_tc: stats need PH/PW");
+    const int BN = (Cout % 256 == 0) ? 256 : (Cout % 128 == 0 ? 128 : 64);
+    CUtensorMap ta, tb;
+    int rc = make_map(&ta, in_bf16, Q, Cin, 128);
+    if (rc) return rc;
+    rc = make_map(&tb, wt_bf16, (long long)taps * Cout, Cin, BN);
+    if (rc) return rc;
+    ConvTcParams p;
+    p.Q = Q; p.Cin = Cin; p.Cout = Cout; p.taps = taps;
+    for (int i = 0; i < 9; ++i) p.shift[i] = i < taps ? shifts[i] : 0;
+    p.bias = bias; p.out = (bf16*)out_bf16; p.stats = stats; p.PH = PH; p.PW = PW; p.VH = VH; p.VW = VW;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (BN == 256) return launch_conv<256, 4>(st, ta, tb, p);
+    if (BN == 128) return launch_conv<128, 4>(st, ta, tb, p);
+    return launch_conv<64, 4>(st, ta, tb, p);
+}
+
+// dw_oihw[co][ci][t] += sum_q dy[q][co] * x[q + shifts[t]][ci];  x: bf16 [Q][CinP] (CinP >= Cin, extra
+// channels ignored), dy: bf16 [Q][Cout] with zero rows wherever the product must not count.
+// stg: fp32 workspace of taps*Cout*CinP floats (zeroed here).
+extern "C" int kp_conv_wgrad_tc(kp_stream stream, const void* x_bf16, const void* dy_bf16, int64_t Q, int Cin, int CinP,
+                                int Cout, int taps, const int32_t* shifts, float* stg, float* dw_oihw) {
+    KP_CHECK_ARG(x_bf16 && dy_bf16 && stg && dw_oihw && shifts && Q > 0 && Q < (1LL << 31) - 4096 && taps >= 1 &&
+                     taps <= 9 && CinP % 64 == 0 && Cout % 64 == 0 && Cin <= CinP && (Cout % 128 == 0 || CinP % 128 == 0),
+                 "kp_conv_wgrad_tc: unsupported shape Q=%lld Cin=%d/%d Cout=%d taps=%d", (long long)Q, Cin, CinP, Cout, taps);
+    cudaStream_t st = (cudaStream_t)stream;
+    const bool m_is_cout = (Cout % 128 == 0);
+    const int Mtot = m_is_cout ? Cout : CinP, Ntot = m_is_cout ? CinP : Cout;
+    const int BN = (Ntot % 256 == 0) ? 256 : (Ntot % 128 == 0 ? 128 : 64);
+    CUtensorMap ta, tb;
+    int rc = make_map(&ta, m_is_cout ? dy_bf16 : x_bf16, Q, Mtot, 64);
+    if (rc) return rc;
+    rc = make_map(&tb, m_is_cout ? x_bf16 : dy_bf16, Q, Ntot, 64);
+    if (rc) return rc;
+    WgradTcParams p;
+    p.Q = Q; p.Mtot = Mtot; p.Ntot = Ntot; p.stg = stg;
+    for (int i = 0; i < 9; ++i) {
+        int s = i < taps ? shifts[i] : 0;
+        p.shiftA[i] = m_is_cout ? 0 : s;
+        p.shiftB[i] = m_is_cout ? s : 0;
+    }
+    const int tiles = (Mtot / 128) * (Ntot / BN) * taps;
+    long long blocks64 = (Q + 63) / 64;
+    long long splits = (2LL * kp_sm_count() + tiles - 1) / tiles;
+    if (splits > blocks64 / 8) splits = blocks64 / 8;
+    if (splits < 1) splits = 1;
+    long long per = (blocks64 + splits - 1) / splits;
+    splits = (blocks64 + per - 1) / per;
+    p.kchunk = per * 64;
+    p.splits = (int)splits;
+    KP_CUDA(cudaMemsetAsync(stg, 0, sizeof(float) * (size_t)taps * Mtot * Ntot, st));
+    if (BN == 256) rc = launch_wgrad<256, 4>(st, ta, tb, p, taps);
+    else if (BN == 128) rc = launch_wgrad<128, 4>(st, ta, tb, p, taps);
+    else rc = launch_wgrad<64, 4>(st, ta, tb, p, taps);
+    if (rc) return rc;
+    long long total = (long long)Cout * Cin * taps;
+    int blocks = (int)((total + 255) / 256);
+    if (blocks > kp_sm_count() * 8) blocks = kp_sm_count() * 8;
+    wgrad_finalize_k<<<blocks, 256, 0, st>>>(stg, dw_oihw, taps, Cout, Cin, CinP, m_is_cout ? 1 : 0);
+    KP_LAUNCH_CHECK();
+    return KP_OK;
+}

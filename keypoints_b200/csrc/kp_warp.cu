@@ -1,0 +1,109 @@
+// TPS + rotate augmentation (tps.py:10-87,128-131,154-166): the sampling grid is evaluated per output
+// pixel in registers and consumed immediately by the bilinear sampler — no (N,H,W,2) grid in HBM.
+#include "kp_common.cuh"
+
+namespace {
+
+constexpr int MAX_T = 32;
+
+// F.grid_sample(mode='bilinear', padding_mode='zeros', align_corners=False) for one (n, gx, gy)
+__device__ __forceinline__ void sample_all_channels(const float* __restrict__ x, float* __restrict__ out, int n, int C,
+                                                    int H, int W, int i, int j, float gx, float gy) {
+    float ix = ((gx + 1.f) * W - 1.f) * 0.5f;
+    float iy = ((gy + 1.f) * H - 1.f) * 0.5f;
+    float fx = floorf(ix), fy = floorf(iy);
+    int x0 = (int)fx, y0 = (int)fy, x1 = x0 + 1, y1 = y0 + 1;
+    float wx1 = ix - fx, wx0 = 1.f - wx1, wy1 = iy - fy, wy0 = 1.f - wy1;
+    bool vx0 = x0 >= 0 && x0 < W, vx1 = x1 >= 0 && x1 < W, vy0 = y0 >= 0 && y0 < H, vy1 = y1 >= 0 && y1 < H;
+    for (int c = 0; c < C; ++c) {
+        const float* pl = x + ((long long)n * C + c) * H * W;
+        float v = 0.f;
+        if (vy0 && vx0) v += pl[(long long)y0 * W + x0] * wx0 * wy0;
+        if (vy0 && vx1) v += pl[(long long)y0 * W + x1] * wx1 * wy0;
+        if (vy1 && vx0) v += pl[(long long)y1 * W + x0] * wx0 * wy1;
+        if (vy1 && vx1) v += pl[(long long)y1 * W + x1] * wx1 * wy1;
+        out[(((long long)n * C + c) * H + i) * W + j] = v;
+    }
+}
+
+__global__ void __launch_bounds__(256) tps_warp_k(const float* __restrict__ x, float* __restrict__ out,
+                                                  const float* __restrict__ theta, const float* __restrict__ ctrl,
+                                                  int N, int C, int H, int W, int T, int reduced) {
+    const long long total = (long long)N * H * W;
+    const int rows = reduced ? T + 2 : T + 3;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+         idx += (long long)gridDim.x * blockDim.x) {
+        int j = (int)(idx % W);
+        long long r = idx / W;
+        int i = (int)(r % H);
+        int n = (int)(r / H);
+        const float* th = theta + (long long)n * rows * 2;
+        const float* ct = ctrl + (long long)n * T * 2;
+        float px = W > 1 ? (float)j / (float)(W - 1) : 0.f;
+        float py = H > 1 ? (float)i / (float)(H - 1) : 0.f;
+        const int nw = reduced ? T - 1 : T;           // stored spline weights
+        const float* a = th + nw * 2;                 // affine part: a0, a1, a2
+        float zx = 0.f, zy = 0.f, w0x = 0.f, w0y = 0.f;
+        if (reduced)
+            for (int t = 0; t < nw; ++t) { w0x -= th[t * 2]; w0y -= th[t * 2 + 1]; }
+        for (int t = 0; t < T; ++t) {
+            float dx = px - ct[t * 2], dy = py - ct[t * 2 + 1];
+            float d = sqrtf(dx * dx + dy * dy);
+            float u = d * d * logf(d + 1e-6f);
+            float wx, wy;
+            if (reduced) { wx = t == 0 ? w0x : th[(t - 1) * 2]; wy = t == 0 ? w0y : th[(t - 1) * 2 + 1]; }
+            else { wx = th[t * 2]; wy = th[t * 2 + 1]; }
+            zx = fmaf(u, wx, zx);
+            zy = fmaf(u, wy, zy);
+        }
+        float lx = a[0] + px * a[2] + py * a[4];
+        float ly = a[1] + px * a[3] + py * a[5];
+        float gx = (px + (lx + zx)) * 2.f - 1.f;
+        float gy = (py + (ly + zy)) * 2.f - 1.f;
+        sample_all_channels(x, out, n, C, H, W, i, j, gx, gy);
+    }
+}
+
+__global__ void __launch_bounds__(256) rotate_warp_k(const float* __restrict__ x, float* __restrict__ out,
+                                                     const float* __restrict__ rot, int N, int C, int H, int W) {
+    const long long total = (long long)N * H * W;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+         idx += (long long)gridDim.x * blockDim.x) {
+        int j = (int)(idx % W);
+        long long r = idx / W;
+        int i = (int)(r % H);
+        int n = (int)(r / H);
+        float c = cosf(rot[n]), s = sinf(rot[n]);
+        float bx = (2.f * j + 1.f) / W - 1.f;          // F.affine_grid base grid, align_corners=False
+        float by = (2.f * i + 1.f) / H - 1.f;
+        float gx = c * bx + s * by;
+        float gy = -s * bx + c * by;
+        sample_all_channels(x, out, n, C, H, W, i, j, gx, gy);
+    }
+}
+
+}  // namespace
+
+extern "C" int kp_tps_warp(kp_stream stream, const float* x, float* out, const float* theta, const float* ctrl, int N,
+                           int C, int H, int W, int T, int reduced) {
+    KP_CHECK_ARG(x && out && theta && ctrl && x != out && N > 0 && C > 0 && H > 0 && W > 0 && T > 0 && T <= MAX_T &&
+                     (!reduced || T >= 2),
+                 "kp_tps_warp: bad arguments");
+    long long total = (long long)N * H * W;
+    long long g = (total + 255) / 256;
+    if (g > (long long)kp_sm_count() * 16) g = (long long)kp_sm_count() * 16;
+    tps_warp_k<<<(int)g, 256, 0, (cudaStream_t)stream>>>(x, out, theta, ctrl, N, C, H, W, T, reduced);
+    KP_LAUNCH_CHECK();
+    return KP_OK;
+}
+
+extern "C" int kp_rotate_warp(kp_stream stream, const float* x, float* out, const float* rot, int N, int C, int H,
+                              int W) {
+    KP_CHECK_ARG(x && out && rot && x != out && N > 0 && C > 0 && H > 0 && W > 0, "kp_rotate_warp: bad arguments");
+    long long total = (long long)N * H * W;
+    long long g = (total + 255) / 256;
+    if (g > (long long)kp_sm_count() * 16) g = (long long)kp_sm_count() * 16;
+    rotate_warp_k<<<(int)g, 256, 0, (cudaStream_t)stream>>>(x, out, rot, N, C, H, W);
+    KP_LAUNCH_CHECK();
+    return KP_OK;
+}

@@ -1,0 +1,359 @@
+"""Fused training step for KeyNet / TransporterNet (reference inner loops: keypoints.py:70-84,
+transporter.py:75-89): augment -> forward -> L2 loss -> backward -> gradient all-reduce -> Adam, run as
+one chain of C-ABI kernel launches on static NHWC buffers and replayed as a CUDA graph.
+
+Data parallel: one process per GPU; each rank trains on its own shard of the batch with
+local BatchNorm statistics; the only exchange is a sum all-reduce of the flat fp32 gradient bucket
+(ordered decoder | keypoint | encoder so the first bucket is ready first), then Adam with 1/world scaling.
+"""
+from __future__ import annotations
+
+import math
+from typing import Optional
+
+import torch
+
+from . import engine, lib as L
+from .engine import CachedAlloc, LayerGrads, LayerParams
+from .models import knn
+from .models.keynet import KeyNet
+from .models.transporter import TransporterNet
+
+
+class _UnitState:
+    """Specs, parameter / gradient views into the flat buckets and static buffers of one Unit."""
+
+    def __init__(self, name, unit: knn.Unit):
+        self.name = name
+        self.unit = unit
+        self.specs, self.mods = unit.layers()
+        self.alloc = CachedAlloc(name)
+        self.params = None
+        self.grads = None
+        self.packs = None
+        self.ctxs = None
+        self.span = (0, 0)
+
+    def tensors(self):
+        return knn.trainable(self.mods)
+
+
+class Trainer:
+    def __init__(self, net, precision: str = 'bf16', lr: float = 1e-4, betas=(0.9, 0.999), eps: float = 1e-8,
+                 augment: Optional[dict] = None, use_graph: bool = True, process_group=None, device=None):
+        if not torch.cuda.is_available():
+            raise RuntimeError('keypoints_b200.Trainer needs a CUDA (sm_100a) device; there is no CPU path')
+        self.device = torch.device(device if device is not None else f'cuda:{torch.cuda.current_device()}')
+        L.device_info()                       # fails loudly on a non-sm_100 device
+        self.net = net.to(self.device)
+        self.kind = 'keynet' if isinstance(net, KeyNet) else 'transporter'
+        if self.kind == 'transporter' and not isinstance(net, TransporterNet):
+            raise TypeError('Trainer supports KeyNet and TransporterNet')
+        if self.kind == 'transporter' and net.combine_method != 'max':
+            raise NotImplementedError("only combine_method='max' is implemented")
+        self.precision = precision
+        self.T = engine.act_dtype(precision)
+        self.lr, self.betas, self.eps = lr, betas, eps
+        self.sigma = float(getattr(net.key2map, 'sigma', 0.1))
+        self.augment = augment               # dict(cntl_pts=4, variance=0.05, max_rotate=0.1) or None
+        self.use_graph = use_graph
+        self.pg = process_group
+        self.world = 1
+        if process_group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()):
+            self.world = torch.distributed.get_world_size(process_group)
+        first = net.encoder if self.kind == 'keynet' else net.feature
+        # bucket order = order in which backward finishes units
+        self.units = {'decoder': _UnitState('decoder', net.decoder), 'keypoint': _UnitState('keypoint', net.keypoint),
+                      'encoder': _UnitState('encoder', first)}
+        self._flatten()
+        self.misc = CachedAlloc('misc')
+        self.graph = None
+        self.graph_key = None
+        self.steps_done = 0
+        self.step_dev = torch.zeros(1, dtype=torch.int32, device=self.device)
+        self.loss_sum = torch.zeros(1, dtype=torch.float64, device=self.device)
+        self.numel = 1
+
+    # ------------------------------------------------------------------------------------------
+    def _flatten(self):
+        tensors = []
+        for u in self.units.values():
+            start = sum(t.numel() for t in tensors)
+            tensors += u.tensors()
+            u.span = (start, sum(t.numel() for t in tensors))
+        n = sum(t.numel() for t in tensors)
+        self.flat_p = torch.empty(n, dtype=torch.float32, device=self.device)
+        self.flat_g = torch.zeros(n, dtype=torch.float32, device=self.device)
+        self.flat_m = torch.zeros(n, dtype=torch.float32, device=self.device)
+        self.flat_v = torch.zeros(n, dtype=torch.float32, device=self.device)
+        off = 0
+        gviews = {}
+        for t in tensors:
+            k = t.numel()
+            self.flat_p[off:off + k].copy_(t.data.reshape(-1))
+            t.data = self.flat_p[off:off + k].view_as(t)          # the module now aliases the flat bucket
+            gviews[id(t)] = self.flat_g[off:off + k].view_as(t)
+            off += k
+        for u in self.units.values():
+            u.params = knn.layer_params(u.mods)
+            u.grads = []
+            for conv, bn in u.mods:
+                g = LayerGrads(dw=gviews[id(conv.weight)], db=None if conv.bias is None else gviews[id(conv.bias)])
+                if bn is not None:
+                    g.dgamma, g.dbeta = gviews[id(bn.weight)], gviews[id(bn.bias)]
+                u.grads.append(g)
+        self.n_params = n
+
+    # ------------------------------------------------------------------------------------------
+    def _pack(self, shapes):
+        for u in self.units.values():
+            u.packs = [engine.pack_layer(s, p, cp, self.precision, u.alloc, f'pk{i}')
+                       for i, (s, p, cp) in enumerate(zip(u.specs, u.params, shapes[u.name]))]
+
+    def _pitches(self, u: _UnitState, cin_pitch):
+        out, cp = [], cin_pitch
+        for s in u.specs:
+            out.append(cp)
+            cp = engine.pitch(s.cout, self.precision)
+        return out
+
+    def _fwd_unit(self, u: _UnitState, x_pad, H, W, out, out_pad):
+        u.ctxs = engine.unit_forward(u.specs, u.params, x_pad, H, W, self.precision, out, out_pad, alloc=u.alloc,
+                                     training=True, packs=u.packs, tag='f')
+
+    def _bwd_unit(self, u: _UnitState, dout, dout_pad, need_dx):
+        return engine.unit_backward(u.specs, u.params, u.grads, u.ctxs, dout, dout_pad, self.precision, need_dx,
+                                    alloc=u.alloc, tag='b')
+
+    def _bottleneck_dims(self, H, W):
+        h, w = H, W
+        for s in self.units['encoder'].specs:
+            h, w = engine.post_dims(s.post, h, w)
+        return h, w
+
+    # ------------------------------------------------------------------------------------------
+    def _augment(self, x):
+        """TpsAndRotate (data_augments.py:27-38) with parameters drawn on the device."""
+        a = self.augment
+        n, c, H, W = x.shape
+        dev = x.device
+        T = int(a.get('cntl_pts', 4))
+        st = L.stream()
+
+        def draw():
+            theta = torch.randn(n, T + 3, 2, device=dev) * float(a.get('variance', 0.05))
+            ctrl = torch.rand(n, T, 2, device=dev)
+            rot = (torch.rand(n, device=dev) * 2 - 1) * float(a.get('max_rotate', 0.1))
+            return theta, ctrl, rot
+
+        def perturb(src, dst, tmp, prm):
+            theta, ctrl, rot = prm
+            L.call('kp_tps_warp', st, L.ptr(src), L.ptr(tmp), L.ptr(theta), L.ptr(ctrl), n, c, H, W, T, 0)
+            L.call('kp_rotate_warp', st, L.ptr(tmp), L.ptr(dst), L.ptr(rot), n, c, H, W)
+
+        mk = lambda name: self.misc(name, (n, c, H, W), torch.float32, dev)
+        tmp, x1, x2, m1, m2, ones = mk('aug.tmp'), mk('aug.x1'), mk('aug.x2'), mk('aug.m1'), mk('aug.m2'), mk('aug.ones')
+        ones.fill_(1.0)
+        p1, p2 = draw(), draw()
+        perturb(x, x1, tmp, p1)
+        perturb(ones, m1, tmp, p1)
+        perturb(x1, x2, tmp, p2)
+        perturb(m1, m2, tmp, p2)
+        return x1, x2, m2
+
+    # ------------------------------------------------------------------------------------------
+    def _forward_backward(self, xa, xb, mask):
+        """xa: source / first image, xb: target (the loss compares the reconstruction with xb)."""
+        n, c, H, W = xa.shape
+        dev = self.device
+        st = L.stream()
+        enc, kp, dec = self.units['encoder'], self.units['keypoint'], self.units['decoder']
+        h, w = self._bottleneck_dims(H, W)
+        C = enc.specs[-1].cout
+        K = kp.specs[-1].cout
+        f32 = torch.float32
+        prec = self.precision
+        cin_p = engine.pitch(c, prec)
+        dec_cin = dec.specs[0].cin
+        dec_cp = engine.pitch(dec_cin, prec)
+        self._pack({'encoder': self._pitches(enc, cin_p), 'keypoint': self._pitches(kp, cin_p),
+                    'decoder': self._pitches(dec, dec_cp)})
+        dec_in = self.misc('dec_in', (n, h + 2, w + 2, dec_cp), self.T, dev, zero=True)
+        heat = self.misc('heat', (n, K, h, w), f32, dev)
+        k_t = self.misc('k_t', (n, K, 2), f32, dev)
+        p_h = self.misc('p_h', (n, K, h), f32, dev)
+        p_w = self.misc('p_w', (n, K, w), f32, dev)
+        xhat = self.misc('xhat', (n, c, H, W), f32, dev)
+        dxhat = self.misc('dxhat', (n, c, H, W), f32, dev)
+        sig, eps = self.sigma, 1e-6
+
+        if self.kind == 'keynet':
+            m = self.misc('m', (n, K, h, w), f32, dev)
+            xe = engine.to_padded(xa, prec, self.misc, 'xe')
+            xk = engine.to_padded(xb, prec, self.misc, 'xk')
+            self._fwd_unit(enc, xe, H, W, dec_in[..., :C], 1)
+            self._fwd_unit(kp, xk, H, W, heat.permute(0, 2, 3, 1), 0)
+            L.call('kp_spatial_softmax_fwd', st, L.ptr(heat), n * K, h, w, L.ptr(k_t), L.ptr(p_h), L.ptr(p_w))
+            L.call('kp_gaussian_fwd', st, L.ptr(k_t), n * K, h, w, sig, eps, L.ptr(m))
+            L.call('kp_bn_act_fwd', st, L.nchw(m), L.view(dec_in[..., C:C + K]), None, None, L.ACT_NONE, L.POST_NONE, 1,
+                   n, h, w, K)
+        else:
+            phi_s = self.misc('phi_s', (n, h, w, C), self.T, dev)
+            phi_t = self.misc('phi_t', (n, h, w, C), self.T, dev)
+            k_s = self.misc('k_s', (n, K, 2), f32, dev)
+            mask_s = self.misc('mask_s', (n, 1, h, w), f32, dev)
+            mask_t = self.misc('mask_t', (n, 1, h, w), f32, dev)
+            amax = self.misc('amax', (n, h, w), torch.int32, dev)
+            xs = engine.to_padded(xa, prec, self.misc, 'xs')
+            xt = engine.to_padded(xb, prec, self.misc, 'xt')
+            # source frame: constants, but its BatchNorm running statistics update (transporter.py:36-37)
+            self._fwd_unit(enc, xs, H, W, phi_s, 0)
+            self._fwd_unit(kp, xs, H, W, heat.permute(0, 2, 3, 1), 0)
+            L.call('kp_spatial_softmax_fwd', st, L.ptr(heat), n * K, h, w, L.ptr(k_s), None, None)
+            self._fwd_unit(enc, xt, H, W, phi_t, 0)
+            self._fwd_unit(kp, xt, H, W, heat.permute(0, 2, 3, 1), 0)
+            L.call('kp_spatial_softmax_fwd', st, L.ptr(heat), n * K, h, w, L.ptr(k_t), L.ptr(p_h), L.ptr(p_w))
+            L.call('kp_transport_fwd', st, L.view(phi_s), L.view(phi_t), L.ptr(k_s), L.ptr(k_t), L.view(dec_in[..., :C]),
+                   1, L.ptr(mask_s), L.ptr(mask_t), L.ptr(amax), n, h, w, C, K, sig, eps)
+        self._fwd_unit(dec, dec_in, h, w, xhat.permute(0, 2, 3, 1), 0)
+
+        self.numel = xhat.numel()
+        self.loss_sum.zero_()
+        L.call('kp_l2_loss', st, L.ptr(xhat), L.ptr(xb), L.ptr(mask), self.numel, 1.0 / self.numel, L.ptr(self.loss_sum),
+               L.ptr(dxhat))
+
+        # ---- backward ----
+        self.flat_g.zero_()
+        ddec = self._bwd_unit(dec, dxhat.permute(0, 2, 3, 1), 0, True)
+        self._bucket_ready('decoder')
+        dk = self.misc('dk', (n, K, 2), f32, dev)
+        dheat = self.misc('dheat', (n, K, h, w), f32, dev)
+        if self.kind == 'keynet':
+            L.call('kp_gaussian_bwd', st, L.view(ddec[..., C:C + K]), 1, L.ptr(k_t), None, n, K, h, w, sig, eps, L.ptr(dk))
+            L.call('kp_spatial_softmax_bwd', st, L.ptr(dk), L.ptr(k_t), L.ptr(p_h), L.ptr(p_w), n * K, h, w, L.ptr(dheat))
+            self._bwd_unit(kp, dheat.permute(0, 2, 3, 1), 0, False)
+            self._bucket_ready('keypoint')
+            self._bwd_unit(enc, ddec[..., :C], 1, False)
+            self._bucket_ready('encoder')
+        else:
+            dphi = self.misc('dphi_t', (n, h, w, C), self.T, dev)
+            dmask = self.misc('dmask', (n, h, w, 1), f32, dev)
+            L.call('kp_transport_bwd', st, L.view(ddec[..., :C]), 1, L.view(phi_s), L.view(phi_t), L.ptr(mask_s),
+                   L.ptr(mask_t), L.view(dphi), L.ptr(dmask), n, h, w, C)
+            L.call('kp_gaussian_bwd', st, L.view(dmask), 0, L.ptr(k_t), L.ptr(amax), n, K, h, w, sig, eps, L.ptr(dk))
+            L.call('kp_spatial_softmax_bwd', st, L.ptr(dk), L.ptr(k_t), L.ptr(p_h), L.ptr(p_w), n * K, h, w, L.ptr(dheat))
+            self._bwd_unit(kp, dheat.permute(0, 2, 3, 1), 0, False)
+            self._bucket_ready('keypoint')
+            self._bwd_unit(enc, dphi, 0, False)
+            self._bucket_ready('encoder')
+
+    # ------------------------------------------------------------------------------------------
+    def _bucket_ready(self, name):
+        """Hook for bucket-wise all-reduce; buckets are reduced in `_allreduce` (see there)."""
+        return None
+
+    def _allreduce(self):
+        """Sum all-reduce of the gradient buckets over NCCL/NVLink (gloo in the CPU tests)."""
+        if self.world == 1:
+            return
+        works = []
+        for u in self.units.values():
+            a, b = u.span
+            works.append(torch.distributed.all_reduce(self.flat_g[a:b], op=torch.distributed.ReduceOp.SUM, group=self.pg,
+                                                      async_op=True))
+        for wk in works:
+            wk.wait()
+
+    def _adam(self):
+        L.call('kp_adam_step', L.stream(), L.ptr(self.flat_p), L.ptr(self.flat_g), L.ptr(self.flat_m), L.ptr(self.flat_v),
+               self.n_params, self.lr, self.betas[0], self.betas[1], self.eps, 0, 1.0 / self.world, L.ptr(self.step_dev))
+
+    def _whole(self, xa, xb, mask):
+        if self.augment is not None:
+            xa, xb, mask = self._augment(xa)
+        self._forward_backward(xa, xb, mask)
+
+    # ------------------------------------------------------------------------------------------
+    def step(self, xa: torch.Tensor, xb: Optional[torch.Tensor] = None, mask: Optional[torch.Tensor] = None):
+        """One training step on device tensors (NCHW fp32).  With ``augment`` set, ``xa`` is the clean batch and the
+        (x, x_, loss_mask) triple is produced by the TPS+rotate kernels.  Returns the device scalar holding
+        sum((xhat-x_)^2 mask); ``loss()`` converts it."""
+        xa = xa.to(self.device, torch.float32).contiguous()
+        if self.augment is None:
+            if xb is None:
+                raise ValueError('xb is required without augmentation')
+            xb = xb.to(self.device, torch.float32).contiguous()
+            if mask is not None:
+                mask = mask.to(self.device, torch.float32).contiguous()
+        if not self.use_graph:
+            self._whole(xa, xb, mask)
+            self._allreduce()
+            self._adam()
+            self.steps_done += 1
+            return self.loss_sum
+        key = (tuple(xa.shape), None if xb is None else tuple(xb.shape), None if mask is None else tuple(mask.shape))
+        if self.graph is None or self.graph_key != key:
+            self._capture(xa, xb, mask, key)
+        self.in_a.copy_(xa, non_blocking=True)
+        if xb is not None and self.augment is None:
+            self.in_b.copy_(xb, non_blocking=True)
+        if mask is not None and self.augment is None:
+            self.in_m.copy_(mask, non_blocking=True)
+        self.graph.replay()
+        if self.world > 1:
+            self._allreduce()
+            self.graph2.replay()
+        self.steps_done += 1
+        return self.loss_sum
+
+    def _capture(self, xa, xb, mask, key):
+        self.in_a = xa.clone()
+        self.in_b = None if (xb is None or self.augment is not None) else xb.clone()
+        self.in_m = None if (mask is None or self.augment is not None) else mask.clone()
+        # warm-up outside capture: allocates every static buffer, sets kernel attributes, builds nothing lazily later
+        state = self._snapshot()
+        s = torch.cuda.Stream(device=self.device)
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            self._whole(self.in_a, self.in_b, self.in_m)
+            self._adam()
+        torch.cuda.current_stream().wait_stream(s)
+        torch.cuda.synchronize()
+        self._restore(state)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self._whole(self.in_a, self.in_b, self.in_m)
+            if self.world == 1:
+                self._adam()
+        if self.world > 1:
+            self.graph2 = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph2):
+                self._adam()
+        self.graph_key = key
+
+    def _snapshot(self):
+        bufs = [b for _, bn in self._all_mods() if bn is not None for b in (bn.running_mean, bn.running_var, bn.num_batches_tracked)]
+        return ([t.clone() for t in (self.flat_p, self.flat_m, self.flat_v, self.step_dev)], [(b, b.clone()) for b in bufs])
+
+    def _restore(self, state):
+        flats, bufs = state
+        for dst, src in zip((self.flat_p, self.flat_m, self.flat_v, self.step_dev), flats):
+            dst.copy_(src)
+        for b, saved in bufs:
+            b.copy_(saved)
+
+    def _all_mods(self):
+        for u in self.units.values():
+            yield from u.mods
+
+    # ------------------------------------------------------------------------------------------
+    def loss(self) -> float:
+        """Mean masked L2 loss of the last step (device -> host read)."""
+        return float(self.loss_sum.item()) / self.numel
+
+    def outputs(self):
+        """Keypoints (N,K,2) (y,x) and reconstruction of the last step (static buffers)."""
+        return self.misc.bufs[('misc', 'k_t')], self.misc.bufs[('misc', 'xhat')]
+
+    def activation_bytes(self):
+        return sum(u.alloc.nbytes() for u in self.units.values()) + self.misc.nbytes()

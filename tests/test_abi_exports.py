@@ -1,0 +1,74 @@
+"""CPU-side checks of the drop-in boundary: the C-ABI library loads and exports every symbol declared in
+include/keypoints_b200.h (no compute call is made: there is no GPU here and no CPU fallback)."""
+import os
+import re
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope='module')
+def built():
+    subprocess.run(['make', '-C', os.path.join(ROOT, 'keypoints_b200', 'csrc'), '-j', '8'], check=True,
+                   stdout=subprocess.DEVNULL)
+    from keypoints_b200 import lib
+    return lib
+
+
+def declared_symbols():
+    text = open(os.path.join(ROOT, 'include', 'keypoints_b200.h')).read()
+    text = re.sub(r'/\*.*?\*/', '', text, flags=re.S)
+    return sorted(set(re.findall(r'\b(kp_[a-z0-9_]+)\s*\(', text)))
+
+
+def test_header_symbols_exported(built):
+    handle = built.load()
+    names = declared_symbols()
+    assert len(names) >= 20
+    for n in names:
+        assert hasattr(handle, n), f'{n} declared in include/keypoints_b200.h but not exported'
+    assert sorted(built.EXPORTS) == names, 'lib.py binding table and the header disagree'
+    assert handle.kp_version() == 100
+
+
+def test_sass_is_blackwell_native(built):
+    """The tensor-core kernels must be tcgen05 / TMA code, not a legacy mma.sync path."""
+    sass = subprocess.run(['cuobjdump', '-sass', built.LIB_PATH], capture_output=True, text=True).stdout
+    assert 'UTCHMMA' in sass and 'UTMALDG' in sass and 'LDTM' in sass
+    assert 'HMMA' not in sass.replace('UTCHMMA', '')
+
+
+def test_no_cpu_fallback(built):
+    import torch
+    from keypoints_b200.models import transporter
+    net = transporter.make('VGG_PONG_LAYERNECK', 1, 16, 4)
+    with pytest.raises(RuntimeError):
+        net(torch.zeros(2, 1, 16, 16), torch.zeros(2, 1, 16, 16))
+    with pytest.raises(built.KpError):
+        built.ptr(torch.zeros(1))
+
+
+def test_state_dict_keys_match_reference_layout(built):
+    from oracle import keypoints_oracle as O
+    from keypoints_b200.models import keynet, transporter
+    net = transporter.make('F', 3, 64, 10)
+    ref = O.init_state_dict(O.transporter_ops('F', 3, 64, 10), 0)
+    assert set(net.state_dict().keys()) == set(ref.keys())
+    net.load_state_dict(ref, strict=True)
+    assert sum(p.numel() for p in net.parameters()) == 24468813
+    kn = keynet.build('VGG_PONG', 1, 8, 3)
+    assert set(kn.state_dict().keys()) == set(O.init_state_dict(O.keynet_ops('VGG_PONG', 1, 8, 3), 0).keys())
+
+
+def test_checkpoint_roundtrip(built, tmp_path):
+    import torch
+    from keypoints_b200.models import transporter
+    a = transporter.make('VGG_PONG_LAYERNECK', 1, 16, 4)
+    a.save(str(tmp_path / 'ck'))
+    files = sorted(str(p.relative_to(tmp_path / 'ck')) for p in (tmp_path / 'ck').rglob('*.mdl'))
+    assert files == sorted(f'{u}/{b}.mdl' for u in ('encoder', 'keypoint', 'decoder') for b in ('in_block', 'core', 'out_block'))
+    b = transporter.make('VGG_PONG_LAYERNECK', 1, 16, 4, load=str(tmp_path / 'ck'))
+    for (k1, v1), (k2, v2) in zip(a.state_dict().items(), b.state_dict().items()):
+        assert k1 == k2 and torch.equal(v1, v2)

@@ -1,0 +1,288 @@
+"""GPU parity tests: the CUDA path (through the C ABI, via the keypoints_b200 Python mirror of the reference
+API) against (a) the golden fixtures produced by the unmodified reference and (b) the CPU oracle on the
+same seeded inputs.  Tolerance: the north-star bar, 1e-3 relative (to max |ref|) in fp32 for keypoint
+coordinates and reconstructed pixels; gradients and the remaining outputs use the same bar unless noted."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-3
+
+
+def rel_err(a, b):
+    a = np.asarray(a.detach().float().cpu().numpy() if isinstance(a, torch.Tensor) else a, dtype=np.float64)
+    b = np.asarray(b.detach().float().cpu().numpy() if isinstance(b, torch.Tensor) else b, dtype=np.float64)
+    assert a.shape == b.shape, (a.shape, b.shape)
+    return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-12))
+
+
+def close(a, b, tol=TOL, name=''):
+    e = rel_err(a, b)
+    assert e <= tol, f'{name}: rel-to-max err {e:.3e} > {tol}'
+    return e
+
+
+@pytest.fixture(scope='module')
+def dev():
+    assert torch.cuda.is_available(), 'GPU tests need a CUDA device'
+    from keypoints_b200 import lib
+    sm, major, minor = lib.device_info()
+    assert major == 10
+    return torch.device('cuda:0')
+
+
+# ------------------------------------------------------------------------------------------------
+def test_known_answers(dev, golden):
+    from keypoints_b200.models import functional as MF
+    from keypoints_b200 import tps
+    g = golden('known_answers')
+    for v in (1, 5, 100):
+        hm = torch.zeros(1, 1, 5, 5, device=dev); hm[0, 0, 2, 2] = float(v)
+        close(MF.spacial_logsoftmax(hm), g[f'peak5_center_{v}/logsoft'], 1e-5)
+        close(MF.spacial_softmax(hm), g[f'peak5_center_{v}/soft'], 1e-5)
+    hm = torch.zeros(1, 1, 5, 5, device=dev); hm[0, 0, 4, 4] = 5.0
+    close(MF.spacial_logsoftmax(hm), np.full((1, 1, 2), 0.627881), 1e-5)
+    hm = torch.zeros(1, 1, 16, 16, device=dev); hm[0, 0, 0, 15] = 20.0
+    k = MF.spacial_logsoftmax(hm)
+    close(k, g['coords16/k'], 1e-5)
+    close(MF.gaussian_like_function(k, 16, 16), g['coords16/g'], 1e-5)
+    # identity TPS (theta = 0) must reproduce the input: grid is the identity map (tps.py:197-212)
+    x = torch.rand(1, 2, 6, 3, device=dev)
+    c = torch.tensor([[0., 0], [1., 0], [1., 1], [0, 1]]).unsqueeze(0)
+    ref = torch.nn.functional.grid_sample(x.cpu(), torch.from_numpy(g['tps_identity/grid']), padding_mode='zeros',
+                                          align_corners=False)
+    close(tps.tps_transform(x, torch.zeros(1, 7, 2), c), ref, 1e-5)
+
+
+def test_functional_golden(dev, golden):
+    from keypoints_b200.models import functional as MF
+    g = golden('functional')
+    heat = torch.from_numpy(g['ssm/heat']).to(dev).requires_grad_(True)
+    k, (ph, pw) = MF.spacial_logsoftmax(heat, probs=True)
+    close(k, g['ssm/k'], 1e-5, 'k'); close(ph, g['ssm/ph'], 1e-5, 'ph'); close(pw, g['ssm/pw'], 1e-5, 'pw')
+    (k * torch.from_numpy(g['ssm/gk']).to(dev)).sum().backward()
+    close(heat.grad, g['ssm/dheat'], 1e-5, 'dheat')
+    k2, (ph2, _) = MF.spacial_softmax(heat.detach(), probs=True)
+    close(k2, g['ssm/k_soft'], 1e-5); close(ph2, g['ssm/ph_soft'], 1e-5)
+    kp = torch.from_numpy(g['gauss/kp']).to(dev).requires_grad_(True)
+    m = MF.gaussian_like_function(kp, 6, 11)
+    close(m, g['gauss/m'], 1e-5, 'm')
+    (m * torch.from_numpy(g['gauss/gm']).to(dev)).sum().backward()
+    close(kp.grad, g['gauss/dkp'], 1e-4, 'dkp')
+
+
+def test_tps_golden(dev, golden):
+    from keypoints_b200 import tps, data_augments
+    g = golden('tps')
+    x, theta, ctrl, rot = (torch.from_numpy(g[k]) for k in ('x', 'theta', 'ctrl', 'rot'))
+    xd = x.to(dev)
+    close(tps.tps_transform(xd, theta, ctrl), g['tps'], 1e-4, 'tps')
+    close(tps.rotate_affine_grid_multi(xd, rot), g['rot_out'], 1e-4, 'rot')
+    # reduced (T+2) form against the reference grid + torch sampler
+    ref = torch.nn.functional.grid_sample(x, torch.from_numpy(g['grid_reduced']), padding_mode='zeros', align_corners=False)
+    close(tps.tps_transform(xd, torch.from_numpy(g['theta_reduced']), ctrl), ref, 1e-4, 'tps_reduced')
+    torch.manual_seed(77)          # same CPU RNG consumption order as data_augments.py:31,35
+    x1, x2, mask = data_augments.TpsAndRotate(4, 0.05, 0.1)(xd, xd)
+    close(x1, g['aug/x1'], 2e-4, 'x1'); close(x2, g['aug/x2'], 5e-4, 'x2'); close(mask, g['aug/mask'], 5e-4, 'mask')
+
+
+# ------------------------------------------------------------------------------------------------
+MODELS = [('transporter_pong', 'transporter', 'VGG_PONG_LAYERNECK'), ('keynet_F', 'keynet', 'F'),
+          ('transporter_F', 'transporter', 'F'), ('keynet_pong_mu', 'keynet', 'VGG_PONG')]
+
+
+def build_net(kind, model_type, cin, z, K, seed, dev):
+    from oracle import keypoints_oracle as O
+    from keypoints_b200.models import keynet, transporter
+    if kind == 'transporter':
+        net = transporter.make(model_type, cin, z, K)
+        ops = O.transporter_ops(model_type, cin, z, K)
+    else:
+        net = keynet.build(model_type, cin, z, K)
+        ops = O.keynet_ops(model_type, cin, z, K)
+    sd = O.init_state_dict(ops, seed)
+    net.load_state_dict(sd, strict=True)
+    return net.to(dev), sd, ops
+
+
+def bn_sibling(key, keys):
+    if not key.endswith('.bias'):
+        return None
+    head, idx, _ = key.rsplit('.', 2)
+    sib = f'{head}.{int(idx) + 1}.bias'
+    return sib if sib in keys else None
+
+
+@pytest.mark.parametrize('name,kind,model_type', MODELS)
+def test_module_api_vs_reference_golden(dev, golden, name, kind, model_type):
+    """Reference-API path (nn.Module forward, autograd backward, torch Adam as the scripts use) in fp32."""
+    import keypoints_b200
+    keypoints_b200.set_precision('fp32')
+    g = golden(name)
+    cin, z, K, n, h, w, seed = (int(v) for v in g['meta'])
+    net, _, _ = build_net(kind, model_type, cin, z, K, seed, dev)
+    a, b = torch.from_numpy(g['a']).to(dev), torch.from_numpy(g['b']).to(dev)
+    mask = torch.from_numpy(g['mask']).to(dev) if 'mask' in g else None
+    optim = torch.optim.Adam(net.parameters(), lr=1e-4)
+    optim.zero_grad()
+    res = net(a, b)
+    loss = ((res[0] - b) ** 2 * mask).mean() if mask is not None else ((res[0] - b) ** 2).mean()
+    loss.backward()
+    names = ['x_hat', 'phi', 'k', 'm', 'p', 'heat', 'mask_s', 'mask_t'] if kind == 'transporter' else \
+            ['x_hat', 'z', 'k', 'm', 'p', 'heat']
+    for nm, r in zip(names, res):
+        if nm == 'p':
+            close(r[0], g['out/p_h'], TOL, 'p_h'); close(r[1], g['out/p_w'], TOL, 'p_w')
+        else:
+            close(r, g[f'out/{nm}'], TOL, nm)
+    close(loss, g['loss'], TOL, 'loss')
+    grads = dict(net.named_parameters())
+    for key in g:
+        if key.startswith('grad/'):
+            sib = bn_sibling(key, g)
+            if sib is not None:     # bias feeding train-mode BN: exactly zero here, rounding noise in the reference
+                assert float(grads[key[5:]].grad.abs().max()) <= 1e-3 * np.abs(g[sib]).max()
+            else:
+                close(grads[key[5:]].grad, g[key], 2e-3, key)
+        elif key.startswith('gradsample/'):
+            close(grads[key[11:]].grad.reshape(-1)[::997], g[key], 2e-3, key)
+        elif key.startswith('stat/'):
+            close(net.state_dict()[key[5:]], g[key], TOL, key)
+    if any(k.startswith('adam/') for k in g):
+        optim.step()
+        sd = net.state_dict()
+        for key in g:
+            if key.startswith('adam/') and bn_sibling('grad/' + key[5:], g) is None:
+                e = np.abs(sd[key[5:]].cpu().numpy().astype(np.float64) - g[key]).max()
+                assert e <= 0.05 * 1e-4, f'{key}: {e}'          # within 5 % of one lr-sized step
+
+
+@pytest.mark.parametrize('name,kind,model_type', MODELS)
+@pytest.mark.parametrize('use_graph', [False, True])
+def test_fused_trainer_vs_oracle(dev, golden, name, kind, model_type, use_graph):
+    """Fused step (static buffers, fused loss/Adam, optional CUDA graph) in fp32 against the CPU oracle,
+    two consecutive steps (the second checks Adam state, BN running stats and graph replay)."""
+    from oracle import keypoints_oracle as O
+    from keypoints_b200.trainer import Trainer
+    g = golden(name)
+    cin, z, K, n, h, w, seed = (int(v) for v in g['meta'])
+    net, sd, ops = build_net(kind, model_type, cin, z, K, seed, dev)
+    a, b = torch.from_numpy(g['a']), torch.from_numpy(g['b'])
+    mask = torch.from_numpy(g['mask']) if 'mask' in g else None
+    tr = Trainer(net, precision='fp32', use_graph=use_graph)
+    oracle = O.OracleTrainer(kind, model_type, cin, z, K, {k: v.clone() for k, v in sd.items()})
+    torch.set_num_threads(max(1, torch.get_num_threads()))
+    for step in range(2):
+        tr.step(a.to(dev), b.to(dev), None if mask is None else mask.to(dev))
+        ref_loss, ref_out = oracle.step(a, b, mask)
+        k_t, xhat = tr.outputs()
+        close(torch.tensor(tr.loss()), ref_loss, TOL, f'loss step {step}')
+        close(k_t, ref_out[2], TOL, f'k step {step}')
+        close(xhat, ref_out[0], TOL, f'x_hat step {step}')
+        assert float((k_t.cpu() - ref_out[2]).abs().max()) <= 1e-3          # keypoint (x,y) max-abs-err
+    new = net.state_dict()
+    for key, ref in oracle.sd.items():
+        if key.endswith('num_batches_tracked'):
+            assert int(new[key]) == int(ref)
+        elif 'running_' in key:
+            close(new[key], ref, TOL, key)
+        elif bn_sibling('grad/' + key, {'grad/' + k: 0 for k in oracle.sd}) is None:
+            # Adam's first steps are +-lr * sign(g): elements whose gradient is below the fp32 noise floor may take
+            # the other sign, so bound the fraction of such elements instead of the max
+            e = (new[key].cpu() - ref.detach()).abs()
+            assert float(e.max()) <= 2.2 * 2e-4, f'{key}: param diverged by {float(e.max())}'
+            frac = float((e > 0.1 * 1e-4).float().mean())
+            assert frac <= 2e-3, f'{key}: {frac} of elements off'
+
+
+# ------------------------------------------------------------------------------------------------
+def _conv_ref(x, w, b):
+    return torch.nn.functional.conv2d(torch.nn.functional.pad(x, (1, 1, 1, 1), mode='replicate') if w.shape[-1] == 3 else x, w, b)
+
+
+@pytest.mark.parametrize('cin,cout,k,n,h,w', [(64, 128, 3, 2, 8, 8), (128, 64, 3, 3, 12, 20), (256, 256, 3, 1, 16, 16),
+                                                (512, 64, 1, 2, 4, 4), (128, 512, 3, 2, 6, 5)])
+def test_tensor_core_conv_vs_fp32(dev, cin, cout, k, n, h, w):
+    """tcgen05 fprop / dgrad / wgrad against an fp32 reference fed the same bf16-rounded operands."""
+    from keypoints_b200 import engine, lib as L
+    from keypoints_b200.engine import ConvSpec, LayerParams, LayerGrads
+    torch.manual_seed(cin + cout + h)
+    spec = ConvSpec(k=k, cin=cin, cout=cout, bn=True, act='none')
+    x = torch.randn(n, cin, h, w).bfloat16().float()
+    wt = (torch.randn(cout, cin, k, k) / (cin * k * k) ** 0.5).bfloat16().float()
+    bias = torch.randn(cout) * 0.1
+    p = LayerParams(w=wt.to(dev), b=bias.to(dev), gamma=torch.ones(cout, device=dev), beta=torch.zeros(cout, device=dev),
+                    rmean=torch.zeros(cout, device=dev), rvar=torch.ones(cout, device=dev),
+                    nbt=torch.zeros((), dtype=torch.long, device=dev))
+    assert engine.uses_tc(spec, cin, 'bf16')
+    xp = engine.to_padded(x.to(dev), 'bf16')
+    out = torch.empty(n, h, w, cout, device=dev)                      # BN output (identity affine of normalised y)
+    ctxs = engine.unit_forward([spec], [p], xp, h, w, 'bf16', out, 0)
+    y = ctxs[0].y[:, :h, :w, :].float().permute(0, 3, 1, 2)
+    ref_y = _conv_ref(x, wt, bias)
+    close(y, ref_y, 1e-2, 'fprop (bf16 store)')
+    ref_bn = torch.nn.functional.batch_norm(ref_y, None, None, training=True)
+    close(out.permute(0, 3, 1, 2), ref_bn, 1e-2, 'bn(fprop): statistics from the fp32 accumulators')
+    close(p.rmean, 0.1 * ref_y.mean(dim=(0, 2, 3)), 2e-3, 'running_mean')
+    # backward
+    dout = torch.randn(n, cout, h, w).bfloat16().float()
+    xr = x.clone().requires_grad_(True)
+    wr = wt.clone().requires_grad_(True)
+    ref = torch.nn.functional.batch_norm(_conv_ref(xr, wr, bias), None, None, training=True)
+    ref.backward(dout)
+    g = LayerGrads(dw=torch.zeros(cout, cin, k, k, device=dev), db=torch.zeros(cout, device=dev),
+                   dgamma=torch.zeros(cout, device=dev), dbeta=torch.zeros(cout, device=dev))
+    dxp = engine.unit_backward([spec], [p], [g], ctxs, dout.to(dev).permute(0, 2, 3, 1), 0, 'bf16', True)
+    dx = engine.fold_to_nchw(dxp, cin, h, w)
+    close(g.dw, wr.grad, 2e-2, 'wgrad')
+    close(dx, xr.grad, 2e-2, 'dgrad')
+
+
+def test_adjoint_identity_full_size(dev):
+    """Size-independent property at the BASELINE layer sizes: <conv(x,w), dy> == <w, wgrad(x,dy)> == <x, dgrad(dy,w)>
+    for the tensor-core kernels (bf16 operands, fp32 accumulation), 128x128x64->128 at batch 8."""
+    from keypoints_b200 import engine, lib as L
+    from keypoints_b200.engine import ConvSpec, LayerParams, LayerGrads
+    torch.manual_seed(0)
+    n, cin, cout, h, w = 8, 64, 128, 128, 128
+    spec = ConvSpec(k=3, cin=cin, cout=cout, bn=False, act='none')
+    x = torch.randn(n, cin, h, w, device=dev).bfloat16().float()
+    wt = (torch.randn(cout, cin, 3, 3, device=dev) / 24).bfloat16().float()
+    p = LayerParams(w=wt, b=None)
+    xp = engine.to_padded(x, 'bf16')
+    out = torch.empty(n, h, w, cout, device=dev)
+    ctxs = engine.unit_forward([spec], [p], xp, h, w, 'bf16', out, 0)
+    dy = torch.randn(n, h, w, cout, device=dev).bfloat16().float()
+    g = LayerGrads(dw=torch.zeros_like(wt), db=torch.zeros(cout, device=dev))
+    dxp = engine.unit_backward([spec], [p], [g], ctxs, dy, 0, 'bf16', True)
+    dx = engine.fold_to_nchw(dxp, cin, h, w)
+    lhs = float((out.double() * dy.double()).sum())
+    via_w = float((g.dw.double() * wt.double()).sum())
+    via_x = float((dx.double() * x.double()).sum())
+    norm = float((out.double() ** 2).sum() ** 0.5 * (dy.double() ** 2).sum() ** 0.5)   # Cauchy-Schwarz scale
+    assert abs(lhs - via_w) / norm < 1e-4, (lhs, via_w, norm)
+    assert abs(lhs - via_x) / norm < 1e-4, (lhs, via_x, norm)
+
+
+@pytest.mark.parametrize('name,kind,model_type', [('keynet_F', 'keynet', 'F'), ('transporter_F', 'transporter', 'F')])
+def test_bf16_tensor_core_step_vs_oracle(dev, golden, name, kind, model_type):
+    """Throughput mode end to end (bf16 activations, tcgen05 convs).  SURVEY.md 7: the reference's own graph under
+    autocast(bf16) deviates from its fp32 run by 2.4e-1 (x_hat) / 3.7e-2 (k) on F at init, so this is a sanity
+    bound, not the 1e-3 parity gate (that gate is the fp32 mode above)."""
+    from oracle import keypoints_oracle as O
+    from keypoints_b200.trainer import Trainer
+    g = golden(name)
+    cin, z, K, n, h, w, seed = (int(v) for v in g['meta'])
+    net, sd, ops = build_net(kind, model_type, cin, z, K, seed, dev)
+    a, b = torch.from_numpy(g['a']), torch.from_numpy(g['b'])
+    mask = torch.from_numpy(g['mask']) if 'mask' in g else None
+    tr = Trainer(net, precision='bf16', use_graph=False)
+    tr.step(a.to(dev), b.to(dev), None if mask is None else mask.to(dev))
+    k_t, xhat = tr.outputs()
+    ek, ex = rel_err(k_t, g['out/k']), rel_err(xhat, g['out/x_hat'])
+    el = abs(tr.loss() - float(g['loss'])) / float(g['loss'])
+    print(f'bf16 end-to-end deviation {name}: k {ek:.3e}  x_hat {ex:.3e}  loss {el:.3e}')
+    assert ek < 0.1 and ex < 0.35 and el < 0.1
+    assert torch.isfinite(tr.flat_p).all()
