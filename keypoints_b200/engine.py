@@ -185,7 +185,8 @@ def unit_forward(specs: List[ConvSpec], params: List[LayerParams], x_pad: torch.
         if tc:
             sh = fshifts(s.k, PW)
             L.call('kp_conv_tc', st, L.ptr(cur), N * PH * PW, cinp, L.ptr(pk['tc_f']), len(sh), L.shifts_array(sh),
-                   L.ptr(p.b), L.ptr(y), s.cout, L.ptr(stats), PH, PW, h, w)
+                   L.ptr(p.b), L.ptr(y), s.cout, L.ptr(stats), PH, PW, h, w,
+                   flops=2.0 * N * h * w * s.cin * s.cout * s.k * s.k)
         else:
             src = cur if s.k == 3 else cur[:, 1:, 1:, :]
             L.call('kp_conv_simt', st, L.view(src), L.ptr(pk['simt_f']), L.ptr(p.b), L.view(y[:, :h, :w, :]),
@@ -266,11 +267,11 @@ def unit_backward(specs: List[ConvSpec], params: List[LayerParams], grads: List[
             stg = alloc(f'{tag}.stg', (max(sp.k * sp.k * sp.cout * cx.x.shape[3] for sp, cx in zip(specs, ctxs) if cx.tc),),
                         torch.float32, dev)
             L.call('kp_conv_wgrad_tc', st, L.ptr(c.x), L.ptr(dyp), Q, s.cin, cinp, s.cout, len(sh), L.shifts_array(sh),
-                   L.ptr(stg), L.ptr(g.dw))
+                   L.ptr(stg), L.ptr(g.dw), flops=2.0 * N * h * w * s.cin * s.cout * s.k * s.k)
             if want_dx:
                 dx = alloc(f'{tag}.dx{i}', (N, PH, PW, cinp), T, dev)
                 L.call('kp_conv_tc', st, L.ptr(dyp), Q, s.cout, L.ptr(c.pack['tc_d']), len(sh), L.shifts_array(sh), None,
-                       L.ptr(dx), cinp, None, PH, PW, PH, PW)
+                       L.ptr(dx), cinp, None, PH, PW, PH, PW, flops=2.0 * N * h * w * s.cin * s.cout * s.k * s.k)
         else:
             src = c.x if s.k == 3 else c.x[:, 1:, 1:, :]
             L.call('kp_conv_wgrad_simt', st, L.view(src), L.view(dy_int), L.ptr(g.dw), N, h, w, s.cin, s.cout, s.k)

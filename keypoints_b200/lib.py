@@ -84,12 +84,21 @@ def load():
     return lib
 
 
-def call(name, *args):
+timing = None         # when a list: (name, flops, start_event, end_event) per call (bench.py roofline leg)
+
+
+def call(name, *args, flops=0.0):
     global launches
     lib = load()
+    if timing is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
     rc = getattr(lib, name)(*args)
     if rc != 0:
         raise KpError(f'{name} failed ({rc}): {lib.kp_last_error().decode()}')
+    if timing is not None:
+        e1.record()
+        timing.append((name, flops, e0, e1))
     launches += 1
 
 

@@ -321,10 +321,12 @@ class Trainer:
         torch.cuda.synchronize()
         self._restore(state)
         self.graph = torch.cuda.CUDAGraph()
+        before = L.launches
         with torch.cuda.graph(self.graph):
             self._whole(self.in_a, self.in_b, self.in_m)
             if self.world == 1:
                 self._adam()
+        self.calls_per_step = L.launches - before + (1 if self.world > 1 else 0)
         if self.world > 1:
             self.graph2 = torch.cuda.CUDAGraph()
             with torch.cuda.graph(self.graph2):
