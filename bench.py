@@ -256,9 +256,16 @@ def main():
         rec, L.timing = L.timing, None
         tr2.use_graph = was
         agg = {}
-        for name, fl, a, b in rec:
+        calls = []
+        for name, fl, a, b, tg in rec:
             d = agg.setdefault(name, [0, 0.0, 0.0])
-            d[0] += 1; d[1] += a.elapsed_time(b); d[2] += fl
+            t_ms = a.elapsed_time(b)
+            d[0] += 1; d[1] += t_ms; d[2] += fl
+            calls.append((t_ms, name, tg, fl))
+        if os.environ.get('KP_BENCH_CALLS'):
+            with open(os.environ['KP_BENCH_CALLS'], 'w') as fh:
+                for t_ms, name, tg, fl in sorted(calls, key=lambda c: -c[0]):
+                    fh.write(f'{t_ms:8.4f} ms  {name:24s} {tg:40s} {fl / t_ms / 1e9 if fl else 0:8.1f} TFLOP/s\n')
         total_ms = sum(d[1] for d in agg.values())
         tc_ms = sum(agg[k][1] for k in ('kp_conv_tc', 'kp_conv_wgrad_tc') if k in agg)
         tc_fl = sum(agg[k][2] for k in ('kp_conv_tc', 'kp_conv_wgrad_tc') if k in agg)

@@ -185,7 +185,7 @@ int kp_rotate_warp(kp_stream stream, const float* x, float* out, const float* ro
  * device-resident step counter, incremented by the call and used for the bias corrections instead
  * of `step` — lets the whole train step replay as a CUDA graph. */
 int kp_adam_step(kp_stream stream, float* p, const float* g, float* m, float* v, int64_t n,
-                 float lr, float beta1, float beta2, float eps, int step, float grad_scale,
+                 double lr, double beta1, double beta2, double eps, int step, float grad_scale,
                  int32_t* step_dev);
 
 #ifdef __cplusplus

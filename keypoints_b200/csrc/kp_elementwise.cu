@@ -312,6 +312,244 @@ bn_act_bwd_apply_k(View<TG> dout, View<TY> y, View<TD> dy, const float* __restri
     }
 }
 
+
+// ================================================================================================
+// Fast path: NHWC with unit channel stride, 8 channels (16 bytes) per thread, C/8 a power of two <= 256.
+// One block walks whole image rows: 32-bit index math only, the channel group of a thread is fixed (so the
+// per-channel affine lives in registers and the reductions accumulate in registers), consecutive threads
+// touch consecutive 16-byte chunks of the row.
+// ================================================================================================
+constexpr int V8 = 8;
+
+struct RowFold {   // rows / columns of a replicate-padded gradient that fold into one unpadded coordinate
+    int n, v[3];
+    __device__ __forceinline__ RowFold(int o, int O, int pad) {
+        if (!pad) { n = 1; v[0] = o; return; }
+        n = 0; v[n++] = o + 1;
+        if (o == 0) v[n++] = 0;
+        if (o == O - 1) v[n++] = O + 1;
+    }
+};
+
+template <typename TG>
+__device__ __forceinline__ void fold_acc(const View<TG>& d, int n, const RowFold& fy, const RowFold& fx, int c0, float wgt,
+                                         float (&acc)[V8]) {
+    float t[V8];
+    for (int a = 0; a < fy.n; ++a)
+        for (int b = 0; b < fx.n; ++b) {
+            Vec<TG, V8>::load(d.at(n, fy.v[a], fx.v[b], c0), t);
+#pragma unroll
+            for (int i = 0; i < V8; ++i) acc[i] = fmaf(wgt, t[i], acc[i]);
+        }
+}
+
+template <typename TI, typename TO, int POST>
+__global__ void __launch_bounds__(256)
+bn_act_fwd_rows_k(View<TI> y, View<TO> out, const float* __restrict__ scale, const float* __restrict__ shift, int act,
+                  int pad, int N, int H, int W, int C, int OH, int OW, int cg_shift) {
+    const int ncg = C >> 3;
+    const int cg = threadIdx.x & (ncg - 1), c0 = cg * V8;
+    const int x0 = threadIdx.x >> cg_shift, xstep = 256 >> cg_shift;
+    float sc[V8], sh[V8];
+#pragma unroll
+    for (int i = 0; i < V8; ++i) { sc[i] = scale ? scale[c0 + i] : 1.f; sh[i] = shift ? shift[c0 + i] : 0.f; }
+    const int PH = OH + 2 * pad, PW = OW + 2 * pad, rows = N * PH;
+    const float ry = (OH > 1) ? (float)(H - 1) / (float)(OH - 1) : 0.f;
+    const float rx = (OW > 1) ? (float)(W - 1) / (float)(OW - 1) : 0.f;
+    for (int row = blockIdx.x; row < rows; row += gridDim.x) {
+        const int n = row / PH, py = row - n * PH;
+        const int oy = min(max(py - pad, 0), OH - 1);
+        int y0 = 0, y1 = 0;
+        float ly = 0.f;
+        if (POST == KP_POST_UP) {
+            float sy = ry * oy;
+            y0 = (int)sy; ly = sy - y0; y1 = min(y0 + 1, H - 1);
+        }
+        for (int px = x0; px < PW; px += xstep) {
+            const int ox = min(max(px - pad, 0), OW - 1);
+            float v[V8];
+            if (POST == KP_POST_NONE) {
+                load_act<TI, V8>(y, n, oy, ox, c0, sc, sh, act, v);
+            } else if (POST == KP_POST_POOL) {
+                float a[V8], b[V8], c[V8];
+                load_act<TI, V8>(y, n, 2 * oy, 2 * ox, c0, sc, sh, act, v);
+                load_act<TI, V8>(y, n, 2 * oy, 2 * ox + 1, c0, sc, sh, act, a);
+                load_act<TI, V8>(y, n, 2 * oy + 1, 2 * ox, c0, sc, sh, act, b);
+                load_act<TI, V8>(y, n, 2 * oy + 1, 2 * ox + 1, c0, sc, sh, act, c);
+#pragma unroll
+                for (int i = 0; i < V8; ++i) v[i] = fmaxf(fmaxf(v[i], a[i]), fmaxf(b[i], c[i]));
+            } else {
+                float sx = rx * ox;
+                int xa = (int)sx;
+                float lx = sx - xa;
+                int xb = min(xa + 1, W - 1);
+                float a00[V8], a01[V8], a10[V8], a11[V8];
+                load_act<TI, V8>(y, n, y0, xa, c0, sc, sh, act, a00);
+                load_act<TI, V8>(y, n, y0, xb, c0, sc, sh, act, a01);
+                load_act<TI, V8>(y, n, y1, xa, c0, sc, sh, act, a10);
+                load_act<TI, V8>(y, n, y1, xb, c0, sc, sh, act, a11);
+#pragma unroll
+                for (int i = 0; i < V8; ++i)
+                    v[i] = (1.f - ly) * ((1.f - lx) * a00[i] + lx * a01[i]) + ly * ((1.f - lx) * a10[i] + lx * a11[i]);
+            }
+            Vec<TO, V8>::store(out.at(n, py, px, c0), v);
+        }
+    }
+}
+
+// MODE 0: reduce only (BatchNorm pass 1)   MODE 1: reduce + write dy = dz (no BatchNorm)   MODE 2: apply (pass 2)
+template <typename TG, typename TY, typename TD, int POST, int MODE>
+__global__ void __launch_bounds__(256)
+bn_act_bwd_rows_k(View<TG> dout, View<TY> y, View<TD> dy, const float* __restrict__ scale,
+                  const float* __restrict__ shift, const float* __restrict__ mean, const float* __restrict__ invstd,
+                  double* sums, double count, int act, int pad, int N, int H, int W, int C, int OH, int OW, int cg_shift) {
+    __shared__ float red[2][256 * V8];
+    const int ncg = C >> 3;
+    const int cg = threadIdx.x & (ncg - 1), c0 = cg * V8;
+    const int x0 = threadIdx.x >> cg_shift, xstep = 256 >> cg_shift;
+    float sc[V8], sh[V8], mu[V8], is[V8], s1[V8], s2[V8];
+#pragma unroll
+    for (int i = 0; i < V8; ++i) {
+        sc[i] = scale ? scale[c0 + i] : 1.f; sh[i] = shift ? shift[c0 + i] : 0.f;
+        mu[i] = mean ? mean[c0 + i] : 0.f; is[i] = invstd ? invstd[c0 + i] : 1.f;
+        if (MODE == 2) { s1[i] = (float)(sums[c0 + i] / count); s2[i] = (float)(sums[C + c0 + i] / count); }
+        else { s1[i] = 0.f; s2[i] = 0.f; }
+    }
+    const float ry = (OH > 1) ? (float)(H - 1) / (float)(OH - 1) : 0.f;
+    const float rx = (OW > 1) ? (float)(W - 1) / (float)(OW - 1) : 0.f;
+    // consume one element: g = gradient w.r.t. the activation output, yv = raw conv output
+    auto emit = [&](int n, int yy, int xx, float (&g)[V8], const float (&yv)[V8]) {
+#pragma unroll
+        for (int i = 0; i < V8; ++i) g[i] *= act_grad(fmaf(yv[i], sc[i], sh[i]), act);
+        if (MODE == 2) {
+#pragma unroll
+            for (int i = 0; i < V8; ++i) g[i] = sc[i] * (g[i] - s1[i] - (yv[i] - mu[i]) * is[i] * s2[i]);
+            Vec<TD, V8>::store(dy.at(n, yy, xx, c0), g);
+        } else {
+#pragma unroll
+            for (int i = 0; i < V8; ++i) { s1[i] += g[i]; s2[i] += g[i] * (yv[i] - mu[i]) * is[i]; }
+            if (MODE == 1) Vec<TD, V8>::store(dy.at(n, yy, xx, c0), g);
+        }
+    };
+    if (POST == KP_POST_POOL) {
+        const int HW2 = (H + 1) >> 1, WW2 = (W + 1) >> 1, rows = N * HW2;
+        for (int row = blockIdx.x; row < rows; row += gridDim.x) {
+            const int n = row / HW2, wy = (row - n * HW2) * 2;
+            const RowFold fy(wy >> 1, OH, pad);
+            for (int wi = x0; wi < WW2; wi += xstep) {
+                const int wx = wi * 2;
+                const bool full = (wy + 1 < H) && (wx + 1 < W);
+                float yv[4][V8], best[V8], t[V8];
+                int bi[V8];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int yy = wy + (q >> 1), xx = wx + (q & 1);
+                    if (yy < H && xx < W) Vec<TY, V8>::load(y.at(n, yy, xx, c0), yv[q]);
+                    else {
+#pragma unroll
+                        for (int i = 0; i < V8; ++i) yv[q][i] = 0.f;
+                    }
+                }
+#pragma unroll
+                for (int i = 0; i < V8; ++i) { best[i] = -INFINITY; bi[i] = 0; t[i] = 0.f; }
+                if (full) {
+#pragma unroll
+                    for (int q = 0; q < 4; ++q)
+#pragma unroll
+                        for (int i = 0; i < V8; ++i) {
+                            float a = apply_act(fmaf(yv[q][i], sc[i], sh[i]), act);
+                            if (a > best[i] || q == 0) { best[i] = a; bi[i] = q; }      // first maximum wins
+                        }
+                    const RowFold fx(wx >> 1, OW, pad);
+                    fold_acc<TG>(dout, n, fy, fx, c0, 1.f, t);
+                }
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int yy = wy + (q >> 1), xx = wx + (q & 1);
+                    if (yy < H && xx < W) {
+                        float g[V8];
+#pragma unroll
+                        for (int i = 0; i < V8; ++i) g[i] = (full && bi[i] == q) ? t[i] : 0.f;
+                        emit(n, yy, xx, g, yv[q]);
+                    }
+                }
+            }
+        }
+    } else {
+        const int rows = N * H;
+        for (int row = blockIdx.x; row < rows; row += gridDim.x) {
+            const int n = row / H, yy = row - n * H;
+            if (POST == KP_POST_NONE) {
+                const RowFold fy(yy, OH, pad);
+                for (int xx = x0; xx < W; xx += xstep) {
+                    float g[V8], yv[V8];
+#pragma unroll
+                    for (int i = 0; i < V8; ++i) g[i] = 0.f;
+                    const RowFold fx(xx, OW, pad);
+                    fold_acc<TG>(dout, n, fy, fx, c0, 1.f, g);
+                    Vec<TY, V8>::load(y.at(n, yy, xx, c0), yv);
+                    emit(n, yy, xx, g, yv);
+                }
+            } else {   // bilinear x2 (align_corners=True) backward: gather the <= 4x4 outputs that read (yy,xx)
+                int ylo = 0, yhi = OH - 1;
+                if (H > 1) { ylo = max(0, 2 * yy - 2); yhi = min(OH - 1, 2 * yy + 3); }
+                for (int xx = x0; xx < W; xx += xstep) {
+                    int xlo = 0, xhi = OW - 1;
+                    if (W > 1) { xlo = max(0, 2 * xx - 2); xhi = min(OW - 1, 2 * xx + 3); }
+                    float g[V8], yv[V8];
+#pragma unroll
+                    for (int i = 0; i < V8; ++i) g[i] = 0.f;
+                    for (int Y = ylo; Y <= yhi; ++Y) {
+                        float sy = ry * Y;
+                        int ya = (int)sy;
+                        float ly = sy - ya;
+                        int yb = min(ya + 1, H - 1);
+                        float wyv = (ya == yy ? 1.f - ly : 0.f) + (yb == yy ? ly : 0.f);
+                        if (wyv == 0.f) continue;
+                        const RowFold fy(Y, OH, pad);
+                        for (int X = xlo; X <= xhi; ++X) {
+                            float sx = rx * X;
+                            int xa = (int)sx;
+                            float lx = sx - xa;
+                            int xb = min(xa + 1, W - 1);
+                            float wxv = (xa == xx ? 1.f - lx : 0.f) + (xb == xx ? lx : 0.f);
+                            if (wxv == 0.f) continue;
+                            const RowFold fx(X, OW, pad);
+                            fold_acc<TG>(dout, n, fy, fx, c0, wyv * wxv, g);
+                        }
+                    }
+                    Vec<TY, V8>::load(y.at(n, yy, xx, c0), yv);
+                    emit(n, yy, xx, g, yv);
+                }
+            }
+        }
+    }
+    if (MODE != 2) {
+#pragma unroll
+        for (int i = 0; i < V8; ++i) { red[0][threadIdx.x * V8 + i] = s1[i]; red[1][threadIdx.x * V8 + i] = s2[i]; }
+        __syncthreads();
+        // threads 0 .. C-1: one channel each, sum over the 256/ncg threads that share its channel group
+        for (int ch = threadIdx.x; ch < C; ch += 256) {
+            const int g8 = ch >> 3, i = ch & 7;
+            float a = 0.f, b = 0.f;
+            for (int t = g8; t < 256; t += ncg) { a += red[0][t * V8 + i]; b += red[1][t * V8 + i]; }
+            atomicAdd(&sums[ch], (double)a);
+            atomicAdd(&sums[C + ch], (double)b);
+        }
+    }
+}
+
+static bool fast_ok(int C, long long rows_px) {
+    if (C % 8) return false;
+    int ncg = C / 8;
+    return ncg >= 1 && ncg <= 256 && (ncg & (ncg - 1)) == 0 && rows_px < (1LL << 31);
+}
+static int ilog2(int v) { int s = 0; while ((1 << s) < v) ++s; return s; }
+static int rows_grid(long long rows) {
+    long long cap = (long long)kp_sm_count() * 8;
+    return (int)(rows < cap ? (rows < 1 ? 1 : rows) : cap);
+}
+
 static void out_dims(int post, int H, int W, int* OH, int* OW) {
     if (post == KP_POST_POOL) { *OH = H / 2; *OW = W / 2; }
     else if (post == KP_POST_UP) { *OH = 2 * H; *OW = 2 * W; }
@@ -351,7 +589,15 @@ extern "C" int kp_bn_act_fwd(kp_stream stream, const kp_view* y, const kp_view* 
         return dispatch1(out->dtype, [&](auto to) -> int {
             using TI = decltype(ti);
             using TO = decltype(to);
-            if (vec) {
+            if (vec && fast_ok(C, P * C)) {
+                const int g = rows_grid((long long)N * (OH + 2 * pad)), sh = ilog2(C / 8);
+                cudaStream_t st = (cudaStream_t)stream;
+#define KP_FWD(POSTV) bn_act_fwd_rows_k<TI, TO, POSTV><<<g, 256, 0, st>>>(make_view<TI>(y), make_view<TO>(out), scale, shift, act, pad, N, H, W, C, OH, OW, sh)
+                if (post == KP_POST_NONE) KP_FWD(KP_POST_NONE);
+                else if (post == KP_POST_POOL) KP_FWD(KP_POST_POOL);
+                else KP_FWD(KP_POST_UP);
+#undef KP_FWD
+            } else if (vec) {
                 Launch2D l = plan2d(P, C, 8);
                 bn_act_fwd_k<TI, TO, 8><<<l.grid, l.block, 0, (cudaStream_t)stream>>>(
                     make_view<TI>(y), make_view<TO>(out), scale, shift, act, post, pad, N, H, W, C, OH, OW);
@@ -383,7 +629,22 @@ extern "C" int kp_bn_act_bwd_reduce(kp_stream stream, const kp_view* dout, const
                 using TG = decltype(tg);
                 using TY = decltype(ty);
                 using TD = decltype(td);
-                if (vec) {
+                if (vec && fast_ok(C, P * C)) {
+                    const long long rows = post == KP_POST_POOL ? (long long)N * ((H + 1) / 2) : (long long)N * H;
+                    const int g = rows_grid(rows), sh = ilog2(C / 8);
+                    cudaStream_t st = (cudaStream_t)stream;
+#define KP_BWD(POSTV, MODEV) bn_act_bwd_rows_k<TG, TY, TD, POSTV, MODEV><<<g, 256, 0, st>>>(make_view<TG>(dout), make_view<TY>(y), make_view<TD>(dyv), scale, shift, mean, invstd, sums, 1.0, act, pad, N, H, W, C, OH, OW, sh)
+                    if (dyv->ptr) {
+                        if (post == KP_POST_NONE) KP_BWD(KP_POST_NONE, 1);
+                        else if (post == KP_POST_POOL) KP_BWD(KP_POST_POOL, 1);
+                        else KP_BWD(KP_POST_UP, 1);
+                    } else {
+                        if (post == KP_POST_NONE) KP_BWD(KP_POST_NONE, 0);
+                        else if (post == KP_POST_POOL) KP_BWD(KP_POST_POOL, 0);
+                        else KP_BWD(KP_POST_UP, 0);
+                    }
+#undef KP_BWD
+                } else if (vec) {
                     Launch2D l = plan2d(P, C, 8);
                     bn_act_bwd_reduce_k<TG, TY, TD, 8><<<l.grid, l.block, 0, (cudaStream_t)stream>>>(
                         make_view<TG>(dout), make_view<TY>(y), make_view<TD>(dyv), scale, shift, mean, invstd, sums,
@@ -418,7 +679,16 @@ extern "C" int kp_bn_act_bwd_apply(kp_stream stream, const kp_view* dout, const 
                 using TG = decltype(tg);
                 using TY = decltype(ty);
                 using TD = decltype(td);
-                if (vec) {
+                if (vec && fast_ok(C, P * C)) {
+                    const long long rows = post == KP_POST_POOL ? (long long)N * ((H + 1) / 2) : (long long)N * H;
+                    const int g = rows_grid(rows), sh = ilog2(C / 8);
+                    cudaStream_t st = (cudaStream_t)stream;
+#define KP_APP(POSTV) bn_act_bwd_rows_k<TG, TY, TD, POSTV, 2><<<g, 256, 0, st>>>(make_view<TG>(dout), make_view<TY>(y), make_view<TD>(dy), scale, shift, mean, invstd, const_cast<double*>(sums), count, act, pad, N, H, W, C, OH, OW, sh)
+                    if (post == KP_POST_NONE) KP_APP(KP_POST_NONE);
+                    else if (post == KP_POST_POOL) KP_APP(KP_POST_POOL);
+                    else KP_APP(KP_POST_UP);
+#undef KP_APP
+                } else if (vec) {
                     Launch2D l = plan2d(P, C, 8);
                     bn_act_bwd_apply_k<TG, TY, TD, 8><<<l.grid, l.block, 0, (cudaStream_t)stream>>>(
                         make_view<TG>(dout), make_view<TY>(y), make_view<TD>(dy), scale, shift, mean, invstd, sums,

@@ -6,7 +6,7 @@ __global__ void adam_tick_k(int* step_dev) { *step_dev += 1; }
 
 __global__ void __launch_bounds__(256) adam_k(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                                               float* __restrict__ v, long long n, float lr, float b1, float b2,
-                                              float eps, float bc1, float bc2_sqrt, float gscale,
+                                              float eps, float bc1, float bc2_sqrt, float gscale, float omb1, float omb2,
                                               const int* __restrict__ step_dev) {
     if (step_dev) {   // CUDA-graph friendly: the step count lives on the device
         double t = (double)*step_dev;
@@ -15,8 +15,8 @@ __global__ void __launch_bounds__(256) adam_k(float* __restrict__ p, const float
     }
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
         float gi = g[i] * gscale;
-        float mi = b1 * m[i] + (1.f - b1) * gi;
-        float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+        float mi = b1 * m[i] + omb1 * gi;
+        float vi = b2 * v[i] + omb2 * gi * gi;
         m[i] = mi;
         v[i] = vi;
         float denom = sqrtf(vi) / bc2_sqrt + eps;
@@ -25,8 +25,8 @@ __global__ void __launch_bounds__(256) adam_k(float* __restrict__ p, const float
 }
 }  // namespace
 
-extern "C" int kp_adam_step(kp_stream stream, float* p, const float* g, float* m, float* v, int64_t n, float lr,
-                            float beta1, float beta2, float eps, int step, float grad_scale, int32_t* step_dev) {
+extern "C" int kp_adam_step(kp_stream stream, float* p, const float* g, float* m, float* v, int64_t n, double lr,
+                            double beta1, double beta2, double eps, int step, float grad_scale, int32_t* step_dev) {
     KP_CHECK_ARG(p && g && m && v && n > 0 && (step > 0 || step_dev), "kp_adam_step: bad arguments");
     if (step_dev) adam_tick_k<<<1, 1, 0, (cudaStream_t)stream>>>(step_dev);
     if (step <= 0) step = 1;
@@ -34,8 +34,9 @@ extern "C" int kp_adam_step(kp_stream stream, float* p, const float* g, float* m
     double bc2 = 1.0 - pow((double)beta2, (double)step);
     long long blocks = (n + 255) / 256;
     if (blocks > (long long)kp_sm_count() * 8) blocks = (long long)kp_sm_count() * 8;
-    adam_k<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(p, g, m, v, n, lr, beta1, beta2, eps, (float)bc1,
-                                                         (float)sqrt(bc2), grad_scale, step_dev);
+    adam_k<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(p, g, m, v, n, (float)lr, (float)beta1, (float)beta2, (float)eps, (float)bc1,
+                                                         (float)sqrt(bc2), grad_scale, (float)(1.0 - beta1),
+                                                         (float)(1.0 - beta2), step_dev);
     KP_LAUNCH_CHECK();
     return KP_OK;
 }

@@ -186,7 +186,7 @@ def unit_forward(specs: List[ConvSpec], params: List[LayerParams], x_pad: torch.
             sh = fshifts(s.k, PW)
             L.call('kp_conv_tc', st, L.ptr(cur), N * PH * PW, cinp, L.ptr(pk['tc_f']), len(sh), L.shifts_array(sh),
                    L.ptr(p.b), L.ptr(y), s.cout, L.ptr(stats), PH, PW, h, w,
-                   flops=2.0 * N * h * w * s.cin * s.cout * s.k * s.k)
+                   flops=2.0 * N * h * w * s.cin * s.cout * s.k * s.k, tag=f'{tag}{i} {s.cin}->{s.cout}@{h}x{w} k{s.k}')
         else:
             src = cur if s.k == 3 else cur[:, 1:, 1:, :]
             L.call('kp_conv_simt', st, L.view(src), L.ptr(pk['simt_f']), L.ptr(p.b), L.view(y[:, :h, :w, :]),
@@ -213,7 +213,7 @@ def unit_forward(specs: List[ConvSpec], params: List[LayerParams], x_pad: torch.
             nxt = alloc(f'{tag}.x{i + 1}', (N, oh + 2, ow + 2, cp), T, dev, zero=cp != s.cout)
             dst, pad = nxt[..., :s.cout], 1
         L.call('kp_bn_act_fwd', st, L.view(y[:, :h, :w, :]), L.view(dst), L.ptr(c.scale), L.ptr(c.shift), L.ACTS[s.act],
-               L.POSTS[s.post], pad, N, h, w, s.cout)
+               L.POSTS[s.post], pad, N, h, w, s.cout, tag=f'{tag}{i} {s.cin}->{s.cout}@{h}x{w} {s.post}')
         ctxs.append(c)
         if not last:
             cur, h, w = nxt, oh, ow
@@ -251,9 +251,11 @@ def unit_backward(specs: List[ConvSpec], params: List[LayerParams], grads: List[
             if c.mean is None:
                 raise NotImplementedError('backward through eval-mode BatchNorm is not supported')
             L.call('kp_bn_act_bwd_reduce', st, L.view(dout), L.view(yv), None, L.ptr(c.scale), L.ptr(c.shift),
-                   L.ptr(c.mean), L.ptr(c.invstd), L.ptr(sums), a, po, dout_pad, N, h, w, s.cout)
+                   L.ptr(c.mean), L.ptr(c.invstd), L.ptr(sums), a, po, dout_pad, N, h, w, s.cout,
+                   tag=f'{tag}{i} {s.cin}->{s.cout}@{h}x{w} {s.post}')
             L.call('kp_bn_act_bwd_apply', st, L.view(dout), L.view(yv), L.view(dy_int), L.ptr(c.scale), L.ptr(c.shift),
-                   L.ptr(c.mean), L.ptr(c.invstd), L.ptr(sums), float(N * h * w), a, po, dout_pad, N, h, w, s.cout)
+                   L.ptr(c.mean), L.ptr(c.invstd), L.ptr(sums), float(N * h * w), a, po, dout_pad, N, h, w, s.cout,
+                   tag=f'{tag}{i} {s.cin}->{s.cout}@{h}x{w} {s.post}')
             L.call('kp_bn_grad_finalize', st, L.ptr(sums), s.cout, L.ptr(g.dgamma), L.ptr(g.dbeta))
             # the bias of a conv feeding train-mode BatchNorm has an exactly zero gradient
         else:
@@ -267,11 +269,11 @@ def unit_backward(specs: List[ConvSpec], params: List[LayerParams], grads: List[
             stg = alloc(f'{tag}.stg', (max(sp.k * sp.k * sp.cout * cx.x.shape[3] for sp, cx in zip(specs, ctxs) if cx.tc),),
                         torch.float32, dev)
             L.call('kp_conv_wgrad_tc', st, L.ptr(c.x), L.ptr(dyp), Q, s.cin, cinp, s.cout, len(sh), L.shifts_array(sh),
-                   L.ptr(stg), L.ptr(g.dw), flops=2.0 * N * h * w * s.cin * s.cout * s.k * s.k)
+                   L.ptr(stg), L.ptr(g.dw), flops=2.0 * N * h * w * s.cin * s.cout * s.k * s.k, tag=f'{tag}{i} {s.cin}->{s.cout}@{h}x{w} k{s.k}')
             if want_dx:
                 dx = alloc(f'{tag}.dx{i}', (N, PH, PW, cinp), T, dev)
                 L.call('kp_conv_tc', st, L.ptr(dyp), Q, s.cout, L.ptr(c.pack['tc_d']), len(sh), L.shifts_array(sh), None,
-                       L.ptr(dx), cinp, None, PH, PW, PH, PW, flops=2.0 * N * h * w * s.cin * s.cout * s.k * s.k)
+                       L.ptr(dx), cinp, None, PH, PW, PH, PW, flops=2.0 * N * h * w * s.cin * s.cout * s.k * s.k, tag=f'{tag}{i} {s.cin}->{s.cout}@{h}x{w} k{s.k}')
         else:
             src = c.x if s.k == 3 else c.x[:, 1:, 1:, :]
             L.call('kp_conv_wgrad_simt', st, L.view(src), L.view(dy_int), L.ptr(g.dw), N, h, w, s.cin, s.cout, s.k)

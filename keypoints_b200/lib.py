@@ -56,7 +56,7 @@ SIGNATURES = {
     'kp_l2_loss': [_P, _P, _P, _P, _L, _F, _P, _P],
     'kp_tps_warp': [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I],
     'kp_rotate_warp': [_P, _P, _P, _P, _I, _I, _I, _I],
-    'kp_adam_step': [_P, _P, _P, _P, _P, _L, _F, _F, _F, _F, _I, _F, _P],
+    'kp_adam_step': [_P, _P, _P, _P, _P, _L, _D, _D, _D, _D, _I, _F, _P],
 }
 EXPORTS = sorted(list(SIGNATURES) + ['kp_last_error', 'kp_version'])
 
@@ -87,7 +87,7 @@ def load():
 timing = None         # when a list: (name, flops, start_event, end_event) per call (bench.py roofline leg)
 
 
-def call(name, *args, flops=0.0):
+def call(name, *args, flops=0.0, tag=''):
     global launches
     lib = load()
     if timing is not None:
@@ -98,7 +98,7 @@ def call(name, *args, flops=0.0):
         raise KpError(f'{name} failed ({rc}): {lib.kp_last_error().decode()}')
     if timing is not None:
         e1.record()
-        timing.append((name, flops, e0, e1))
+        timing.append((name, flops, e0, e1, tag))
     launches += 1
 
 

@@ -13,7 +13,7 @@ from typing import Optional
 
 import torch
 
-from . import engine, lib as L
+from . import engine, lib as L, parallel
 from .engine import CachedAlloc, LayerGrads, LayerParams
 from .models import knn
 from .models.keynet import KeyNet
@@ -256,13 +256,7 @@ class Trainer:
         """Sum all-reduce of the gradient buckets over NCCL/NVLink (gloo in the CPU tests)."""
         if self.world == 1:
             return
-        works = []
-        for u in self.units.values():
-            a, b = u.span
-            works.append(torch.distributed.all_reduce(self.flat_g[a:b], op=torch.distributed.ReduceOp.SUM, group=self.pg,
-                                                      async_op=True))
-        for wk in works:
-            wk.wait()
+        parallel.wait_all(parallel.allreduce_buckets(self.flat_g, [u.span for u in self.units.values()], self.pg))
 
     def _adam(self):
         L.call('kp_adam_step', L.stream(), L.ptr(self.flat_p), L.ptr(self.flat_g), L.ptr(self.flat_m), L.ptr(self.flat_v),
