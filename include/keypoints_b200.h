@@ -118,20 +118,19 @@ int kp_bn_finalize(kp_stream stream, const double* stats, int C, double count, c
 int kp_bn_act_fwd(kp_stream stream, const kp_view* y, const kp_view* out, const float* scale,
                   const float* shift, int act, int post, int pad, int N, int H, int W, int C);
 
-/* Backward of the above.  dout: gradient w.r.t. `out` (ptr at the padded origin if pad=1: border
+/* Backward of the above, two passes.  dout: gradient w.r.t. `out` (ptr at the padded origin if pad=1: border
  * gradients are folded into the edge pixels = replication_pad2d backward).
- * Pass 1 (reduce): sums[0:C] += sum dz, sums[C:2C] += sum dz * xhat (double).  If dy is non-NULL
- * (layers without BatchNorm) pass 1 also writes dy = dz and pass 2 is not needed.
- * Pass 2 (apply): dy = scale * (dz - sums[0]/count - xhat * sums[1]/count); dgamma = sums[1],
- * dbeta = sums[0] are written by kp_bn_grad_finalize. */
+ * Pass 1 (reduce): dz = d/d(BatchNorm output) — fold + pool/upsample backward + activation backward — is written to
+ * dy (nullable), and sums[0:C] += sum dz, sums[C:2C] += sum dz * xhat (double).  For layers without BatchNorm
+ * (scale/shift/mean/invstd NULL) dy is the final gradient and sums[0:C] the bias gradient.
+ * Pass 2 (apply, BatchNorm only), in place: dy = scale * (dy - sums[0]/count - xhat * sums[1]/count). */
 int kp_bn_act_bwd_reduce(kp_stream stream, const kp_view* dout, const kp_view* y, const kp_view* dy,
                          const float* scale, const float* shift, const float* mean,
                          const float* invstd, double* sums, int act, int post, int pad, int N,
                          int H, int W, int C);
-int kp_bn_act_bwd_apply(kp_stream stream, const kp_view* dout, const kp_view* y, const kp_view* dy,
-                        const float* scale, const float* shift, const float* mean,
-                        const float* invstd, const double* sums, double count, int act, int post,
-                        int pad, int N, int H, int W, int C);
+int kp_bn_act_bwd_apply(kp_stream stream, const kp_view* y, const kp_view* dy, const float* scale,
+                        const float* mean, const float* invstd, const double* sums, double count,
+                        int N, int H, int W, int C);
 /* dgamma[c] = sums[C+c], dbeta[c] = sums[c] (any nullable; fp32, overwritten). */
 int kp_bn_grad_finalize(kp_stream stream, const double* sums, int C, float* dgamma, float* dbeta);
 

@@ -57,6 +57,13 @@ template <typename T> struct Vec<T, 1> {
     static __device__ __forceinline__ void store(T* p, const float (&f)[1]) { from_f(p, f[0]); }
 };
 template <> struct Vec<float, 8> {
+    struct Raw { float4 a, b; };
+    static __device__ __forceinline__ Raw load_raw(const float* p) {
+        Raw r; r.a = *reinterpret_cast<const float4*>(p); r.b = *reinterpret_cast<const float4*>(p + 4); return r;
+    }
+    static __device__ __forceinline__ void unpack(const Raw& r, float (&f)[8]) {
+        f[0] = r.a.x; f[1] = r.a.y; f[2] = r.a.z; f[3] = r.a.w; f[4] = r.b.x; f[5] = r.b.y; f[6] = r.b.z; f[7] = r.b.w;
+    }
     static __device__ __forceinline__ void load(const float* p, float (&f)[8]) {
         float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
         f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
@@ -67,6 +74,13 @@ template <> struct Vec<float, 8> {
     }
 };
 template <> struct Vec<bf16, 8> {
+    struct Raw { uint4 a; };
+    static __device__ __forceinline__ Raw load_raw(const bf16* p) { Raw r; r.a = *reinterpret_cast<const uint4*>(p); return r; }
+    static __device__ __forceinline__ void unpack(const Raw& r, float (&f)[8]) {
+        const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&r.a);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { float2 t = __bfloat1622float2(h[i]); f[2 * i] = t.x; f[2 * i + 1] = t.y; }
+    }
     static __device__ __forceinline__ void load(const bf16* p, float (&f)[8]) {
         uint4 u = *reinterpret_cast<const uint4*>(p);
         const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);

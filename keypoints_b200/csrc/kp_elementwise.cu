@@ -281,45 +281,15 @@ bn_act_bwd_reduce_k(View<TG> dout, View<TY> y, View<TD> dy, const float* __restr
     }
 }
 
-template <typename TG, typename TY, typename TD, int V>
-__global__ void __launch_bounds__(256)
-bn_act_bwd_apply_k(View<TG> dout, View<TY> y, View<TD> dy, const float* __restrict__ scale,
-                   const float* __restrict__ shift, const float* __restrict__ mean,
-                   const float* __restrict__ invstd, const double* __restrict__ sums, double count, int act,
-                   int post, int pad, int N, int H, int W, int C, int OH, int OW) {
-    const int c0 = (blockIdx.y * blockDim.x + threadIdx.x) * V;
-    if (c0 >= C) return;
-    float sc[V], sh[V], mu[V], is[V], m1[V], m2[V];
-#pragma unroll
-    for (int i = 0; i < V; ++i) {
-        sc[i] = scale[c0 + i]; sh[i] = shift[c0 + i]; mu[i] = mean[c0 + i]; is[i] = invstd[c0 + i];
-        m1[i] = (float)(sums[c0 + i] / count);
-        m2[i] = (float)(sums[C + c0 + i] / count);
-    }
-    const long long P = (long long)N * H * W;
-    const float ry = (OH > 1) ? (float)(H - 1) / (float)(OH - 1) : 0.f;
-    const float rx = (OW > 1) ? (float)(W - 1) / (float)(OW - 1) : 0.f;
-    for (long long p = (long long)blockIdx.x * blockDim.y + threadIdx.y; p < P; p += (long long)gridDim.x * blockDim.y) {
-        int xx = (int)(p % W);
-        long long r = p / W;
-        int yy = (int)(r % H);
-        int n = (int)(r / H);
-        float g[V], yv[V];
-        compute_dz<TG, TY, V>(dout, y, sc, sh, act, post, pad, n, yy, xx, c0, H, W, OH, OW, ry, rx, g, yv);
-#pragma unroll
-        for (int i = 0; i < V; ++i) g[i] = sc[i] * (g[i] - m1[i] - (yv[i] - mu[i]) * is[i] * m2[i]);
-        Vec<TD, V>::store(dy.at(n, yy, xx, c0), g);
-    }
-}
-
-
 // ================================================================================================
 // Fast path: NHWC with unit channel stride, 8 channels (16 bytes) per thread, C/8 a power of two <= 256.
 // One block walks whole image rows: 32-bit index math only, the channel group of a thread is fixed (so the
 // per-channel affine lives in registers and the reductions accumulate in registers), consecutive threads
-// touch consecutive 16-byte chunks of the row.
+// touch consecutive 16-byte chunks of a row, and the inner loops are unrolled x4 with every load issued
+// before the first use so each thread keeps 4-10 independent 16-byte requests in flight.
 // ================================================================================================
 constexpr int V8 = 8;
+constexpr int UNR = 4;
 
 struct RowFold {   // rows / columns of a replicate-padded gradient that fold into one unpadded coordinate
     int n, v[3];
@@ -343,10 +313,19 @@ __device__ __forceinline__ void fold_acc(const View<TG>& d, int n, const RowFold
         }
 }
 
+template <typename T>
+__device__ __forceinline__ void raw_act(const typename Vec<T, V8>::Raw& r, const float (&sc)[V8], const float (&sh)[V8],
+                                        int act, float (&v)[V8]) {
+    Vec<T, V8>::unpack(r, v);
+#pragma unroll
+    for (int i = 0; i < V8; ++i) v[i] = apply_act(fmaf(v[i], sc[i], sh[i]), act);
+}
+
 template <typename TI, typename TO, int POST>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 2)
 bn_act_fwd_rows_k(View<TI> y, View<TO> out, const float* __restrict__ scale, const float* __restrict__ shift, int act,
                   int pad, int N, int H, int W, int C, int OH, int OW, int cg_shift) {
+    using RawI = typename Vec<TI, V8>::Raw;
     const int ncg = C >> 3;
     const int cg = threadIdx.x & (ncg - 1), c0 = cg * V8;
     const int x0 = threadIdx.x >> cg_shift, xstep = 256 >> cg_shift;
@@ -359,50 +338,71 @@ bn_act_fwd_rows_k(View<TI> y, View<TO> out, const float* __restrict__ scale, con
     for (int row = blockIdx.x; row < rows; row += gridDim.x) {
         const int n = row / PH, py = row - n * PH;
         const int oy = min(max(py - pad, 0), OH - 1);
-        int y0 = 0, y1 = 0;
+        int ya = oy, yb = oy;
         float ly = 0.f;
+        if (POST == KP_POST_POOL) { ya = 2 * oy; yb = 2 * oy + 1; }
         if (POST == KP_POST_UP) {
             float sy = ry * oy;
-            y0 = (int)sy; ly = sy - y0; y1 = min(y0 + 1, H - 1);
+            ya = (int)sy; ly = sy - ya; yb = min(ya + 1, H - 1);
         }
-        for (int px = x0; px < PW; px += xstep) {
-            const int ox = min(max(px - pad, 0), OW - 1);
-            float v[V8];
-            if (POST == KP_POST_NONE) {
-                load_act<TI, V8>(y, n, oy, ox, c0, sc, sh, act, v);
-            } else if (POST == KP_POST_POOL) {
-                float a[V8], b[V8], c[V8];
-                load_act<TI, V8>(y, n, 2 * oy, 2 * ox, c0, sc, sh, act, v);
-                load_act<TI, V8>(y, n, 2 * oy, 2 * ox + 1, c0, sc, sh, act, a);
-                load_act<TI, V8>(y, n, 2 * oy + 1, 2 * ox, c0, sc, sh, act, b);
-                load_act<TI, V8>(y, n, 2 * oy + 1, 2 * ox + 1, c0, sc, sh, act, c);
+        for (int pxb = x0; pxb < PW; pxb += UNR * xstep) {
+            RawI r[UNR][POST == KP_POST_NONE ? 1 : 4];
+            float lx[UNR];
 #pragma unroll
-                for (int i = 0; i < V8; ++i) v[i] = fmaxf(fmaxf(v[i], a[i]), fmaxf(b[i], c[i]));
-            } else {
-                float sx = rx * ox;
-                int xa = (int)sx;
-                float lx = sx - xa;
-                int xb = min(xa + 1, W - 1);
-                float a00[V8], a01[V8], a10[V8], a11[V8];
-                load_act<TI, V8>(y, n, y0, xa, c0, sc, sh, act, a00);
-                load_act<TI, V8>(y, n, y0, xb, c0, sc, sh, act, a01);
-                load_act<TI, V8>(y, n, y1, xa, c0, sc, sh, act, a10);
-                load_act<TI, V8>(y, n, y1, xb, c0, sc, sh, act, a11);
-#pragma unroll
-                for (int i = 0; i < V8; ++i)
-                    v[i] = (1.f - ly) * ((1.f - lx) * a00[i] + lx * a01[i]) + ly * ((1.f - lx) * a10[i] + lx * a11[i]);
+            for (int j = 0; j < UNR; ++j) {
+                const int px = pxb + j * xstep;
+                if (px < PW) {
+                    const int ox = min(max(px - pad, 0), OW - 1);
+                    if (POST == KP_POST_NONE) {
+                        r[j][0] = Vec<TI, V8>::load_raw(y.at(n, oy, ox, c0));
+                    } else {
+                        int xa, xb;
+                        if (POST == KP_POST_POOL) { xa = 2 * ox; xb = 2 * ox + 1; lx[j] = 0.f; }
+                        else { float sx = rx * ox; xa = (int)sx; lx[j] = sx - xa; xb = min(xa + 1, W - 1); }
+                        r[j][0] = Vec<TI, V8>::load_raw(y.at(n, ya, xa, c0));
+                        r[j][1] = Vec<TI, V8>::load_raw(y.at(n, ya, xb, c0));
+                        r[j][2] = Vec<TI, V8>::load_raw(y.at(n, yb, xa, c0));
+                        r[j][3] = Vec<TI, V8>::load_raw(y.at(n, yb, xb, c0));
+                    }
+                }
             }
-            Vec<TO, V8>::store(out.at(n, py, px, c0), v);
+#pragma unroll
+            for (int j = 0; j < UNR; ++j) {
+                const int px = pxb + j * xstep;
+                if (px < PW) {
+                    float v[V8];
+                    raw_act<TI>(r[j][0], sc, sh, act, v);
+                    if (POST != KP_POST_NONE) {
+                        float a[V8], b[V8], c[V8];
+                        raw_act<TI>(r[j][1], sc, sh, act, a);
+                        raw_act<TI>(r[j][2], sc, sh, act, b);
+                        raw_act<TI>(r[j][3], sc, sh, act, c);
+                        if (POST == KP_POST_POOL) {
+#pragma unroll
+                            for (int i = 0; i < V8; ++i) v[i] = fmaxf(fmaxf(v[i], a[i]), fmaxf(b[i], c[i]));
+                        } else {
+                            const float l = lx[j];
+#pragma unroll
+                            for (int i = 0; i < V8; ++i)
+                                v[i] = (1.f - ly) * ((1.f - l) * v[i] + l * a[i]) + ly * ((1.f - l) * b[i] + l * c[i]);
+                        }
+                    }
+                    Vec<TO, V8>::store(out.at(n, py, px, c0), v);
+                }
+            }
         }
     }
 }
 
-// MODE 0: reduce only (BatchNorm pass 1)   MODE 1: reduce + write dy = dz (no BatchNorm)   MODE 2: apply (pass 2)
-template <typename TG, typename TY, typename TD, int POST, int MODE>
-__global__ void __launch_bounds__(256)
+// Backward pass 1: dz = gradient w.r.t. the BatchNorm output (replicate-pad fold + pool/upsample backward +
+// activation backward), written to dy; per-channel sums of dz and dz*xhat accumulated.
+template <typename TG, typename TY, typename TD, int POST>
+__global__ void __launch_bounds__(256, 2)
 bn_act_bwd_rows_k(View<TG> dout, View<TY> y, View<TD> dy, const float* __restrict__ scale,
                   const float* __restrict__ shift, const float* __restrict__ mean, const float* __restrict__ invstd,
-                  double* sums, double count, int act, int pad, int N, int H, int W, int C, int OH, int OW, int cg_shift) {
+                  double* sums, int act, int pad, int N, int H, int W, int C, int OH, int OW, int cg_shift) {
+    using RawG = typename Vec<TG, V8>::Raw;
+    using RawY = typename Vec<TY, V8>::Raw;
     __shared__ float red[2][256 * V8];
     const int ncg = C >> 3;
     const int cg = threadIdx.x & (ncg - 1), c0 = cg * V8;
@@ -412,24 +412,19 @@ bn_act_bwd_rows_k(View<TG> dout, View<TY> y, View<TD> dy, const float* __restric
     for (int i = 0; i < V8; ++i) {
         sc[i] = scale ? scale[c0 + i] : 1.f; sh[i] = shift ? shift[c0 + i] : 0.f;
         mu[i] = mean ? mean[c0 + i] : 0.f; is[i] = invstd ? invstd[c0 + i] : 1.f;
-        if (MODE == 2) { s1[i] = (float)(sums[c0 + i] / count); s2[i] = (float)(sums[C + c0 + i] / count); }
-        else { s1[i] = 0.f; s2[i] = 0.f; }
+        s1[i] = 0.f; s2[i] = 0.f;
     }
     const float ry = (OH > 1) ? (float)(H - 1) / (float)(OH - 1) : 0.f;
     const float rx = (OW > 1) ? (float)(W - 1) / (float)(OW - 1) : 0.f;
     // consume one element: g = gradient w.r.t. the activation output, yv = raw conv output
     auto emit = [&](int n, int yy, int xx, float (&g)[V8], const float (&yv)[V8]) {
 #pragma unroll
-        for (int i = 0; i < V8; ++i) g[i] *= act_grad(fmaf(yv[i], sc[i], sh[i]), act);
-        if (MODE == 2) {
-#pragma unroll
-            for (int i = 0; i < V8; ++i) g[i] = sc[i] * (g[i] - s1[i] - (yv[i] - mu[i]) * is[i] * s2[i]);
-            Vec<TD, V8>::store(dy.at(n, yy, xx, c0), g);
-        } else {
-#pragma unroll
-            for (int i = 0; i < V8; ++i) { s1[i] += g[i]; s2[i] += g[i] * (yv[i] - mu[i]) * is[i]; }
-            if (MODE == 1) Vec<TD, V8>::store(dy.at(n, yy, xx, c0), g);
+        for (int i = 0; i < V8; ++i) {
+            g[i] *= act_grad(fmaf(yv[i], sc[i], sh[i]), act);
+            s1[i] += g[i];
+            s2[i] = fmaf(g[i], (yv[i] - mu[i]) * is[i], s2[i]);
         }
+        if (dy.p) Vec<TD, V8>::store(dy.at(n, yy, xx, c0), g);
     };
     if (POST == KP_POST_POOL) {
         const int HW2 = (H + 1) >> 1, WW2 = (W + 1) >> 1, rows = N * HW2;
@@ -439,19 +434,30 @@ bn_act_bwd_rows_k(View<TG> dout, View<TY> y, View<TD> dy, const float* __restric
             for (int wi = x0; wi < WW2; wi += xstep) {
                 const int wx = wi * 2;
                 const bool full = (wy + 1 < H) && (wx + 1 < W);
+                RawY ry4[4];
                 float yv[4][V8], best[V8], t[V8];
                 int bi[V8];
+                bool ok[4];
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
                     const int yy = wy + (q >> 1), xx = wx + (q & 1);
-                    if (yy < H && xx < W) Vec<TY, V8>::load(y.at(n, yy, xx, c0), yv[q]);
+                    ok[q] = yy < H && xx < W;
+                    if (ok[q]) ry4[q] = Vec<TY, V8>::load_raw(y.at(n, yy, xx, c0));
+                }
+#pragma unroll
+                for (int i = 0; i < V8; ++i) { best[i] = -INFINITY; bi[i] = 0; t[i] = 0.f; }
+                if (full) {
+                    const RowFold fx(wx >> 1, OW, pad);
+                    fold_acc<TG>(dout, n, fy, fx, c0, 1.f, t);
+                }
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    if (ok[q]) Vec<TY, V8>::unpack(ry4[q], yv[q]);
                     else {
 #pragma unroll
                         for (int i = 0; i < V8; ++i) yv[q][i] = 0.f;
                     }
                 }
-#pragma unroll
-                for (int i = 0; i < V8; ++i) { best[i] = -INFINITY; bi[i] = 0; t[i] = 0.f; }
                 if (full) {
 #pragma unroll
                     for (int q = 0; q < 4; ++q)
@@ -460,84 +466,379 @@ bn_act_bwd_rows_k(View<TG> dout, View<TY> y, View<TD> dy, const float* __restric
                             float a = apply_act(fmaf(yv[q][i], sc[i], sh[i]), act);
                             if (a > best[i] || q == 0) { best[i] = a; bi[i] = q; }      // first maximum wins
                         }
-                    const RowFold fx(wx >> 1, OW, pad);
-                    fold_acc<TG>(dout, n, fy, fx, c0, 1.f, t);
                 }
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
-                    const int yy = wy + (q >> 1), xx = wx + (q & 1);
-                    if (yy < H && xx < W) {
+                    if (ok[q]) {
                         float g[V8];
 #pragma unroll
                         for (int i = 0; i < V8; ++i) g[i] = (full && bi[i] == q) ? t[i] : 0.f;
-                        emit(n, yy, xx, g, yv[q]);
+                        emit(n, wy + (q >> 1), wx + (q & 1), g, yv[q]);
                     }
                 }
             }
         }
-    } else {
+    } else if (POST == KP_POST_NONE) {
         const int rows = N * H;
         for (int row = blockIdx.x; row < rows; row += gridDim.x) {
             const int n = row / H, yy = row - n * H;
-            if (POST == KP_POST_NONE) {
-                const RowFold fy(yy, OH, pad);
-                for (int xx = x0; xx < W; xx += xstep) {
-                    float g[V8], yv[V8];
+            const RowFold fy(yy, OH, pad);
+            for (int xb = x0; xb < W; xb += UNR * xstep) {
+                RawG rg[UNR];
+                RawY ryv[UNR];
 #pragma unroll
-                    for (int i = 0; i < V8; ++i) g[i] = 0.f;
-                    const RowFold fx(xx, OW, pad);
-                    fold_acc<TG>(dout, n, fy, fx, c0, 1.f, g);
-                    Vec<TY, V8>::load(y.at(n, yy, xx, c0), yv);
-                    emit(n, yy, xx, g, yv);
-                }
-            } else {   // bilinear x2 (align_corners=True) backward: gather the <= 4x4 outputs that read (yy,xx)
-                int ylo = 0, yhi = OH - 1;
-                if (H > 1) { ylo = max(0, 2 * yy - 2); yhi = min(OH - 1, 2 * yy + 3); }
-                for (int xx = x0; xx < W; xx += xstep) {
-                    int xlo = 0, xhi = OW - 1;
-                    if (W > 1) { xlo = max(0, 2 * xx - 2); xhi = min(OW - 1, 2 * xx + 3); }
-                    float g[V8], yv[V8];
-#pragma unroll
-                    for (int i = 0; i < V8; ++i) g[i] = 0.f;
-                    for (int Y = ylo; Y <= yhi; ++Y) {
-                        float sy = ry * Y;
-                        int ya = (int)sy;
-                        float ly = sy - ya;
-                        int yb = min(ya + 1, H - 1);
-                        float wyv = (ya == yy ? 1.f - ly : 0.f) + (yb == yy ? ly : 0.f);
-                        if (wyv == 0.f) continue;
-                        const RowFold fy(Y, OH, pad);
-                        for (int X = xlo; X <= xhi; ++X) {
-                            float sx = rx * X;
-                            int xa = (int)sx;
-                            float lx = sx - xa;
-                            int xb = min(xa + 1, W - 1);
-                            float wxv = (xa == xx ? 1.f - lx : 0.f) + (xb == xx ? lx : 0.f);
-                            if (wxv == 0.f) continue;
-                            const RowFold fx(X, OW, pad);
-                            fold_acc<TG>(dout, n, fy, fx, c0, wyv * wxv, g);
-                        }
+                for (int j = 0; j < UNR; ++j) {
+                    const int xx = xb + j * xstep;
+                    if (xx < W) {
+                        rg[j] = Vec<TG, V8>::load_raw(dout.at(n, fy.v[0], xx + pad, c0));
+                        ryv[j] = Vec<TY, V8>::load_raw(y.at(n, yy, xx, c0));
                     }
-                    Vec<TY, V8>::load(y.at(n, yy, xx, c0), yv);
-                    emit(n, yy, xx, g, yv);
+                }
+#pragma unroll
+                for (int j = 0; j < UNR; ++j) {
+                    const int xx = xb + j * xstep;
+                    if (xx < W) {
+                        float g[V8], yv[V8];
+                        Vec<TG, V8>::unpack(rg[j], g);
+                        Vec<TY, V8>::unpack(ryv[j], yv);
+                        if (pad && (fy.n > 1 || xx == 0 || xx == W - 1)) {      // border pixel: add the folded copies
+                            const RowFold fx(xx, OW, pad);
+                            float t[V8];
+                            for (int a = 0; a < fy.n; ++a)
+                                for (int b = 0; b < fx.n; ++b) {
+                                    if (a == 0 && b == 0) continue;
+                                    Vec<TG, V8>::load(dout.at(n, fy.v[a], fx.v[b], c0), t);
+#pragma unroll
+                                    for (int i = 0; i < V8; ++i) g[i] += t[i];
+                                }
+                        }
+                        emit(n, yy, xx, g, yv);
+                    }
+                }
+            }
+        }
+    } else {   // bilinear x2 (align_corners=True) backward: gather the <= 4x4 outputs that read (yy,xx)
+        const int rows = N * H;
+        for (int row = blockIdx.x; row < rows; row += gridDim.x) {
+            const int n = row / H, yy = row - n * H;
+            int ylo = 0, yhi = OH - 1;
+            if (H > 1) { ylo = max(0, 2 * yy - 2); yhi = min(OH - 1, 2 * yy + 3); }
+            for (int xx = x0; xx < W; xx += xstep) {
+                int xlo = 0, xhi = OW - 1;
+                if (W > 1) { xlo = max(0, 2 * xx - 2); xhi = min(OW - 1, 2 * xx + 3); }
+                const RawY ryv = Vec<TY, V8>::load_raw(y.at(n, yy, xx, c0));
+                // horizontal taps first (at most 6 candidates, <= 4 non-zero), kept in registers
+                float wxs[6];
+                int nx = 0, xsel[6];
+                for (int X = xlo; X <= xhi; ++X) {
+                    float sx = rx * X;
+                    int xa = (int)sx;
+                    float lx = sx - xa;
+                    int xb = min(xa + 1, W - 1);
+                    float wv = (xa == xx ? 1.f - lx : 0.f) + (xb == xx ? lx : 0.f);
+                    if (wv != 0.f && nx < 6) { wxs[nx] = wv; xsel[nx] = X; ++nx; }
+                }
+                float g[V8], yv[V8];
+#pragma unroll
+                for (int i = 0; i < V8; ++i) g[i] = 0.f;
+                for (int Y = ylo; Y <= yhi; ++Y) {
+                    float sy = ry * Y;
+                    int ya = (int)sy;
+                    float ly = sy - ya;
+                    int yb = min(ya + 1, H - 1);
+                    float wyv = (ya == yy ? 1.f - ly : 0.f) + (yb == yy ? ly : 0.f);
+                    if (wyv == 0.f) continue;
+                    const RowFold fy(Y, OH, pad);
+                    for (int k = 0; k < nx; ++k) {
+                        const RowFold fx(xsel[k], OW, pad);
+                        fold_acc<TG>(dout, n, fy, fx, c0, wyv * wxs[k], g);
+                    }
+                }
+                Vec<TY, V8>::unpack(ryv, yv);
+                emit(n, yy, xx, g, yv);
+            }
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < V8; ++i) { red[0][threadIdx.x * V8 + i] = s1[i]; red[1][threadIdx.x * V8 + i] = s2[i]; }
+    __syncthreads();
+    // one channel per thread: sum over the 256/ncg threads that share its channel group
+    for (int ch = threadIdx.x; ch < C; ch += 256) {
+        const int g8 = ch >> 3, i = ch & 7;
+        float a = 0.f, b = 0.f;
+        for (int t = g8; t < 256; t += ncg) { a += red[0][t * V8 + i]; b += red[1][t * V8 + i]; }
+        atomicAdd(&sums[ch], (double)a);
+        atomicAdd(&sums[C + ch], (double)b);
+    }
+}
+
+// Backward pass 2 (BatchNorm only), in place: dy = scale * (dz - mean(dz) - xhat * mean(dz * xhat))
+template <typename TY, typename TD>
+__global__ void __launch_bounds__(256, 2)
+bn_bwd_apply_rows_k(View<TY> y, View<TD> dy, const float* __restrict__ scale, const float* __restrict__ mean,
+                    const float* __restrict__ invstd, const double* __restrict__ sums, double count, int N, int H, int W,
+                    int C, int cg_shift) {
+    using RawY = typename Vec<TY, V8>::Raw;
+    using RawD = typename Vec<TD, V8>::Raw;
+    const int ncg = C >> 3;
+    const int cg = threadIdx.x & (ncg - 1), c0 = cg * V8;
+    const int x0 = threadIdx.x >> cg_shift, xstep = 256 >> cg_shift;
+    float a0[V8], a1[V8], a2[V8];      // dy = a0*dz + a1*y + a2
+#pragma unroll
+    for (int i = 0; i < V8; ++i) {
+        const float sc = scale[c0 + i], mu = mean[c0 + i], is = invstd[c0 + i];
+        const float m1 = (float)(sums[c0 + i] / count), m2 = (float)(sums[C + c0 + i] / count);
+        a0[i] = sc;
+        a1[i] = -sc * is * m2;
+        a2[i] = -sc * m1 + sc * is * m2 * mu;
+    }
+    const int rows = N * H;
+    for (int row = blockIdx.x; row < rows; row += gridDim.x) {
+        const int n = row / H, yy = row - n * H;
+        for (int xb = x0; xb < W; xb += UNR * xstep) {
+            RawY ryv[UNR];
+            RawD rd[UNR];
+#pragma unroll
+            for (int j = 0; j < UNR; ++j) {
+                const int xx = xb + j * xstep;
+                if (xx < W) {
+                    ryv[j] = Vec<TY, V8>::load_raw(y.at(n, yy, xx, c0));
+                    rd[j] = Vec<TD, V8>::load_raw(dy.at(n, yy, xx, c0));
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < UNR; ++j) {
+                const int xx = xb + j * xstep;
+                if (xx < W) {
+                    float g[V8], yv[V8];
+                    Vec<TD, V8>::unpack(rd[j], g);
+                    Vec<TY, V8>::unpack(ryv[j], yv);
+#pragma unroll
+                    for (int i = 0; i < V8; ++i) g[i] = fmaf(a0[i], g[i], fmaf(a1[i], yv[i], a2[i]));
+                    Vec<TD, V8>::store(dy.at(n, yy, xx, c0), g);
                 }
             }
         }
     }
-    if (MODE != 2) {
+}
+
+// generic (any strides / channel count) version of pass 2
+template <typename TY, typename TD>
+__global__ void bn_bwd_apply_generic_k(View<TY> y, View<TD> dy, const float* __restrict__ scale,
+                                       const float* __restrict__ mean, const float* __restrict__ invstd,
+                                       const double* __restrict__ sums, double count, int N, int H, int W, int C) {
+    const long long total = (long long)N * H * W * C;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        int c = (int)(i % C);
+        long long p = i / C;
+        int xx = (int)(p % W);
+        long long r = p / W;
+        int yy = (int)(r % H);
+        int n = (int)(r / H);
+        float dz = to_f(*dy.at(n, yy, xx, c)), yv = to_f(*y.at(n, yy, xx, c));
+        float m1 = (float)(sums[c] / count), m2 = (float)(sums[C + c] / count);
+        from_f(dy.at(n, yy, xx, c), scale[c] * (dz - m1 - (yv - mean[c]) * invstd[c] * m2));
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Bilinear x2 (align_corners=True) specialisations.  Forward: one thread produces a 2x2 output quad from the
+// 3x3 input neighbourhood it needs, so BatchNorm + activation run 9 (not 16) times per 4 outputs.  Backward: one
+// thread gathers the 4x4 outputs that read its input pixel with all 16 loads issued up front; only pixels whose
+// gather touches the replicate-padded border take the slow folding path.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float actf(float z, float slope) { return fmaxf(z, slope * z); }
+
+template <typename TI, typename TO>
+__global__ void __launch_bounds__(256, 2)
+bn_act_fwd_up_quad_k(View<TI> y, View<TO> out, const float* __restrict__ scale, const float* __restrict__ shift,
+                     float slope, int pad, int N, int H, int W, int C, int cg_shift) {
+    // Outputs (2k, 2k+1) x (2j, 2j+1).  With src = r * dst, r = (H-1)/(2H-1): floor(r*2k) = k-1 (k >= 1) and
+    // floor(r*(2k+1)) = k, so output row 2k blends input rows (k-1, k) and row 2k+1 blends (k, k+1): a fixed
+    // 3x3 window, no index selects.  The fractions come from the same float formula PyTorch uses.
+    using RawI = typename Vec<TI, V8>::Raw;
+    const int OH = 2 * H, OW = 2 * W;
+    const int ncg = C >> 3;
+    const int cg = threadIdx.x & (ncg - 1), c0 = cg * V8;
+    const int x0 = threadIdx.x >> cg_shift, xstep = 256 >> cg_shift;
+    float sc[V8], sh[V8];
 #pragma unroll
-        for (int i = 0; i < V8; ++i) { red[0][threadIdx.x * V8 + i] = s1[i]; red[1][threadIdx.x * V8 + i] = s2[i]; }
-        __syncthreads();
-        // threads 0 .. C-1: one channel each, sum over the 256/ncg threads that share its channel group
-        for (int ch = threadIdx.x; ch < C; ch += 256) {
-            const int g8 = ch >> 3, i = ch & 7;
-            float a = 0.f, b = 0.f;
-            for (int t = g8; t < 256; t += ncg) { a += red[0][t * V8 + i]; b += red[1][t * V8 + i]; }
-            atomicAdd(&sums[ch], (double)a);
-            atomicAdd(&sums[C + ch], (double)b);
+    for (int i = 0; i < V8; ++i) { sc[i] = scale ? scale[c0 + i] : 1.f; sh[i] = shift ? shift[c0 + i] : 0.f; }
+    const float ry = (float)(H - 1) / (float)(OH - 1);
+    const float rx = (float)(W - 1) / (float)(OW - 1);
+    const int rows = N * H;
+    for (int row = blockIdx.x; row < rows; row += gridDim.x) {
+        const int n = row / H, k = row - n * H;
+        const int yr[3] = {max(k - 1, 0), k, min(k + 1, H - 1)};
+        const float ly0 = k > 0 ? fminf(fmaxf(ry * (2 * k) - (float)(k - 1), 0.f), 1.f) : 0.f;
+        const float ly1 = fminf(fmaxf(ry * (2 * k + 1) - (float)k, 0.f), 1.f);
+        for (int j = x0; j < W; j += xstep) {
+            const int xr[3] = {max(j - 1, 0), j, min(j + 1, W - 1)};
+            const float lx0 = j > 0 ? fminf(fmaxf(rx * (2 * j) - (float)(j - 1), 0.f), 1.f) : 0.f;
+            const float lx1 = fminf(fmaxf(rx * (2 * j + 1) - (float)j, 0.f), 1.f);
+            RawI r[3][3];
+#pragma unroll
+            for (int a = 0; a < 3; ++a)
+#pragma unroll
+                for (int b = 0; b < 3; ++b) r[a][b] = Vec<TI, V8>::load_raw(y.at(n, yr[a], xr[b], c0));
+            float h[3][2][V8];          // horizontally interpolated rows: [input row][output column parity]
+#pragma unroll
+            for (int a = 0; a < 3; ++a) {
+                float v0[V8], v1[V8], v2[V8];
+                Vec<TI, V8>::unpack(r[a][0], v0);
+                Vec<TI, V8>::unpack(r[a][1], v1);
+                Vec<TI, V8>::unpack(r[a][2], v2);
+#pragma unroll
+                for (int i = 0; i < V8; ++i) {
+                    const float p0 = actf(fmaf(v0[i], sc[i], sh[i]), slope);
+                    const float p1 = actf(fmaf(v1[i], sc[i], sh[i]), slope);
+                    const float p2 = actf(fmaf(v2[i], sc[i], sh[i]), slope);
+                    h[a][0][i] = (1.f - lx0) * p0 + lx0 * p1;
+                    h[a][1][i] = (1.f - lx1) * p1 + lx1 * p2;
+                }
+            }
+#pragma unroll
+            for (int a = 0; a < 2; ++a)
+#pragma unroll
+                for (int b = 0; b < 2; ++b) {
+                    float o[V8];
+                    const float l = a == 0 ? ly0 : ly1;
+#pragma unroll
+                    for (int i = 0; i < V8; ++i) o[i] = (1.f - l) * h[a][b][i] + l * h[a + 1][b][i];
+                    const int oy = 2 * k + a, ox = 2 * j + b;
+                    Vec<TO, V8>::store(out.at(n, oy + pad, ox + pad, c0), o);
+                    if (pad) {   // replicate border copies
+                        const bool top = oy == 0, bot = oy == OH - 1, lef = ox == 0, rig = ox == OW - 1;
+                        if (top) Vec<TO, V8>::store(out.at(n, 0, ox + 1, c0), o);
+                        if (bot) Vec<TO, V8>::store(out.at(n, OH + 1, ox + 1, c0), o);
+                        if (lef) Vec<TO, V8>::store(out.at(n, oy + 1, 0, c0), o);
+                        if (rig) Vec<TO, V8>::store(out.at(n, oy + 1, OW + 1, c0), o);
+                        if (top && lef) Vec<TO, V8>::store(out.at(n, 0, 0, c0), o);
+                        if (top && rig) Vec<TO, V8>::store(out.at(n, 0, OW + 1, c0), o);
+                        if (bot && lef) Vec<TO, V8>::store(out.at(n, OH + 1, 0, c0), o);
+                        if (bot && rig) Vec<TO, V8>::store(out.at(n, OH + 1, OW + 1, c0), o);
+                    }
+                }
         }
     }
 }
+
+template <typename TG, typename TY, typename TD>
+__global__ void __launch_bounds__(256, 2)
+bn_act_bwd_up_k(View<TG> dout, View<TY> y, View<TD> dy, const float* __restrict__ scale,
+                const float* __restrict__ shift, const float* __restrict__ mean, const float* __restrict__ invstd,
+                double* sums, float slope, int pad, int N, int H, int W, int C, int cg_shift) {
+    using RawG = typename Vec<TG, V8>::Raw;
+    __shared__ float red[2][256 * V8];
+    const int OH = 2 * H, OW = 2 * W;
+    const int ncg = C >> 3;
+    const int cg = threadIdx.x & (ncg - 1), c0 = cg * V8;
+    const int x0 = threadIdx.x >> cg_shift, xstep = 256 >> cg_shift;
+    float sc[V8], sh[V8], mu[V8], is[V8], s1[V8], s2[V8];
+#pragma unroll
+    for (int i = 0; i < V8; ++i) {
+        sc[i] = scale ? scale[c0 + i] : 1.f; sh[i] = shift ? shift[c0 + i] : 0.f;
+        mu[i] = mean ? mean[c0 + i] : 0.f; is[i] = invstd ? invstd[c0 + i] : 1.f;
+        s1[i] = 0.f; s2[i] = 0.f;
+    }
+    const float ry = (OH > 1) ? (float)(H - 1) / (float)(OH - 1) : 0.f;
+    const float rx = (OW > 1) ? (float)(W - 1) / (float)(OW - 1) : 0.f;
+    const int rows = N * H;
+    for (int row = blockIdx.x; row < rows; row += gridDim.x) {
+        const int n = row / H, yy = row - n * H;
+        // vertical taps: outputs 2yy-1 .. 2yy+2
+        float wy[4];
+        int Ys[4];
+        bool ybord = false;
+#pragma unroll
+        for (int a = 0; a < 4; ++a) {
+            int Y = 2 * yy - 1 + a;
+            float wv = 0.f;
+            if (Y >= 0 && Y < OH) {
+                float sy = ry * Y;
+                int t = (int)sy;
+                float l = sy - t;
+                int tb = min(t + 1, H - 1);
+                wv = (t == yy ? 1.f - l : 0.f) + (tb == yy ? l : 0.f);
+                if (wv != 0.f && (Y == 0 || Y == OH - 1)) ybord = true;
+            }
+            wy[a] = wv;
+            Ys[a] = min(max(Y, 0), OH - 1);
+        }
+        for (int xx = x0; xx < W; xx += xstep) {
+            float wx[4];
+            int Xs[4];
+            bool bord = ybord;
+#pragma unroll
+            for (int b = 0; b < 4; ++b) {
+                int X = 2 * xx - 1 + b;
+                float wv = 0.f;
+                if (X >= 0 && X < OW) {
+                    float sx = rx * X;
+                    int t = (int)sx;
+                    float l = sx - t;
+                    int tb = min(t + 1, W - 1);
+                    wv = (t == xx ? 1.f - l : 0.f) + (tb == xx ? l : 0.f);
+                    if (wv != 0.f && (X == 0 || X == OW - 1)) bord = true;
+                }
+                wx[b] = wv;
+                Xs[b] = min(max(X, 0), OW - 1);
+            }
+            float g[V8], yv[V8];
+#pragma unroll
+            for (int i = 0; i < V8; ++i) g[i] = 0.f;
+            const typename Vec<TY, V8>::Raw ryv = Vec<TY, V8>::load_raw(y.at(n, yy, xx, c0));
+            if (!(pad && bord)) {
+                RawG r[4][4];
+#pragma unroll
+                for (int a = 0; a < 4; ++a)
+#pragma unroll
+                    for (int b = 0; b < 4; ++b) r[a][b] = Vec<TG, V8>::load_raw(dout.at(n, Ys[a] + pad, Xs[b] + pad, c0));
+#pragma unroll
+                for (int a = 0; a < 4; ++a)
+#pragma unroll
+                    for (int b = 0; b < 4; ++b) {
+                        float t[V8];
+                        Vec<TG, V8>::unpack(r[a][b], t);
+                        const float wgt = wy[a] * wx[b];
+#pragma unroll
+                        for (int i = 0; i < V8; ++i) g[i] = fmaf(wgt, t[i], g[i]);
+                    }
+            } else {
+                for (int a = 0; a < 4; ++a) {
+                    if (wy[a] == 0.f) continue;
+                    const RowFold fy(Ys[a], OH, pad);
+                    for (int b = 0; b < 4; ++b) {
+                        if (wx[b] == 0.f) continue;
+                        const RowFold fx(Xs[b], OW, pad);
+                        fold_acc<TG>(dout, n, fy, fx, c0, wy[a] * wx[b], g);
+                    }
+                }
+            }
+            Vec<TY, V8>::unpack(ryv, yv);
+#pragma unroll
+            for (int i = 0; i < V8; ++i) {
+                g[i] *= (fmaf(yv[i], sc[i], sh[i]) > 0.f) ? 1.f : slope;
+                s1[i] += g[i];
+                s2[i] = fmaf(g[i], (yv[i] - mu[i]) * is[i], s2[i]);
+            }
+            if (dy.p) Vec<TD, V8>::store(dy.at(n, yy, xx, c0), g);
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < V8; ++i) { red[0][threadIdx.x * V8 + i] = s1[i]; red[1][threadIdx.x * V8 + i] = s2[i]; }
+    __syncthreads();
+    for (int ch = threadIdx.x; ch < C; ch += 256) {
+        const int g8 = ch >> 3, i = ch & 7;
+        float a = 0.f, b = 0.f;
+        for (int t = g8; t < 256; t += ncg) { a += red[0][t * V8 + i]; b += red[1][t * V8 + i]; }
+        atomicAdd(&sums[ch], (double)a);
+        atomicAdd(&sums[C + ch], (double)b);
+    }
+}
+
+static float act_slope(int act) { return act == KP_ACT_LEAKY ? 0.01f : (act == KP_ACT_RELU ? 0.f : 1.f); }
+
 
 static bool fast_ok(int C, long long rows_px) {
     if (C % 8) return false;
@@ -595,7 +896,8 @@ extern "C" int kp_bn_act_fwd(kp_stream stream, const kp_view* y, const kp_view* 
 #define KP_FWD(POSTV) bn_act_fwd_rows_k<TI, TO, POSTV><<<g, 256, 0, st>>>(make_view<TI>(y), make_view<TO>(out), scale, shift, act, pad, N, H, W, C, OH, OW, sh)
                 if (post == KP_POST_NONE) KP_FWD(KP_POST_NONE);
                 else if (post == KP_POST_POOL) KP_FWD(KP_POST_POOL);
-                else KP_FWD(KP_POST_UP);
+                else if (H < 2 || W < 2) KP_FWD(KP_POST_UP);
+                else bn_act_fwd_up_quad_k<TI, TO><<<rows_grid((long long)N * H), 256, 0, st>>>(make_view<TI>(y), make_view<TO>(out), scale, shift, act_slope(act), pad, N, H, W, C, sh);
 #undef KP_FWD
             } else if (vec) {
                 Launch2D l = plan2d(P, C, 8);
@@ -633,16 +935,11 @@ extern "C" int kp_bn_act_bwd_reduce(kp_stream stream, const kp_view* dout, const
                     const long long rows = post == KP_POST_POOL ? (long long)N * ((H + 1) / 2) : (long long)N * H;
                     const int g = rows_grid(rows), sh = ilog2(C / 8);
                     cudaStream_t st = (cudaStream_t)stream;
-#define KP_BWD(POSTV, MODEV) bn_act_bwd_rows_k<TG, TY, TD, POSTV, MODEV><<<g, 256, 0, st>>>(make_view<TG>(dout), make_view<TY>(y), make_view<TD>(dyv), scale, shift, mean, invstd, sums, 1.0, act, pad, N, H, W, C, OH, OW, sh)
-                    if (dyv->ptr) {
-                        if (post == KP_POST_NONE) KP_BWD(KP_POST_NONE, 1);
-                        else if (post == KP_POST_POOL) KP_BWD(KP_POST_POOL, 1);
-                        else KP_BWD(KP_POST_UP, 1);
-                    } else {
-                        if (post == KP_POST_NONE) KP_BWD(KP_POST_NONE, 0);
-                        else if (post == KP_POST_POOL) KP_BWD(KP_POST_POOL, 0);
-                        else KP_BWD(KP_POST_UP, 0);
-                    }
+#define KP_BWD(POSTV) bn_act_bwd_rows_k<TG, TY, TD, POSTV><<<g, 256, 0, st>>>(make_view<TG>(dout), make_view<TY>(y), make_view<TD>(dyv), scale, shift, mean, invstd, sums, act, pad, N, H, W, C, OH, OW, sh)
+                    if (post == KP_POST_NONE) KP_BWD(KP_POST_NONE);
+                    else if (post == KP_POST_POOL) KP_BWD(KP_POST_POOL);
+                    else if (H < 2 || W < 2) KP_BWD(KP_POST_UP);
+                    else bn_act_bwd_up_k<TG, TY, TD><<<g, 256, 0, st>>>(make_view<TG>(dout), make_view<TY>(y), make_view<TD>(dyv), scale, shift, mean, invstd, sums, act_slope(act), pad, N, H, W, C, sh);
 #undef KP_BWD
                 } else if (vec) {
                     Launch2D l = plan2d(P, C, 8);
@@ -662,46 +959,31 @@ extern "C" int kp_bn_act_bwd_reduce(kp_stream stream, const kp_view* dout, const
     });
 }
 
-extern "C" int kp_bn_act_bwd_apply(kp_stream stream, const kp_view* dout, const kp_view* y, const kp_view* dy,
-                                   const float* scale, const float* shift, const float* mean, const float* invstd,
-                                   const double* sums, double count, int act, int post, int pad, int N, int H, int W,
-                                   int C) {
-    KP_CHECK_ARG(dout && y && dy && dout->ptr && y->ptr && dy->ptr && sums && scale && shift && mean && invstd &&
-                     count > 0 && N > 0 && H > 0 && W > 0 && C > 0,
+extern "C" int kp_bn_act_bwd_apply(kp_stream stream, const kp_view* y, const kp_view* dy, const float* scale,
+                                   const float* mean, const float* invstd, const double* sums, double count, int N,
+                                   int H, int W, int C) {
+    KP_CHECK_ARG(y && dy && y->ptr && dy->ptr && sums && scale && mean && invstd && count > 0 && N > 0 && H > 0 &&
+                     W > 0 && C > 0,
                  "kp_bn_act_bwd_apply: bad arguments");
-    int OH, OW;
-    out_dims(post, H, W, &OH, &OW);
-    const bool vec = view_vec8_ok(y, C) && view_vec8_ok(dout, C) && view_vec8_ok(dy, C);
+    const bool vec = view_vec8_ok(y, C) && view_vec8_ok(dy, C);
     const long long P = (long long)N * H * W;
-    return dispatch1(dout->dtype, [&](auto tg) -> int {
-        return dispatch1(y->dtype, [&](auto ty) -> int {
-            return dispatch1(dy->dtype, [&](auto td) -> int {
-                using TG = decltype(tg);
-                using TY = decltype(ty);
-                using TD = decltype(td);
-                if (vec && fast_ok(C, P * C)) {
-                    const long long rows = post == KP_POST_POOL ? (long long)N * ((H + 1) / 2) : (long long)N * H;
-                    const int g = rows_grid(rows), sh = ilog2(C / 8);
-                    cudaStream_t st = (cudaStream_t)stream;
-#define KP_APP(POSTV) bn_act_bwd_rows_k<TG, TY, TD, POSTV, 2><<<g, 256, 0, st>>>(make_view<TG>(dout), make_view<TY>(y), make_view<TD>(dy), scale, shift, mean, invstd, const_cast<double*>(sums), count, act, pad, N, H, W, C, OH, OW, sh)
-                    if (post == KP_POST_NONE) KP_APP(KP_POST_NONE);
-                    else if (post == KP_POST_POOL) KP_APP(KP_POST_POOL);
-                    else KP_APP(KP_POST_UP);
-#undef KP_APP
-                } else if (vec) {
-                    Launch2D l = plan2d(P, C, 8);
-                    bn_act_bwd_apply_k<TG, TY, TD, 8><<<l.grid, l.block, 0, (cudaStream_t)stream>>>(
-                        make_view<TG>(dout), make_view<TY>(y), make_view<TD>(dy), scale, shift, mean, invstd, sums,
-                        count, act, post, pad, N, H, W, C, OH, OW);
-                } else {
-                    Launch2D l = plan2d(P, C, 1);
-                    bn_act_bwd_apply_k<TG, TY, TD, 1><<<l.grid, l.block, 0, (cudaStream_t)stream>>>(
-                        make_view<TG>(dout), make_view<TY>(y), make_view<TD>(dy), scale, shift, mean, invstd, sums,
-                        count, act, post, pad, N, H, W, C, OH, OW);
-                }
-                KP_LAUNCH_CHECK();
-                return (int)KP_OK;
-            });
+    cudaStream_t st = (cudaStream_t)stream;
+    return dispatch1(y->dtype, [&](auto ty) -> int {
+        return dispatch1(dy->dtype, [&](auto td) -> int {
+            using TY = decltype(ty);
+            using TD = decltype(td);
+            if (vec && fast_ok(C, P * C)) {
+                bn_bwd_apply_rows_k<TY, TD><<<rows_grid((long long)N * H), 256, 0, st>>>(
+                    make_view<TY>(y), make_view<TD>(dy), scale, mean, invstd, sums, count, N, H, W, C, ilog2(C / 8));
+            } else {
+                long long total = P * C;
+                long long g = (total + 255) / 256;
+                if (g > (long long)kp_sm_count() * 16) g = (long long)kp_sm_count() * 16;
+                bn_bwd_apply_generic_k<TY, TD><<<(int)g, 256, 0, st>>>(make_view<TY>(y), make_view<TD>(dy), scale, mean,
+                                                                      invstd, sums, count, N, H, W, C);
+            }
+            KP_LAUNCH_CHECK();
+            return KP_OK;
         });
     });
 }

@@ -250,12 +250,11 @@ def unit_backward(specs: List[ConvSpec], params: List[LayerParams], grads: List[
         if s.bn:
             if c.mean is None:
                 raise NotImplementedError('backward through eval-mode BatchNorm is not supported')
-            L.call('kp_bn_act_bwd_reduce', st, L.view(dout), L.view(yv), None, L.ptr(c.scale), L.ptr(c.shift),
+            L.call('kp_bn_act_bwd_reduce', st, L.view(dout), L.view(yv), L.view(dy_int), L.ptr(c.scale), L.ptr(c.shift),
                    L.ptr(c.mean), L.ptr(c.invstd), L.ptr(sums), a, po, dout_pad, N, h, w, s.cout,
                    tag=f'{tag}{i} {s.cin}->{s.cout}@{h}x{w} {s.post}')
-            L.call('kp_bn_act_bwd_apply', st, L.view(dout), L.view(yv), L.view(dy_int), L.ptr(c.scale), L.ptr(c.shift),
-                   L.ptr(c.mean), L.ptr(c.invstd), L.ptr(sums), float(N * h * w), a, po, dout_pad, N, h, w, s.cout,
-                   tag=f'{tag}{i} {s.cin}->{s.cout}@{h}x{w} {s.post}')
+            L.call('kp_bn_act_bwd_apply', st, L.view(yv), L.view(dy_int), L.ptr(c.scale), L.ptr(c.mean), L.ptr(c.invstd),
+                   L.ptr(sums), float(N * h * w), N, h, w, s.cout, tag=f'{tag}{i} {s.cin}->{s.cout}@{h}x{w} {s.post}')
             L.call('kp_bn_grad_finalize', st, L.ptr(sums), s.cout, L.ptr(g.dgamma), L.ptr(g.dbeta))
             # the bias of a conv feeding train-mode BatchNorm has an exactly zero gradient
         else:

@@ -234,7 +234,7 @@ def test_fused_trainer_vs_oracle(dev, golden, name, kind, model_type, use_graph)
             # fused Adam kernel == torch.optim.Adam semantics on our own gradient bucket
             gflat, m, v, p = tr.flat_g.cpu(), torch.zeros_like(p0).cpu(), torch.zeros_like(p0).cpu(), p0.cpu().clone()
             O.adam_step(p, gflat, m, v, 1)
-            R.rows.append(('adam kernel vs oracle adam (max abs / lr)', float((tr.flat_p.cpu() - p).abs().max()) / 1e-4, 1e-3))
+            R.rows.append(('adam kernel vs oracle adam (max abs / lr)', float((tr.flat_p.cpu() - p).abs().max()) / 1e-4, 5e-3))   # a few fp32 ulps of |p| ~ 1
             close(tr.flat_m.cpu(), m, 1e-6, 'adam m'); close(tr.flat_v.cpu(), v, 1e-6, 'adam v')
     new = net.state_dict()
     for key, ref in oracle.sd.items():
