@@ -2,6 +2,7 @@
 // path for thin layers (Cin in {1,3}, Cout in {1,3,K}) where a tensor-core tile would be empty.
 // 64x64 output tile per block, K chunk of 16, 4x4 register tile per thread.
 #include "kp_common.cuh"
+#include <stdlib.h>
 
 namespace {
 
@@ -208,6 +209,225 @@ __global__ void pack_weights_k(const float* __restrict__ w, int Cout, int Cin, i
     }
 }
 
+// ================================================================================================
+// Thin-layer kernels (bf16 or fp32 activations, fp32 math on the CUDA cores).  The first conv of a stack
+// (Cin <= 4) and the 1x1 heads with a handful of outputs are HBM-bound: a 128x128x64 tile machine wastes most
+// of its lanes on them.  Here a warp walks pixels; each lane owns two channels of the WIDE side (64 channels per
+// warp pass), the <= 36 values of the THIN side of a pixel are staged in shared memory and broadcast.
+// ================================================================================================
+constexpr int THIN_MAX = 36;
+constexpr int TILE_PX = 256;
+
+template <typename T>
+__device__ __forceinline__ void load2(const T* p, float& a, float& b);
+template <> __device__ __forceinline__ void load2<float>(const float* p, float& a, float& b) {
+    float2 v = *reinterpret_cast<const float2*>(p); a = v.x; b = v.y;
+}
+template <> __device__ __forceinline__ void load2<bf16>(const bf16* p, float& a, float& b) {
+    float2 v = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(p)); a = v.x; b = v.y;
+}
+__device__ __forceinline__ void store2(float* p, float a, float b) { *reinterpret_cast<float2*>(p) = make_float2(a, b); }
+__device__ __forceinline__ void store2(bf16* p, float a, float b) {
+    *reinterpret_cast<__nv_bfloat162*>(p) = __floats2bfloat162_rn(a, b);
+}
+
+// stage the thin values of TILE_PX pixels: thin[p][kk], kk = t*Cthin + c, gathered at (y + t/ks + off, x + t%ks + off)
+template <typename TT>
+__device__ __forceinline__ void stage_thin(const View<TT>& thin, float* sm_thin, int* sm_xy, long long p0, long long M, int OH,
+                                           int OW, int IH, int IW, int Cthin, int ks, int off, int KK, int KKP) {
+    const int tid = threadIdx.x;
+    long long p = p0 + tid;
+    int n = 0, y = 0, x = 0;
+    const bool ok = p < M;
+    if (ok) {
+        x = (int)(p % OW);
+        long long r = p / OW;
+        y = (int)(r % OH);
+        n = (int)(r / OH);
+    }
+    sm_xy[tid * 3 + 0] = ok ? n : -1;
+    sm_xy[tid * 3 + 1] = y;
+    sm_xy[tid * 3 + 2] = x;
+    float* dst = sm_thin + tid * KKP;
+    for (int kk = 0; kk < KKP; ++kk) {
+        float v = 0.f;
+        if (ok && kk < KK) {
+            int t = kk / Cthin, c = kk - t * Cthin;
+            int iy = y + t / ks + off, ix = x + t % ks + off;
+            if (iy >= 0 && iy < IH && ix >= 0 && ix < IW) v = to_f(*thin.at(n, iy, ix, c));
+        }
+        dst[kk] = v;
+    }
+}
+
+// out[pix][wide] = bias[wide] + sum_kk thin[pix][kk] * wk[kk][wide]      (wide = 64 channels per blockIdx.y)
+template <typename TT, typename TO, int KKP>
+__global__ void __launch_bounds__(256)
+thin_fprop_k(View<TT> thin, const float* __restrict__ wk, const float* __restrict__ bias, View<TO> out, double* stats,
+             int N, int OH, int OW, int IH, int IW, int Cthin, int Cwide, int ks, int off) {
+    __shared__ __align__(16) float sm_thin[TILE_PX * KKP];
+    __shared__ int sm_xy[TILE_PX * 3];
+    __shared__ float sm_red[8][2][64];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int KK = ks * ks * Cthin;
+    const int c0 = blockIdx.y * 64 + lane * 2;
+    const long long M = (long long)N * OH * OW;
+    float w0[KKP], w1[KKP];
+#pragma unroll
+    for (int kk = 0; kk < KKP; ++kk) {
+        w0[kk] = kk < KK ? wk[(long long)kk * Cwide + c0] : 0.f;
+        w1[kk] = kk < KK ? wk[(long long)kk * Cwide + c0 + 1] : 0.f;
+    }
+    const float b0 = bias ? bias[c0] : 0.f, b1 = bias ? bias[c0 + 1] : 0.f;
+    float s1a = 0.f, s1b = 0.f, s2a = 0.f, s2b = 0.f;
+    const long long ntiles = (M + TILE_PX - 1) / TILE_PX;
+    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        __syncthreads();
+        stage_thin<TT>(thin, sm_thin, sm_xy, tile * TILE_PX, M, OH, OW, IH, IW, Cthin, ks, off, KK, KKP);
+        __syncthreads();
+        for (int i = 0; i < 32; ++i) {
+            const int pp = warp * 32 + i;
+            const int n = sm_xy[pp * 3];
+            if (n < 0) break;
+            const float4* pv = reinterpret_cast<const float4*>(sm_thin + pp * KKP);
+            float a0 = b0, a1 = b1;
+#pragma unroll
+            for (int k4 = 0; k4 < KKP / 4; ++k4) {
+                float4 v = pv[k4];
+                a0 = fmaf(v.x, w0[4 * k4], a0); a1 = fmaf(v.x, w1[4 * k4], a1);
+                a0 = fmaf(v.y, w0[4 * k4 + 1], a0); a1 = fmaf(v.y, w1[4 * k4 + 1], a1);
+                a0 = fmaf(v.z, w0[4 * k4 + 2], a0); a1 = fmaf(v.z, w1[4 * k4 + 2], a1);
+                a0 = fmaf(v.w, w0[4 * k4 + 3], a0); a1 = fmaf(v.w, w1[4 * k4 + 3], a1);
+            }
+            store2(out.at(n, sm_xy[pp * 3 + 1], sm_xy[pp * 3 + 2], c0), a0, a1);
+            s1a += a0; s1b += a1; s2a = fmaf(a0, a0, s2a); s2b = fmaf(a1, a1, s2b);
+        }
+    }
+    if (stats) {
+        sm_red[warp][0][lane * 2] = s1a; sm_red[warp][0][lane * 2 + 1] = s1b;
+        sm_red[warp][1][lane * 2] = s2a; sm_red[warp][1][lane * 2 + 1] = s2b;
+        __syncthreads();
+        if (threadIdx.x < 128) {
+            const int q = threadIdx.x >> 6, ch = threadIdx.x & 63;
+            float a = 0.f;
+            for (int w = 0; w < 8; ++w) a += sm_red[w][q][ch];
+            atomicAdd(&stats[q * Cwide + blockIdx.y * 64 + ch], (double)a);
+        }
+    }
+}
+
+// G[kk][wide] = sum_pix thin[pix][kk] * wide[pix][wide]; written (atomically) at dw[wide*sa + (kk%cdiv)*sb + (kk/cdiv)*sc]
+template <typename TT, typename TW, int KKP>
+__global__ void __launch_bounds__(256)
+thin_wgrad_k(View<TT> thin, View<TW> wide, float* dw, int N, int OH, int OW, int IH, int IW, int Cthin, int ks, int off,
+             int cdiv, long long sa, long long sb, long long sc) {
+    __shared__ __align__(16) float sm_thin[TILE_PX * KKP];
+    __shared__ int sm_xy[TILE_PX * 3];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int KK = ks * ks * Cthin;
+    const int c0 = blockIdx.y * 64 + lane * 2;
+    const long long M = (long long)N * OH * OW;
+    float g0[KKP], g1[KKP];
+#pragma unroll
+    for (int kk = 0; kk < KKP; ++kk) { g0[kk] = 0.f; g1[kk] = 0.f; }
+    const long long ntiles = (M + TILE_PX - 1) / TILE_PX;
+    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        __syncthreads();
+        stage_thin<TT>(thin, sm_thin, sm_xy, tile * TILE_PX, M, OH, OW, IH, IW, Cthin, ks, off, KK, KKP);
+        __syncthreads();
+        for (int i = 0; i < 32; ++i) {
+            const int pp = warp * 32 + i;
+            const int n = sm_xy[pp * 3];
+            if (n < 0) break;
+            float d0, d1;
+            load2<TW>(wide.at(n, sm_xy[pp * 3 + 1], sm_xy[pp * 3 + 2], c0), d0, d1);
+            const float4* pv = reinterpret_cast<const float4*>(sm_thin + pp * KKP);
+#pragma unroll
+            for (int k4 = 0; k4 < KKP / 4; ++k4) {
+                float4 v = pv[k4];
+                g0[4 * k4] = fmaf(v.x, d0, g0[4 * k4]); g1[4 * k4] = fmaf(v.x, d1, g1[4 * k4]);
+                g0[4 * k4 + 1] = fmaf(v.y, d0, g0[4 * k4 + 1]); g1[4 * k4 + 1] = fmaf(v.y, d1, g1[4 * k4 + 1]);
+                g0[4 * k4 + 2] = fmaf(v.z, d0, g0[4 * k4 + 2]); g1[4 * k4 + 2] = fmaf(v.z, d1, g1[4 * k4 + 2]);
+                g0[4 * k4 + 3] = fmaf(v.w, d0, g0[4 * k4 + 3]); g1[4 * k4 + 3] = fmaf(v.w, d1, g1[4 * k4 + 3]);
+            }
+        }
+    }
+    // reduce the 8 warps of the block through shared memory (reusing the staging buffer), one atomic per output
+    __syncthreads();
+    float* red = sm_thin;                      // [KKP][64] floats <= 36*64*4 = 9 KB < staging size
+    for (int i = threadIdx.x; i < KKP * 64; i += 256) red[i] = 0.f;
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < KKP; ++kk) {
+        atomicAdd(&red[kk * 64 + lane * 2], g0[kk]);
+        atomicAdd(&red[kk * 64 + lane * 2 + 1], g1[kk]);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < KK * 64; i += 256) {
+        const int kk = i >> 6, wc = blockIdx.y * 64 + (i & 63);
+        atomicAdd(&dw[wc * sa + (kk % cdiv) * sb + (kk / cdiv) * sc], red[i]);
+    }
+}
+
+// 1x1 conv with <= 16 outputs: one thread per pixel, 8 input channels per 16-byte load
+template <typename TI, typename TO>
+__global__ void __launch_bounds__(256)
+thin_out_fprop_k(View<TI> in, const float* __restrict__ wk /*[Cin][Cout]*/, const float* __restrict__ bias, View<TO> out,
+                 int N, int OH, int OW, int Cin, int Cout) {
+    extern __shared__ float sm_w[];            // [Cin][16]
+    for (int i = threadIdx.x; i < Cin * 16; i += blockDim.x) {
+        int ci = i >> 4, co = i & 15;
+        sm_w[i] = co < Cout ? wk[(long long)ci * Cout + co] : 0.f;
+    }
+    __syncthreads();
+    const long long M = (long long)N * OH * OW;
+    for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < M; p += (long long)gridDim.x * blockDim.x) {
+        int x = (int)(p % OW);
+        long long r = p / OW;
+        int y = (int)(r % OH);
+        int n = (int)(r / OH);
+        float acc[16];
+#pragma unroll
+        for (int co = 0; co < 16; ++co) acc[co] = (bias && co < Cout) ? bias[co] : 0.f;
+        const TI* src = in.at(n, y, x, 0);
+        for (int c8 = 0; c8 < Cin; c8 += 8) {
+            float v[8];
+            Vec<TI, 8>::load(src + c8, v);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float4* wr = reinterpret_cast<const float4*>(sm_w + (c8 + j) * 16);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    if (q * 4 < Cout) {
+                        float4 wv = wr[q];
+                        acc[q * 4] = fmaf(v[j], wv.x, acc[q * 4]);
+                        acc[q * 4 + 1] = fmaf(v[j], wv.y, acc[q * 4 + 1]);
+                        acc[q * 4 + 2] = fmaf(v[j], wv.z, acc[q * 4 + 2]);
+                        acc[q * 4 + 3] = fmaf(v[j], wv.w, acc[q * 4 + 3]);
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int co = 0; co < 16; ++co)
+            if (co < Cout) from_f(out.at(n, y, x, co), acc[co]);
+    }
+}
+
+static bool thin_fast_enabled() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("KP_SIMT_FAST");
+        v = (e && e[0] == '0') ? 0 : 1;
+    }
+    return v == 1;
+}
+static int thin_grid(long long M) {
+    long long tiles = (M + TILE_PX - 1) / TILE_PX;
+    long long cap = (long long)kp_sm_count() * 4;
+    return (int)(tiles < cap ? (tiles < 1 ? 1 : tiles) : cap);
+}
+
 }  // namespace
 
 extern "C" int kp_conv_simt(kp_stream stream, const kp_view* in, const float* wk, const float* bias,
@@ -218,6 +438,40 @@ extern "C" int kp_conv_simt(kp_stream stream, const kp_view* in, const float* wk
                  "kp_conv_simt: bad arguments");
     long long M = (long long)N * OH * OW;
     dim3 grid((unsigned)((M + BM - 1) / BM), (unsigned)((Cout + BN - 1) / BN), 1);
+    const int KKt = ks * ks * Cin;
+    const bool out2 = out->sc == 1 && (((uintptr_t)out->ptr) % 8) == 0 && out->sx % 2 == 0 && out->sy % 2 == 0 && out->sn % 2 == 0;
+    if (thin_fast_enabled() && KKt <= THIN_MAX && Cout % 64 == 0 && out2) {      // thin-K: first conv / dgrad of a thin head
+        dim3 g2((unsigned)thin_grid(M), (unsigned)(Cout / 64), 1);
+        return dispatch1(in->dtype, [&](auto ti) -> int {
+            return dispatch1(out->dtype, [&](auto to) -> int {
+                using TI = decltype(ti);
+                using TO = decltype(to);
+                cudaStream_t st = (cudaStream_t)stream;
+#define KP_THIN(KKPV) thin_fprop_k<TI, TO, KKPV><<<g2, 256, 0, st>>>(make_view<TI>(in), wk, bias, make_view<TO>(out), stats, N, OH, OW, IH, IW, Cin, Cout, ks, off)
+                if (KKt <= 4) KP_THIN(4);
+                else if (KKt <= 12) KP_THIN(12);
+                else if (KKt <= 28) KP_THIN(28);
+                else KP_THIN(36);
+#undef KP_THIN
+                KP_LAUNCH_CHECK();
+                return KP_OK;
+            });
+        });
+    }
+    if (thin_fast_enabled() && ks == 1 && Cout <= 16 && !stats && view_vec8_ok(in, Cin) && Cin * 16 * 4 <= 48 * 1024) {
+        long long blocks = (M + 255) / 256;
+        if (blocks > (long long)kp_sm_count() * 8) blocks = (long long)kp_sm_count() * 8;
+        return dispatch1(in->dtype, [&](auto ti) -> int {
+            return dispatch1(out->dtype, [&](auto to) -> int {
+                using TI = decltype(ti);
+                using TO = decltype(to);
+                thin_out_fprop_k<TI, TO><<<(int)blocks, 256, Cin * 16 * sizeof(float), (cudaStream_t)stream>>>(
+                    make_view<TI>(in), wk, bias, make_view<TO>(out), N, OH, OW, Cin, Cout);
+                KP_LAUNCH_CHECK();
+                return KP_OK;
+            });
+        });
+    }
     return dispatch1(in->dtype, [&](auto ti) -> int {
         return dispatch1(out->dtype, [&](auto to) -> int {
             using TI = decltype(ti);
@@ -237,6 +491,47 @@ extern "C" int kp_conv_wgrad_simt(kp_stream stream, const kp_view* x, const kp_v
                  "kp_conv_wgrad_simt: bad arguments");
     const int KK = ks * ks * Cin;
     const long long P = (long long)N * H * W;
+    auto pair_ok = [](const kp_view* v) {
+        return v->sc == 1 && (((uintptr_t)v->ptr) % 8) == 0 && v->sx % 2 == 0 && v->sy % 2 == 0 && v->sn % 2 == 0;
+    };
+    if (thin_fast_enabled() && KK <= THIN_MAX && Cout % 64 == 0 && pair_ok(dy)) {
+        // thin = x patches (kk = t*Cin + ci), wide = dy (co): dw[co][ci][t]
+        dim3 g2((unsigned)thin_grid(P), (unsigned)(Cout / 64), 1);
+        const int T = ks * ks;
+        return dispatch1(x->dtype, [&](auto tx) -> int {
+            return dispatch1(dy->dtype, [&](auto tg) -> int {
+                using TX = decltype(tx);
+                using TG = decltype(tg);
+                cudaStream_t st = (cudaStream_t)stream;
+#define KP_THINW(KKPV) thin_wgrad_k<TX, TG, KKPV><<<g2, 256, 0, st>>>(make_view<TX>(x), make_view<TG>(dy), dw_oihw, N, H, W, H + ks - 1, W + ks - 1, Cin, ks, 0, Cin, (long long)Cin * T, (long long)T, 1LL)
+                if (KK <= 4) KP_THINW(4);
+                else if (KK <= 12) KP_THINW(12);
+                else if (KK <= 28) KP_THINW(28);
+                else KP_THINW(36);
+#undef KP_THINW
+                KP_LAUNCH_CHECK();
+                return KP_OK;
+            });
+        });
+    }
+    if (thin_fast_enabled() && ks == 1 && Cout <= 16 && Cin % 64 == 0 && pair_ok(x)) {
+        // thin = dy (kk = co), wide = x (ci): dw[co][ci]
+        dim3 g2((unsigned)thin_grid(P), (unsigned)(Cin / 64), 1);
+        return dispatch1(dy->dtype, [&](auto tg) -> int {
+            return dispatch1(x->dtype, [&](auto tx) -> int {
+                using TX = decltype(tx);
+                using TG = decltype(tg);
+                cudaStream_t st = (cudaStream_t)stream;
+#define KP_THINW(KKPV) thin_wgrad_k<TG, TX, KKPV><<<g2, 256, 0, st>>>(make_view<TG>(dy), make_view<TX>(x), dw_oihw, N, H, W, H, W, Cout, 1, 0, 1 << 30, 1LL, (long long)Cin, 0LL)
+                if (Cout <= 4) KP_THINW(4);
+                else if (Cout <= 12) KP_THINW(12);
+                else KP_THINW(28);
+#undef KP_THINW
+                KP_LAUNCH_CHECK();
+                return KP_OK;
+            });
+        });
+    }
     int tiles = ((KK + BM - 1) / BM) * ((Cout + BN - 1) / BN);
     long long split = (4LL * kp_sm_count() + tiles - 1) / tiles;
     long long maxsplit = (P + 4 * BK - 1) / (4 * BK);

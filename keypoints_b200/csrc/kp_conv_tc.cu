@@ -18,6 +18,7 @@
 //           staging gradient.
 #include "kp_common.cuh"
 #include <cuda.h>
+#include <stdlib.h>
 
 namespace {
 
@@ -375,6 +376,322 @@ wgrad_tc_k(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
     }
 }
 
+// ================================================================================================
+// Persistent variants: one CTA per SM walks a static round-robin list of output tiles.  The accumulator is double
+// buffered in TMEM (2 x BN columns), so the epilogue of tile i (TMEM -> registers -> bias / BatchNorm statistics ->
+// bf16 stores) overlaps the TMA + tcgen05.mma main loop of tile i+1, barriers / TMEM / tensor-map prefetch are paid
+// once per CTA, and the BatchNorm statistics are accumulated per CTA and flushed with one double atomic per channel.
+// ================================================================================================
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(192, 1)
+conv_tc_persist_k(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const ConvTcParams p) {
+    constexpr int STAGE_B_BYTES = BN * 128;
+    constexpr int STAGE_BYTES = STAGE_A_BYTES + STAGE_B_BYTES;
+    constexpr int EPI_FLOATS = 4 * 32 * 33 + 4 * 2 * BN;   // per-warp transpose tiles, per-warp running column sums
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* gen_base = smem_raw + (base - smem_u32(smem_raw));
+    float* epi = reinterpret_cast<float*>(gen_base + STAGES * STAGE_BYTES);
+    const uint32_t bars = base + STAGES * STAGE_BYTES + EPI_FLOATS * 4;   // full[S], empty[S], tfull[2], tempty[2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gen_base + STAGES * STAGE_BYTES + EPI_FLOATS * 4 + 8 * (2 * STAGES + 4));
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int kchunks = p.Cin / 64;
+    const int num_kb = p.taps * kchunks;
+    const int num_m = (int)((p.Q + 127) / 128);
+    const int total = num_m * (p.Cout / BN);
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmA);
+        tma_prefetch_desc(&tmB);
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(bars + 8 * s, 1);
+            mbar_init(bars + 8 * (STAGES + s), 1);
+        }
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(bars + 8 * (2 * STAGES + b), 1);        // tmem full  (tcgen05.commit)
+            mbar_init(bars + 8 * (2 * STAGES + 2 + b), 1);    // tmem empty (one elected epilogue thread)
+        }
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(smem_u32(tmem_slot), 2 * BN);
+    if (threadIdx.x >= 64) {
+        float* wsum0 = epi + 4 * 32 * 33;
+        for (int i = threadIdx.x - 64; i < 4 * 2 * BN; i += 128) wsum0[i] = 0.f;
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (elect_one()) {
+            int it = 0;
+            for (int t = blockIdx.x; t < total; t += gridDim.x) {
+                const int n_t = t / num_m, m_t = t - n_t * num_m;
+                const long long q0 = (long long)m_t * 128;
+                const int n0 = n_t * BN;
+                for (int kb = 0; kb < num_kb; ++kb, ++it) {
+                    const int s = it % STAGES, ph = (it / STAGES) & 1;
+                    mbar_wait(bars + 8 * (STAGES + s), ph ^ 1);
+                    const uint32_t full = bars + 8 * s;
+                    mbar_expect_tx(full, STAGE_BYTES);
+                    const int tap = kb / kchunks, kc = kb - tap * kchunks;
+                    const uint32_t sa = base + s * STAGE_BYTES;
+                    tma_load_2d(sa, &tmA, kc * 64, (int)(q0 + p.shift[tap]), full);
+                    tma_load_2d(sa + STAGE_A_BYTES, &tmB, kc * 64, tap * p.Cout + n0, full);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (elect_one()) {
+            constexpr uint32_t idesc = make_idesc(BN, 0, 0);
+            int it = 0, lt = 0;
+            for (int t = blockIdx.x; t < total; t += gridDim.x, ++lt) {
+                const int buf = lt & 1;
+                mbar_wait(bars + 8 * (2 * STAGES + 2 + buf), ((lt >> 1) & 1) ^ 1);
+                tc_fence_after();
+                const uint32_t dcol = tmem_base + buf * BN;
+                for (int kb = 0; kb < num_kb; ++kb, ++it) {
+                    const int s = it % STAGES, ph = (it / STAGES) & 1;
+                    mbar_wait(bars + 8 * s, ph);
+                    tc_fence_after();
+                    const uint32_t sa = base + s * STAGE_BYTES;
+                    const uint64_t ad = make_desc(sa, 16, 1024), bd = make_desc(sa + STAGE_A_BYTES, 16, 1024);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) umma_bf16(dcol, ad + 2 * k, bd + 2 * k, idesc, (kb | k) ? 1u : 0u);
+                    umma_commit(bars + 8 * (STAGES + s));
+                }
+                umma_commit(bars + 8 * (2 * STAGES + buf));
+            }
+        }
+    } else {
+        const int wq = warp & 3;
+        const int row = wq * 32 + lane;
+        const int et = threadIdx.x - 64;                       // 0..127
+        float* tile = epi + wq * (32 * 33);
+        float* wsum_all = epi + 4 * 32 * 33;                   // [4 warps][2*BN] running column sums of this CTA
+        float* wsum = wsum_all + wq * (2 * BN);
+        int lt = 0, cur_n = -1;
+        auto flush = [&](int n_tile) {                         // all 128 epilogue threads
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            for (int ch = et; ch < BN; ch += 128) {
+                float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+                for (int w = 0; w < 4; ++w) {
+                    s1 += wsum_all[w * 2 * BN + ch];
+                    s2 += wsum_all[w * 2 * BN + BN + ch];
+                    wsum_all[w * 2 * BN + ch] = 0.f;
+                    wsum_all[w * 2 * BN + BN + ch] = 0.f;
+                }
+                atomicAdd(&p.stats[n_tile * BN + ch], (double)s1);
+                atomicAdd(&p.stats[p.Cout + n_tile * BN + ch], (double)s2);
+            }
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+        };
+        for (int t = blockIdx.x; t < total; t += gridDim.x, ++lt) {
+            const int n_t = t / num_m, m_t = t - n_t * num_m;
+            const int n0 = n_t * BN;
+            const int buf = lt & 1;
+            if (p.stats && cur_n >= 0 && cur_n != n_t) flush(cur_n);
+            cur_n = n_t;
+            const long long q = (long long)m_t * 128 + row;
+            bool valid = q < p.Q;
+            if (valid && p.stats) {
+                int x = (int)(q % p.PW);
+                int y = (int)((q / p.PW) % p.PH);
+                valid = x < p.VW && y < p.VH;
+            }
+            mbar_wait(bars + 8 * (2 * STAGES + buf), (lt >> 1) & 1);
+            tc_fence_after();
+#pragma unroll 1
+            for (int c = 0; c < BN / 32; ++c) {
+                uint32_t r[32];
+                tmem_ld32(tmem_base + ((uint32_t)(wq * 32) << 16) + buf * BN + c * 32, r);
+                float v[32];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) + (p.bias ? p.bias[n0 + c * 32 + j] : 0.f);
+                if (q < p.Q) {
+                    uint4* dst = reinterpret_cast<uint4*>(p.out + q * p.Cout + n0 + c * 32);
+#pragma unroll
+                    for (int g = 0; g < 4; ++g) {
+                        uint4 u;
+                        __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) h[e] = __floats2bfloat162_rn(v[g * 8 + 2 * e], v[g * 8 + 2 * e + 1]);
+                        dst[g] = u;
+                    }
+                }
+                if (p.stats) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) tile[lane * 33 + j] = valid ? v[j] : 0.f;
+                    __syncwarp();
+                    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+                    for (int rr = 0; rr < 32; ++rr) {
+                        float tv = tile[rr * 33 + lane];
+                        s1 += tv;
+                        s2 = fmaf(tv, tv, s2);
+                    }
+                    wsum[c * 32 + lane] += s1;
+                    wsum[BN + c * 32 + lane] += s2;
+                    __syncwarp();
+                }
+            }
+            // every epilogue thread has drained its TMEM rows: release the accumulator buffer to the MMA warp
+            tc_fence_before();
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            if (et == 0) mbar_arrive(bars + 8 * (2 * STAGES + 2 + buf));
+        }
+        if (p.stats && cur_n >= 0) flush(cur_n);
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        __syncwarp();
+        tmem_dealloc(tmem_base, 2 * BN);
+    }
+}
+
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(192, 1)
+wgrad_tc_persist_k(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const WgradTcParams p,
+                   int taps) {
+    constexpr int BOX_BYTES = 64 * 128;
+    constexpr int A_BYTES = 2 * BOX_BYTES;
+    constexpr int B_BYTES = (BN / 64) * BOX_BYTES;
+    constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* gen_base = smem_raw + (base - smem_u32(smem_raw));
+    const uint32_t bars = base + STAGES * STAGE_BYTES;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gen_base + STAGES * STAGE_BYTES + 8 * (2 * STAGES + 4));
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int num_m = p.Mtot / 128, num_n = p.Ntot / BN;
+    // work item = (split, tap, n tile, m tile); m fastest so the CTAs of one wave share the same pixel range
+    const int total = num_m * num_n * taps * p.splits;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmA);
+        tma_prefetch_desc(&tmB);
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(bars + 8 * s, 1);
+            mbar_init(bars + 8 * (STAGES + s), 1);
+        }
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(bars + 8 * (2 * STAGES + b), 1);
+            mbar_init(bars + 8 * (2 * STAGES + 2 + b), 1);
+        }
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(smem_u32(tmem_slot), 2 * BN);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    auto decode = [&](int t, int& m0, int& n0, int& tap, long long& qbeg, int& nkb) {
+        int mt = t % num_m; t /= num_m;
+        int nt = t % num_n; t /= num_n;
+        tap = t % taps;
+        int split = t / taps;
+        m0 = mt * 128; n0 = nt * BN;
+        qbeg = (long long)split * p.kchunk;
+        long long qend = qbeg + p.kchunk;
+        if (qend > p.Q) qend = p.Q;
+        nkb = qend > qbeg ? (int)((qend - qbeg + 63) / 64) : 0;
+    };
+
+    if (warp == 0) {
+        if (elect_one()) {
+            int it = 0;
+            for (int t = blockIdx.x; t < total; t += gridDim.x) {
+                int m0, n0, tap, nkb;
+                long long qbeg;
+                decode(t, m0, n0, tap, qbeg, nkb);
+                for (int kb = 0; kb < nkb; ++kb, ++it) {
+                    const int s = it % STAGES, ph = (it / STAGES) & 1;
+                    mbar_wait(bars + 8 * (STAGES + s), ph ^ 1);
+                    const uint32_t full = bars + 8 * s;
+                    mbar_expect_tx(full, STAGE_BYTES);
+                    const long long q = qbeg + (long long)kb * 64;
+                    const uint32_t sa = base + s * STAGE_BYTES;
+#pragma unroll
+                    for (int b = 0; b < 2; ++b)
+                        tma_load_2d(sa + b * BOX_BYTES, &tmA, m0 + b * 64, (int)(q + p.shiftA[tap]), full);
+#pragma unroll
+                    for (int b = 0; b < BN / 64; ++b)
+                        tma_load_2d(sa + A_BYTES + b * BOX_BYTES, &tmB, n0 + b * 64, (int)(q + p.shiftB[tap]), full);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (elect_one()) {
+            constexpr uint32_t idesc = make_idesc(BN, 1, 1);
+            int it = 0, lt = 0;
+            for (int t = blockIdx.x; t < total; t += gridDim.x, ++lt) {
+                int m0, n0, tap, nkb;
+                long long qbeg;
+                decode(t, m0, n0, tap, qbeg, nkb);
+                const int buf = lt & 1;
+                mbar_wait(bars + 8 * (2 * STAGES + 2 + buf), ((lt >> 1) & 1) ^ 1);
+                tc_fence_after();
+                const uint32_t dcol = tmem_base + buf * BN;
+                for (int kb = 0; kb < nkb; ++kb, ++it) {
+                    const int s = it % STAGES, ph = (it / STAGES) & 1;
+                    mbar_wait(bars + 8 * s, ph);
+                    tc_fence_after();
+                    const uint32_t sa = base + s * STAGE_BYTES;
+                    const uint64_t ad = make_desc(sa, BOX_BYTES, 1024), bd = make_desc(sa + A_BYTES, BOX_BYTES, 1024);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) umma_bf16(dcol, ad + 128 * k, bd + 128 * k, idesc, (kb | k) ? 1u : 0u);
+                    umma_commit(bars + 8 * (STAGES + s));
+                }
+                umma_commit(bars + 8 * (2 * STAGES + buf));
+            }
+        }
+    } else {
+        const int wq = warp & 3;
+        const int row = wq * 32 + lane;
+        const int et = threadIdx.x - 64;
+        int lt = 0;
+        for (int t = blockIdx.x; t < total; t += gridDim.x, ++lt) {
+            int m0, n0, tap, nkb;
+            long long qbeg;
+            decode(t, m0, n0, tap, qbeg, nkb);
+            const int buf = lt & 1;
+            mbar_wait(bars + 8 * (2 * STAGES + buf), (lt >> 1) & 1);
+            tc_fence_after();
+            if (nkb > 0) {
+                float* dst_row = p.stg + ((long long)tap * p.Mtot + m0 + row) * p.Ntot + n0;
+#pragma unroll 1
+                for (int c = 0; c < BN / 32; ++c) {
+                    uint32_t r[32];
+                    tmem_ld32(tmem_base + ((uint32_t)(wq * 32) << 16) + buf * BN + c * 32, r);
+#pragma unroll
+                    for (int g = 0; g < 8; ++g)
+                        red_add_v4(dst_row + c * 32 + g * 4, __uint_as_float(r[4 * g]), __uint_as_float(r[4 * g + 1]),
+                                   __uint_as_float(r[4 * g + 2]), __uint_as_float(r[4 * g + 3]));
+                }
+            }
+            tc_fence_before();
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            if (et == 0) mbar_arrive(bars + 8 * (2 * STAGES + 2 + buf));
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        __syncwarp();
+        tmem_dealloc(tmem_base, 2 * BN);
+    }
+}
+
 // staging [t][a][b] -> dw_oihw[co][ci][t] (+=), a/b = (co,ci) or (ci,co)
 __global__ void wgrad_finalize_k(const float* __restrict__ stg, float* __restrict__ dw, int taps, int Cout, int Cin,
                                  int CinStg, int m_is_cout) {
@@ -451,6 +768,47 @@ static int launch_wgrad(cudaStream_t st, const CUtensorMap& a, const CUtensorMap
     return KP_OK;
 }
 
+static bool use_persistent() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("KP_TC_PERSIST");
+        v = (e && e[0] == '0') ? 0 : 1;
+    }
+    return v == 1;
+}
+
+template <int BN, int STAGES>
+static int launch_conv_persist(cudaStream_t st, const CUtensorMap& a, const CUtensorMap& b, const ConvTcParams& p) {
+    constexpr int smem = STAGES * (STAGE_A_BYTES + BN * 128) + (4 * 32 * 33 + 4 * 2 * BN) * 4 +
+                         8 * (2 * STAGES + 4) + 16 + 1024;
+    static_assert(smem <= 227 * 1024, "shared memory budget");
+    static bool attr_done = false;
+    if (!attr_done) {
+        KP_CUDA(cudaFuncSetAttribute(conv_tc_persist_k<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        attr_done = true;
+    }
+    long long total = ((p.Q + 127) / 128) * (p.Cout / BN);
+    int grid = (int)(total < kp_sm_count() ? total : kp_sm_count());
+    conv_tc_persist_k<BN, STAGES><<<grid, 192, smem, st>>>(a, b, p);
+    KP_LAUNCH_CHECK();
+    return KP_OK;
+}
+
+template <int BN, int STAGES>
+static int launch_wgrad_persist(cudaStream_t st, const CUtensorMap& a, const CUtensorMap& b, const WgradTcParams& p, int taps) {
+    constexpr int smem = STAGES * (2 * 8192 + (BN / 64) * 8192) + 8 * (2 * STAGES + 4) + 16 + 1024;
+    static bool attr_done = false;
+    if (!attr_done) {
+        KP_CUDA(cudaFuncSetAttribute(wgrad_tc_persist_k<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        attr_done = true;
+    }
+    long long total = (long long)(p.Mtot / 128) * (p.Ntot / BN) * taps * p.splits;
+    int grid = (int)(total < kp_sm_count() ? total : kp_sm_count());
+    wgrad_tc_persist_k<BN, STAGES><<<grid, 192, smem, st>>>(a, b, p, taps);
+    KP_LAUNCH_CHECK();
+    return KP_OK;
+}
+
 }  // namespace
 
 // in: bf16 [Q][Cin]; wt: bf16 [taps][Cout][Cin]; out: bf16 [Q][Cout]; shifts: host int[taps];
@@ -473,6 +831,11 @@ extern "C" int kp_conv_tc(kp_stream stream, const void* in_bf16, int64_t Q, int 
     for (int i = 0; i < 9; ++i) p.shift[i] = i < taps ? shifts[i] : 0;
     p.bias = bias; p.out = (bf16*)out_bf16; p.stats = stats; p.PH = PH; p.PW = PW; p.VH = VH; p.VW = VW;
     cudaStream_t st = (cudaStream_t)stream;
+    if (use_persistent()) {
+        if (BN == 256) return launch_conv_persist<256, 4>(st, ta, tb, p);
+        if (BN == 128) return launch_conv_persist<128, 5>(st, ta, tb, p);
+        return launch_conv_persist<64, 6>(st, ta, tb, p);
+    }
     if (BN == 256) return launch_conv<256, 4>(st, ta, tb, p);
     if (BN == 128) return launch_conv<128, 4>(st, ta, tb, p);
     return launch_conv<64, 4>(st, ta, tb, p);
@@ -512,7 +875,11 @@ extern "C" int kp_conv_wgrad_tc(kp_stream stream, const void* x_bf16, const void
     p.kchunk = per * 64;
     p.splits = (int)splits;
     KP_CUDA(cudaMemsetAsync(stg, 0, sizeof(float) * (size_t)taps * Mtot * Ntot, st));
-    if (BN == 256) rc = launch_wgrad<256, 4>(st, ta, tb, p, taps);
+    if (use_persistent()) {
+        if (BN == 256) rc = launch_wgrad_persist<256, 4>(st, ta, tb, p, taps);
+        else if (BN == 128) rc = launch_wgrad_persist<128, 6>(st, ta, tb, p, taps);
+        else rc = launch_wgrad_persist<64, 8>(st, ta, tb, p, taps);
+    } else if (BN == 256) rc = launch_wgrad<256, 4>(st, ta, tb, p, taps);
     else if (BN == 128) rc = launch_wgrad<128, 4>(st, ta, tb, p, taps);
     else rc = launch_wgrad<64, 4>(st, ta, tb, p, taps);
     if (rc) return rc;
