@@ -387,11 +387,11 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 }
 
 template <int BN, int STAGES>
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(320, 1)
 conv_tc_persist_k(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const ConvTcParams p) {
     constexpr int STAGE_B_BYTES = BN * 128;
     constexpr int STAGE_BYTES = STAGE_A_BYTES + STAGE_B_BYTES;
-    constexpr int EPI_FLOATS = 4 * 32 * 33 + 4 * 2 * BN;   // per-warp transpose tiles, per-warp running column sums
+    constexpr int EPI_FLOATS = 8 * 32 * 17 + 4 * 2 * BN;   // per-warp 32x16 transpose tiles, per-lane-group running column sums
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* gen_base = smem_raw + (base - smem_u32(smem_raw));
@@ -420,8 +420,8 @@ conv_tc_persist_k(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     }
     if (warp == 1) tmem_alloc(smem_u32(tmem_slot), 2 * BN);
     if (threadIdx.x >= 64) {
-        float* wsum0 = epi + 4 * 32 * 33;
-        for (int i = threadIdx.x - 64; i < 4 * 2 * BN; i += 128) wsum0[i] = 0.f;
+        float* wsum0 = epi + 8 * 32 * 17;
+        for (int i = threadIdx.x - 64; i < 4 * 2 * BN; i += 256) wsum0[i] = 0.f;
     }
     tc_fence_before();
     __syncthreads();
@@ -472,14 +472,15 @@ conv_tc_persist_k(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     } else {
         const int wq = warp & 3;
         const int row = wq * 32 + lane;
-        const int et = threadIdx.x - 64;                       // 0..127
-        float* tile = epi + wq * (32 * 33);
-        float* wsum_all = epi + 4 * 32 * 33;                   // [4 warps][2*BN] running column sums of this CTA
+        const int et = threadIdx.x - 64;                       // 0..255: 8 epilogue warps, 2 per TMEM lane group
+        const int half = (warp - 2) >> 2;                      // which interleaved set of 32-column chunks
+        float* tile = epi + (warp - 2) * (32 * 17);
+        float* wsum_all = epi + 8 * 32 * 17;                   // [4 lane groups][2*BN] running column sums of this CTA
         float* wsum = wsum_all + wq * (2 * BN);
         int lt = 0, cur_n = -1;
         auto flush = [&](int n_tile) {                         // all 128 epilogue threads
-            asm volatile("bar.sync 1, 128;" ::: "memory");
-            for (int ch = et; ch < BN; ch += 128) {
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            for (int ch = et; ch < BN; ch += 256) {
                 float s1 = 0.f, s2 = 0.f;
 #pragma unroll
                 for (int w = 0; w < 4; ++w) {
@@ -491,7 +492,7 @@ conv_tc_persist_k(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                 atomicAdd(&p.stats[n_tile * BN + ch], (double)s1);
                 atomicAdd(&p.stats[p.Cout + n_tile * BN + ch], (double)s2);
             }
-            asm volatile("bar.sync 1, 128;" ::: "memory");
+            asm volatile("bar.sync 1, 256;" ::: "memory");
         };
         for (int t = blockIdx.x; t < total; t += gridDim.x, ++lt) {
             const int n_t = t / num_m, m_t = t - n_t * num_m;
@@ -509,12 +510,22 @@ conv_tc_persist_k(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             mbar_wait(bars + 8 * (2 * STAGES + buf), (lt >> 1) & 1);
             tc_fence_after();
 #pragma unroll 1
-            for (int c = 0; c < BN / 32; ++c) {
+            for (int c = half; c < BN / 32; c += 2) {
                 uint32_t r[32];
                 tmem_ld32(tmem_base + ((uint32_t)(wq * 32) << 16) + buf * BN + c * 32, r);
                 float v[32];
+                if (p.bias && ((reinterpret_cast<uintptr_t>(p.bias) & 15) == 0)) {
+                    const float4* bp = reinterpret_cast<const float4*>(p.bias + n0 + c * 32);
 #pragma unroll
-                for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) + (p.bias ? p.bias[n0 + c * 32 + j] : 0.f);
+                    for (int g = 0; g < 8; ++g) {
+                        const float4 bv = bp[g];
+                        v[4 * g] = __uint_as_float(r[4 * g]) + bv.x; v[4 * g + 1] = __uint_as_float(r[4 * g + 1]) + bv.y;
+                        v[4 * g + 2] = __uint_as_float(r[4 * g + 2]) + bv.z; v[4 * g + 3] = __uint_as_float(r[4 * g + 3]) + bv.w;
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) + (p.bias ? p.bias[n0 + c * 32 + j] : 0.f);
+                }
                 if (q < p.Q) {
                     uint4* dst = reinterpret_cast<uint4*>(p.out + q * p.Cout + n0 + c * 32);
 #pragma unroll
@@ -527,24 +538,236 @@ conv_tc_persist_k(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                     }
                 }
                 if (p.stats) {
+                    // column sums over the warp's 32 rows, 16 columns at a time through a 32x17 shared tile: lane l sums
+                    // column (l & 15) over rows [16 (l >> 4), +16), the two row halves are combined with one shuffle
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) tile[lane * 33 + j] = valid ? v[j] : 0.f;
-                    __syncwarp();
-                    float s1 = 0.f, s2 = 0.f;
+                    for (int hc = 0; hc < 2; ++hc) {
 #pragma unroll
-                    for (int rr = 0; rr < 32; ++rr) {
-                        float tv = tile[rr * 33 + lane];
-                        s1 += tv;
-                        s2 = fmaf(tv, tv, s2);
+                        for (int j = 0; j < 16; ++j) tile[lane * 17 + j] = valid ? v[hc * 16 + j] : 0.f;
+                        __syncwarp();
+                        float s1 = 0.f, s2 = 0.f;
+                        const int col = lane & 15, r0 = (lane >> 4) * 16;
+#pragma unroll
+                        for (int rr = 0; rr < 16; ++rr) {
+                            float tv = tile[(r0 + rr) * 17 + col];
+                            s1 += tv;
+                            s2 = fmaf(tv, tv, s2);
+                        }
+                        s1 += __shfl_xor_sync(0xffffffffu, s1, 16);
+                        s2 += __shfl_xor_sync(0xffffffffu, s2, 16);
+                        if (lane < 16) {
+                            wsum[c * 32 + hc * 16 + col] += s1;
+                            wsum[BN + c * 32 + hc * 16 + col] += s2;
+                        }
+                        __syncwarp();
                     }
-                    wsum[c * 32 + lane] += s1;
-                    wsum[BN + c * 32 + lane] += s2;
-                    __syncwarp();
                 }
             }
             // every epilogue thread has drained its TMEM rows: release the accumulator buffer to the MMA warp
             tc_fence_before();
-            asm volatile("bar.sync 1, 128;" ::: "memory");
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            if (et == 0) mbar_arrive(bars + 8 * (2 * STAGES + 2 + buf));
+        }
+        if (p.stats && cur_n >= 0) flush(cur_n);
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        __syncwarp();
+        tmem_dealloc(tmem_base, 2 * BN);
+    }
+}
+
+// Variant for thin layers (taps*Cin*BN*2 bytes <= RES_BYTES): the whole weight tile set of this CTA's channel tile stays
+// RESIDENT in shared memory (loaded once), the ring streams only the activation tiles.  Halves the L2->SM traffic of
+// the 64/128-channel layers at 128x128 and removes the all-SMs-read-the-same-16KB hot spot on the weight lines.
+template <int BN, int STAGES, int RES_BYTES>
+__global__ void __launch_bounds__(320, 1)
+conv_tc_resident_k(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const ConvTcParams p) {
+    constexpr int STAGE_B_BYTES = BN * 128;
+    constexpr int STAGE_BYTES = STAGE_A_BYTES;
+    constexpr int EPI_FLOATS = 8 * 32 * 17 + 4 * 2 * BN;   // per-warp 32x16 transpose tiles, per-lane-group running column sums
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* gen_base = smem_raw + (base - smem_u32(smem_raw));
+    const uint32_t resb = base + STAGES * STAGE_BYTES;              // resident weights: [num_kb][BN rows x 128 B]
+    float* epi = reinterpret_cast<float*>(gen_base + STAGES * STAGE_BYTES + RES_BYTES);
+    const uint32_t bars = base + STAGES * STAGE_BYTES + RES_BYTES + EPI_FLOATS * 4;   // full[S], empty[S], tfull[2], tempty[2], wfull
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gen_base + STAGES * STAGE_BYTES + RES_BYTES + EPI_FLOATS * 4 + 8 * (2 * STAGES + 5));
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int kchunks = p.Cin / 64;
+    const int num_kb = p.taps * kchunks;
+    const int num_m = (int)((p.Q + 127) / 128);
+    const int total = num_m;                                  // tiles of this CTA column: channel tile = blockIdx.y
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmA);
+        tma_prefetch_desc(&tmB);
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(bars + 8 * s, 1);
+            mbar_init(bars + 8 * (STAGES + s), 1);
+        }
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(bars + 8 * (2 * STAGES + b), 1);        // tmem full  (tcgen05.commit)
+            mbar_init(bars + 8 * (2 * STAGES + 2 + b), 1);    // tmem empty (one elected epilogue thread)
+        }
+        mbar_init(bars + 8 * (2 * STAGES + 4), 1);            // resident weights landed
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(smem_u32(tmem_slot), 2 * BN);
+    if (threadIdx.x >= 64) {
+        float* wsum0 = epi + 8 * 32 * 17;
+        for (int i = threadIdx.x - 64; i < 4 * 2 * BN; i += 256) wsum0[i] = 0.f;
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (elect_one()) {
+            int it = 0;
+            {   // all weight tiles of channel tile blockIdx.y, once
+                const uint32_t wfull = bars + 8 * (2 * STAGES + 4);
+                mbar_expect_tx(wfull, (uint32_t)(num_kb * STAGE_B_BYTES));
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    const int tap = kb / kchunks, kc = kb - tap * kchunks;
+                    tma_load_2d(resb + kb * STAGE_B_BYTES, &tmB, kc * 64, tap * p.Cout + (int)blockIdx.y * BN, wfull);
+                }
+            }
+            for (int t = blockIdx.x; t < total; t += gridDim.x) {
+                const long long q0 = (long long)t * 128;
+                for (int kb = 0; kb < num_kb; ++kb, ++it) {
+                    const int s = it % STAGES, ph = (it / STAGES) & 1;
+                    mbar_wait(bars + 8 * (STAGES + s), ph ^ 1);
+                    const uint32_t full = bars + 8 * s;
+                    mbar_expect_tx(full, STAGE_BYTES);
+                    const int tap = kb / kchunks, kc = kb - tap * kchunks;
+                    tma_load_2d(base + s * STAGE_BYTES, &tmA, kc * 64, (int)(q0 + p.shift[tap]), full);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (elect_one()) {
+            constexpr uint32_t idesc = make_idesc(BN, 0, 0);
+            int it = 0, lt = 0;
+            mbar_wait(bars + 8 * (2 * STAGES + 4), 0);
+            for (int t = blockIdx.x; t < total; t += gridDim.x, ++lt) {
+                const int buf = lt & 1;
+                mbar_wait(bars + 8 * (2 * STAGES + 2 + buf), ((lt >> 1) & 1) ^ 1);
+                tc_fence_after();
+                const uint32_t dcol = tmem_base + buf * BN;
+                for (int kb = 0; kb < num_kb; ++kb, ++it) {
+                    const int s = it % STAGES, ph = (it / STAGES) & 1;
+                    mbar_wait(bars + 8 * s, ph);
+                    tc_fence_after();
+                    const uint32_t sa = base + s * STAGE_BYTES;
+                    const uint64_t ad = make_desc(sa, 16, 1024), bd = make_desc(resb + kb * STAGE_B_BYTES, 16, 1024);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) umma_bf16(dcol, ad + 2 * k, bd + 2 * k, idesc, (kb | k) ? 1u : 0u);
+                    umma_commit(bars + 8 * (STAGES + s));
+                }
+                umma_commit(bars + 8 * (2 * STAGES + buf));
+            }
+        }
+    } else {
+        const int wq = warp & 3;
+        const int row = wq * 32 + lane;
+        const int et = threadIdx.x - 64;                       // 0..255: 8 epilogue warps, 2 per TMEM lane group
+        const int half = (warp - 2) >> 2;                      // which interleaved set of 32-column chunks
+        float* tile = epi + (warp - 2) * (32 * 17);
+        float* wsum_all = epi + 8 * 32 * 17;                   // [4 lane groups][2*BN] running column sums of this CTA
+        float* wsum = wsum_all + wq * (2 * BN);
+        int lt = 0, cur_n = -1;
+        auto flush = [&](int n_tile) {                         // all 128 epilogue threads
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            for (int ch = et; ch < BN; ch += 256) {
+                float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+                for (int w = 0; w < 4; ++w) {
+                    s1 += wsum_all[w * 2 * BN + ch];
+                    s2 += wsum_all[w * 2 * BN + BN + ch];
+                    wsum_all[w * 2 * BN + ch] = 0.f;
+                    wsum_all[w * 2 * BN + BN + ch] = 0.f;
+                }
+                atomicAdd(&p.stats[n_tile * BN + ch], (double)s1);
+                atomicAdd(&p.stats[p.Cout + n_tile * BN + ch], (double)s2);
+            }
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+        };
+        for (int t = blockIdx.x; t < total; t += gridDim.x, ++lt) {
+            const int n_t = blockIdx.y, m_t = t;
+            const int n0 = n_t * BN;
+            const int buf = lt & 1;
+            if (p.stats && cur_n >= 0 && cur_n != n_t) flush(cur_n);
+            cur_n = n_t;
+            const long long q = (long long)m_t * 128 + row;
+            bool valid = q < p.Q;
+            if (valid && p.stats) {
+                int x = (int)(q % p.PW);
+                int y = (int)((q / p.PW) % p.PH);
+                valid = x < p.VW && y < p.VH;
+            }
+            mbar_wait(bars + 8 * (2 * STAGES + buf), (lt >> 1) & 1);
+            tc_fence_after();
+#pragma unroll 1
+            for (int c = half; c < BN / 32; c += 2) {
+                uint32_t r[32];
+                tmem_ld32(tmem_base + ((uint32_t)(wq * 32) << 16) + buf * BN + c * 32, r);
+                float v[32];
+                if (p.bias && ((reinterpret_cast<uintptr_t>(p.bias) & 15) == 0)) {
+                    const float4* bp = reinterpret_cast<const float4*>(p.bias + n0 + c * 32);
+#pragma unroll
+                    for (int g = 0; g < 8; ++g) {
+                        const float4 bv = bp[g];
+                        v[4 * g] = __uint_as_float(r[4 * g]) + bv.x; v[4 * g + 1] = __uint_as_float(r[4 * g + 1]) + bv.y;
+                        v[4 * g + 2] = __uint_as_float(r[4 * g + 2]) + bv.z; v[4 * g + 3] = __uint_as_float(r[4 * g + 3]) + bv.w;
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) + (p.bias ? p.bias[n0 + c * 32 + j] : 0.f);
+                }
+                if (q < p.Q) {
+                    uint4* dst = reinterpret_cast<uint4*>(p.out + q * p.Cout + n0 + c * 32);
+#pragma unroll
+                    for (int g = 0; g < 4; ++g) {
+                        uint4 u;
+                        __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) h[e] = __floats2bfloat162_rn(v[g * 8 + 2 * e], v[g * 8 + 2 * e + 1]);
+                        dst[g] = u;
+                    }
+                }
+                if (p.stats) {
+                    // column sums over the warp's 32 rows, 16 columns at a time through a 32x17 shared tile: lane l sums
+                    // column (l & 15) over rows [16 (l >> 4), +16), the two row halves are combined with one shuffle
+#pragma unroll
+                    for (int hc = 0; hc < 2; ++hc) {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) tile[lane * 17 + j] = valid ? v[hc * 16 + j] : 0.f;
+                        __syncwarp();
+                        float s1 = 0.f, s2 = 0.f;
+                        const int col = lane & 15, r0 = (lane >> 4) * 16;
+#pragma unroll
+                        for (int rr = 0; rr < 16; ++rr) {
+                            float tv = tile[(r0 + rr) * 17 + col];
+                            s1 += tv;
+                            s2 = fmaf(tv, tv, s2);
+                        }
+                        s1 += __shfl_xor_sync(0xffffffffu, s1, 16);
+                        s2 += __shfl_xor_sync(0xffffffffu, s2, 16);
+                        if (lane < 16) {
+                            wsum[c * 32 + hc * 16 + col] += s1;
+                            wsum[BN + c * 32 + hc * 16 + col] += s2;
+                        }
+                        __syncwarp();
+                    }
+                }
+            }
+            // every epilogue thread has drained its TMEM rows: release the accumulator buffer to the MMA warp
+            tc_fence_before();
+            asm volatile("bar.sync 1, 256;" ::: "memory");
             if (et == 0) mbar_arrive(bars + 8 * (2 * STAGES + 2 + buf));
         }
         if (p.stats && cur_n >= 0) flush(cur_n);
@@ -779,7 +1002,7 @@ static bool use_persistent() {
 
 template <int BN, int STAGES>
 static int launch_conv_persist(cudaStream_t st, const CUtensorMap& a, const CUtensorMap& b, const ConvTcParams& p) {
-    constexpr int smem = STAGES * (STAGE_A_BYTES + BN * 128) + (4 * 32 * 33 + 4 * 2 * BN) * 4 +
+    constexpr int smem = STAGES * (STAGE_A_BYTES + BN * 128) + (8 * 32 * 17 + 4 * 2 * BN) * 4 +
                          8 * (2 * STAGES + 4) + 16 + 1024;
     static_assert(smem <= 227 * 1024, "shared memory budget");
     static bool attr_done = false;
@@ -789,7 +1012,27 @@ static int launch_conv_persist(cudaStream_t st, const CUtensorMap& a, const CUte
     }
     long long total = ((p.Q + 127) / 128) * (p.Cout / BN);
     int grid = (int)(total < kp_sm_count() ? total : kp_sm_count());
-    conv_tc_persist_k<BN, STAGES><<<grid, 192, smem, st>>>(a, b, p);
+    conv_tc_persist_k<BN, STAGES><<<grid, 320, smem, st>>>(a, b, p);
+    KP_LAUNCH_CHECK();
+    return KP_OK;
+}
+
+template <int BN, int STAGES, int RES_BYTES>
+static int launch_conv_resident(cudaStream_t st, const CUtensorMap& a, const CUtensorMap& b, const ConvTcParams& p) {
+    constexpr int smem = STAGES * STAGE_A_BYTES + RES_BYTES + (8 * 32 * 17 + 4 * 2 * BN) * 4 + 8 * (2 * STAGES + 5) + 16 + 1024;
+    static_assert(smem <= 227 * 1024, "shared memory budget");
+    static bool attr_done = false;
+    if (!attr_done) {
+        KP_CUDA(cudaFuncSetAttribute(conv_tc_resident_k<BN, STAGES, RES_BYTES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        attr_done = true;
+    }
+    const int ny = p.Cout / BN;
+    long long num_m = (p.Q + 127) / 128;
+    int gx = kp_sm_count() / ny;
+    if (gx < 1) gx = 1;
+    if (gx > num_m) gx = (int)num_m;
+    dim3 grid((unsigned)gx, (unsigned)ny, 1);
+    conv_tc_resident_k<BN, STAGES, RES_BYTES><<<grid, 320, smem, st>>>(a, b, p);
     KP_LAUNCH_CHECK();
     return KP_OK;
 }
@@ -832,6 +1075,14 @@ extern "C" int kp_conv_tc(kp_stream stream, const void* in_bf16, int64_t Q, int 
     p.bias = bias; p.out = (bf16*)out_bf16; p.stats = stats; p.PH = PH; p.PW = PW; p.VH = VH; p.VW = VW;
     cudaStream_t st = (cudaStream_t)stream;
     if (use_persistent()) {
+        constexpr int RES = 9 * 16384;                         // 144 KB of resident weights
+        const long long wbytes = (long long)taps * Cin * BN * 2;
+        static int res_on = -1;
+        if (res_on < 0) { const char* e = getenv("KP_TC_RESIDENT"); res_on = (e && e[0] == '0') ? 0 : 1; }
+        if (res_on && wbytes <= RES && Q >= 128LL * kp_sm_count()) {
+            if (BN == 128) return launch_conv_resident<128, 3, RES>(st, ta, tb, p);
+            if (BN == 64) return launch_conv_resident<64, 3, RES>(st, ta, tb, p);
+        }
         if (BN == 256) return launch_conv_persist<256, 4>(st, ta, tb, p);
         if (BN == 128) return launch_conv_persist<128, 5>(st, ta, tb, p);
         return launch_conv_persist<64, 6>(st, ta, tb, p);

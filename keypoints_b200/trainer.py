@@ -76,24 +76,29 @@ class Trainer:
 
     # ------------------------------------------------------------------------------------------
     def _flatten(self):
-        tensors = []
+        """One flat fp32 bucket for all trainable tensors (decoder | keypoint | encoder); every tensor starts on a
+        128-byte boundary (the kernels use 16-byte vector loads on biases / BN vectors), padding stays zero."""
+        ALIGN = 32
+        tensors, offsets, off = [], [], 0
         for u in self.units.values():
-            start = sum(t.numel() for t in tensors)
-            tensors += u.tensors()
-            u.span = (start, sum(t.numel() for t in tensors))
-        n = sum(t.numel() for t in tensors)
-        self.flat_p = torch.empty(n, dtype=torch.float32, device=self.device)
+            start = off
+            for t in u.tensors():
+                tensors.append(t)
+                offsets.append(off)
+                off += (t.numel() + ALIGN - 1) // ALIGN * ALIGN
+            u.span = (start, off)
+        n = off
+        self.flat_p = torch.zeros(n, dtype=torch.float32, device=self.device)
         self.flat_g = torch.zeros(n, dtype=torch.float32, device=self.device)
         self.flat_m = torch.zeros(n, dtype=torch.float32, device=self.device)
         self.flat_v = torch.zeros(n, dtype=torch.float32, device=self.device)
-        off = 0
         gviews = {}
-        for t in tensors:
+        for t, o in zip(tensors, offsets):
             k = t.numel()
-            self.flat_p[off:off + k].copy_(t.data.reshape(-1))
-            t.data = self.flat_p[off:off + k].view_as(t)          # the module now aliases the flat bucket
-            gviews[id(t)] = self.flat_g[off:off + k].view_as(t)
-            off += k
+            self.flat_p[o:o + k].copy_(t.data.reshape(-1))
+            t.data = self.flat_p[o:o + k].view_as(t)          # the module now aliases the flat bucket
+            gviews[id(t)] = self.flat_g[o:o + k].view_as(t)
+        self.n_true_params = sum(t.numel() for t in tensors)
         for u in self.units.values():
             u.params = knn.layer_params(u.mods)
             u.grads = []

@@ -309,6 +309,9 @@ def test_adjoint_identity_full_size(dev):
     g = LayerGrads(dw=torch.zeros_like(wt), db=torch.zeros(cout, device=dev))
     dxp = engine.unit_backward([spec], [p], [g], ctxs, dy, 0, 'bf16', True)
     dx = engine.fold_to_nchw(dxp, cin, h, w)
+    # direct check of the (resident-weights) fprop against an fp32 CPU convolution of the same bf16-rounded operands
+    ref = _conv_ref(x.cpu(), wt.cpu(), None)
+    close(out.permute(0, 3, 1, 2), ref, 1e-2, 'fprop 64->128 @128x128 (bf16 store)')
     lhs = float((out.double() * dy.double()).sum())
     via_w = float((g.dw.double() * wt.double()).sum())
     via_x = float((dx.double() * x.double()).sum())
