@@ -578,6 +578,248 @@ conv_tc_persist_k(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// CTA-pair variant (tcgen05 cta_group::2): two CTAs of a cluster on one TPC compute a 256-pixel x BN tile with one
+// M=256 MMA stream issued by the leader.  Each CTA stages its own 128 pixel rows of A and only HALF of the weight tile
+// (BN/2 rows), so a pipeline stage is 16 KB + BN/2*128 B instead of 16 KB + BN*128 B: the ring holds 1.5x more k-blocks
+// in flight for the same shared memory, which is what the TMA-latency-bound main loop needs.
+// Barriers: the TMA loads of both CTAs complete on the LEADER's full barrier; tcgen05.commit multicasts the
+// stage-free and accumulator-ready signals to both CTAs; both epilogues arrive on the leader's accumulator-free barrier.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+constexpr uint32_t PEER_MASK = 0xFEFFFFFFu;     // clears the CTA-rank bit of a shared::cluster address -> leader CTA
+__device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap* tm, int c0, int c1, uint32_t bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+        ::"r"(dst), "l"((uint64_t)tm), "r"(c0), "r"(c1), "r"(bar & PEER_MASK)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit_pair(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(bar), "h"((uint16_t)3) : "memory");
+}
+__device__ __forceinline__ void umma_bf16_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+        : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_leader(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(bar & PEER_MASK) : "memory");
+}
+__host__ __device__ constexpr uint32_t make_idesc_m256(int n) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+}
+
+template <int BN, int STAGES>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(320, 1)
+conv_tc_pair_k(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const ConvTcParams p) {
+    constexpr int STAGE_B_BYTES = (BN / 2) * 128;              // this CTA's half of the weight tile
+    constexpr int STAGE_BYTES = STAGE_A_BYTES + STAGE_B_BYTES;
+    constexpr int EPI_FLOATS = 8 * 32 * 17 + 4 * 2 * BN;   // per-warp 32x16 transpose tiles, per-lane-group running column sums
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* gen_base = smem_raw + (base - smem_u32(smem_raw));
+    float* epi = reinterpret_cast<float*>(gen_base + STAGES * STAGE_BYTES);
+    const uint32_t bars = base + STAGES * STAGE_BYTES + EPI_FLOATS * 4;   // full[S], empty[S], tfull[2], tempty[2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gen_base + STAGES * STAGE_BYTES + EPI_FLOATS * 4 + 8 * (2 * STAGES + 4));
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const bool leader = rank == 0;
+    const int kchunks = p.Cin / 64;
+    const int num_kb = p.taps * kchunks;
+    const int num_m = (int)((p.Q + 255) / 256);                 // pair tiles of 256 pixels
+    const int total = num_m * (p.Cout / BN);
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmA);
+        tma_prefetch_desc(&tmB);
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(bars + 8 * s, 1);
+            mbar_init(bars + 8 * (STAGES + s), 1);
+        }
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(bars + 8 * (2 * STAGES + b), 1);        // tmem full  (tcgen05.commit)
+            mbar_init(bars + 8 * (2 * STAGES + 2 + b), 2);    // tmem empty: one arrive from each CTA's epilogue
+        }
+        fence_barrier_init();
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(2 * BN) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    if (threadIdx.x >= 64) {
+        float* wsum0 = epi + 8 * 32 * 17;
+        for (int i = threadIdx.x - 64; i < 4 * 2 * BN; i += 256) wsum0[i] = 0.f;
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();                                         // both CTAs' barriers are initialised before any remote signal
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const int nclusters = gridDim.x >> 1, cid = blockIdx.x >> 1;
+
+    if (warp == 0) {
+        if (elect_one()) {
+            int it = 0;
+            for (int t = cid; t < total; t += nclusters) {
+                const int n_t = t / num_m, m_t = t - n_t * num_m;
+                const long long q0 = (long long)m_t * 256 + rank * 128;
+                const int n0 = n_t * BN + rank * (BN / 2);
+                for (int kb = 0; kb < num_kb; ++kb, ++it) {
+                    const int s = it % STAGES, ph = (it / STAGES) & 1;
+                    mbar_wait(bars + 8 * (STAGES + s), ph ^ 1);
+                    const uint32_t full = bars + 8 * s;
+                    if (leader) mbar_expect_tx(full, 2 * STAGE_BYTES);      // bytes of both CTAs land on the leader's barrier
+                    const int tap = kb / kchunks, kc = kb - tap * kchunks;
+                    const uint32_t sa = base + s * STAGE_BYTES;
+                    tma_load_2d_pair(sa, &tmA, kc * 64, (int)(q0 + p.shift[tap]), full);
+                    tma_load_2d_pair(sa + STAGE_A_BYTES, &tmB, kc * 64, tap * p.Cout + n0, full);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (leader && elect_one()) {
+            constexpr uint32_t idesc = make_idesc_m256(BN);
+            int it = 0, lt = 0;
+            for (int t = cid; t < total; t += nclusters, ++lt) {
+                const int buf = lt & 1;
+                mbar_wait(bars + 8 * (2 * STAGES + 2 + buf), ((lt >> 1) & 1) ^ 1);
+                tc_fence_after();
+                const uint32_t dcol = tmem_base + buf * BN;
+                for (int kb = 0; kb < num_kb; ++kb, ++it) {
+                    const int s = it % STAGES, ph = (it / STAGES) & 1;
+                    mbar_wait(bars + 8 * s, ph);
+                    tc_fence_after();
+                    const uint32_t sa = base + s * STAGE_BYTES;
+                    const uint64_t ad = make_desc(sa, 16, 1024), bd = make_desc(sa + STAGE_A_BYTES, 16, 1024);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) umma_bf16_pair(dcol, ad + 2 * k, bd + 2 * k, idesc, (kb | k) ? 1u : 0u);
+                    umma_commit_pair(bars + 8 * (STAGES + s));
+                }
+                umma_commit_pair(bars + 8 * (2 * STAGES + buf));
+            }
+        }
+    } else {
+        const int wq = warp & 3;
+        const int row = wq * 32 + lane;
+        const int et = threadIdx.x - 64;                       // 0..255: 8 epilogue warps, 2 per TMEM lane group
+        const int half = (warp - 2) >> 2;                      // which interleaved set of 32-column chunks
+        float* tile = epi + (warp - 2) * (32 * 17);
+        float* wsum_all = epi + 8 * 32 * 17;                   // [4 lane groups][2*BN] running column sums of this CTA
+        float* wsum = wsum_all + wq * (2 * BN);
+        int lt = 0, cur_n = -1;
+        auto flush = [&](int n_tile) {                         // all 128 epilogue threads
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            for (int ch = et; ch < BN; ch += 256) {
+                float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+                for (int w = 0; w < 4; ++w) {
+                    s1 += wsum_all[w * 2 * BN + ch];
+                    s2 += wsum_all[w * 2 * BN + BN + ch];
+                    wsum_all[w * 2 * BN + ch] = 0.f;
+                    wsum_all[w * 2 * BN + BN + ch] = 0.f;
+                }
+                atomicAdd(&p.stats[n_tile * BN + ch], (double)s1);
+                atomicAdd(&p.stats[p.Cout + n_tile * BN + ch], (double)s2);
+            }
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+        };
+        for (int t = cid; t < total; t += nclusters, ++lt) {
+            const int n_t = t / num_m, m_t = t - n_t * num_m;
+            const int n0 = n_t * BN;
+            const int buf = lt & 1;
+            if (p.stats && cur_n >= 0 && cur_n != n_t) flush(cur_n);
+            cur_n = n_t;
+            const long long q = (long long)m_t * 256 + rank * 128 + row;
+            bool valid = q < p.Q;
+            if (valid && p.stats) {
+                int x = (int)(q % p.PW);
+                int y = (int)((q / p.PW) % p.PH);
+                valid = x < p.VW && y < p.VH;
+            }
+            mbar_wait(bars + 8 * (2 * STAGES + buf), (lt >> 1) & 1);
+            tc_fence_after();
+#pragma unroll 1
+            for (int c = half; c < BN / 32; c += 2) {
+                uint32_t r[32];
+                tmem_ld32(tmem_base + ((uint32_t)(wq * 32) << 16) + buf * BN + c * 32, r);
+                float v[32];
+                if (p.bias && ((reinterpret_cast<uintptr_t>(p.bias) & 15) == 0)) {
+                    const float4* bp = reinterpret_cast<const float4*>(p.bias + n0 + c * 32);
+#pragma unroll
+                    for (int g = 0; g < 8; ++g) {
+                        const float4 bv = bp[g];
+                        v[4 * g] = __uint_as_float(r[4 * g]) + bv.x; v[4 * g + 1] = __uint_as_float(r[4 * g + 1]) + bv.y;
+                        v[4 * g + 2] = __uint_as_float(r[4 * g + 2]) + bv.z; v[4 * g + 3] = __uint_as_float(r[4 * g + 3]) + bv.w;
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) + (p.bias ? p.bias[n0 + c * 32 + j] : 0.f);
+                }
+                if (q < p.Q) {
+                    uint4* dst = reinterpret_cast<uint4*>(p.out + q * p.Cout + n0 + c * 32);
+#pragma unroll
+                    for (int g = 0; g < 4; ++g) {
+                        uint4 u;
+                        __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) h[e] = __floats2bfloat162_rn(v[g * 8 + 2 * e], v[g * 8 + 2 * e + 1]);
+                        dst[g] = u;
+                    }
+                }
+                if (p.stats) {
+                    // column sums over the warp's 32 rows, 16 columns at a time through a 32x17 shared tile: lane l sums
+                    // column (l & 15) over rows [16 (l >> 4), +16), the two row halves are combined with one shuffle
+#pragma unroll
+                    for (int hc = 0; hc < 2; ++hc) {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) tile[lane * 17 + j] = valid ? v[hc * 16 + j] : 0.f;
+                        __syncwarp();
+                        float s1 = 0.f, s2 = 0.f;
+                        const int col = lane & 15, r0 = (lane >> 4) * 16;
+#pragma unroll
+                        for (int rr = 0; rr < 16; ++rr) {
+                            float tv = tile[(r0 + rr) * 17 + col];
+                            s1 += tv;
+                            s2 = fmaf(tv, tv, s2);
+                        }
+                        s1 += __shfl_xor_sync(0xffffffffu, s1, 16);
+                        s2 += __shfl_xor_sync(0xffffffffu, s2, 16);
+                        if (lane < 16) {
+                            wsum[c * 32 + hc * 16 + col] += s1;
+                            wsum[BN + c * 32 + hc * 16 + col] += s2;
+                        }
+                        __syncwarp();
+                    }
+                }
+            }
+            // every epilogue thread has drained its TMEM rows: release the accumulator buffer to the MMA warp
+            tc_fence_before();
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            if (et == 0) mbar_arrive_leader(bars + 8 * (2 * STAGES + 2 + buf));
+        }
+        if (p.stats && cur_n >= 0) flush(cur_n);
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();                                         // no remote signal may target a CTA that has exited
+    if (warp == 1) {
+        __syncwarp();
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(2 * BN) : "memory");
+    }
+}
+
 // Variant for thin layers (taps*Cin*BN*2 bytes <= RES_BYTES): the whole weight tile set of this CTA's channel tile stays
 // RESIDENT in shared memory (loaded once), the ring streams only the activation tiles.  Halves the L2->SM traffic of
 // the 64/128-channel layers at 128x128 and removes the all-SMs-read-the-same-16KB hot spot on the weight lines.
@@ -1017,6 +1259,25 @@ static int launch_conv_persist(cudaStream_t st, const CUtensorMap& a, const CUte
     return KP_OK;
 }
 
+template <int BN, int STAGES>
+static int launch_conv_pair(cudaStream_t st, const CUtensorMap& a, const CUtensorMap& b, const ConvTcParams& p) {
+    constexpr int smem = STAGES * (STAGE_A_BYTES + (BN / 2) * 128) + (8 * 32 * 17 + 4 * 2 * BN) * 4 +
+                         8 * (2 * STAGES + 4) + 16 + 1024;
+    static_assert(smem <= 227 * 1024, "shared memory budget");
+    static bool attr_done = false;
+    if (!attr_done) {
+        KP_CUDA(cudaFuncSetAttribute(conv_tc_pair_k<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        attr_done = true;
+    }
+    long long total = ((p.Q + 255) / 256) * (p.Cout / BN);
+    int clusters = kp_sm_count() / 2;
+    if (clusters > total) clusters = (int)total;
+    if (clusters < 1) clusters = 1;
+    conv_tc_pair_k<BN, STAGES><<<2 * clusters, 320, smem, st>>>(a, b, p);
+    KP_LAUNCH_CHECK();
+    return KP_OK;
+}
+
 template <int BN, int STAGES, int RES_BYTES>
 static int launch_conv_resident(cudaStream_t st, const CUtensorMap& a, const CUtensorMap& b, const ConvTcParams& p) {
     constexpr int smem = STAGES * STAGE_A_BYTES + RES_BYTES + (8 * 32 * 17 + 4 * 2 * BN) * 4 + 8 * (2 * STAGES + 5) + 16 + 1024;
@@ -1082,6 +1343,15 @@ extern "C" int kp_conv_tc(kp_stream stream, const void* in_bf16, int64_t Q, int 
         if (res_on && wbytes <= RES && Q >= 128LL * kp_sm_count()) {
             if (BN == 128) return launch_conv_resident<128, 3, RES>(st, ta, tb, p);
             if (BN == 64) return launch_conv_resident<64, 3, RES>(st, ta, tb, p);
+        }
+        static int pair_on = -1;
+        if (pair_on < 0) { const char* e = getenv("KP_TC_PAIR"); pair_on = (e && e[0] == '0') ? 0 : 1; }
+        if (pair_on && BN >= 128 && Q >= 256) {
+            CUtensorMap tbh;                                   // each CTA of the pair loads half of the weight tile
+            rc = make_map(&tbh, wt_bf16, (long long)taps * Cout, Cin, BN / 2);
+            if (rc) return rc;
+            if (BN == 256) return launch_conv_pair<256, 6>(st, ta, tbh, p);
+            return launch_conv_pair<128, 8>(st, ta, tbh, p);
         }
         if (BN == 256) return launch_conv_persist<256, 4>(st, ta, tb, p);
         if (BN == 128) return launch_conv_persist<128, 5>(st, ta, tb, p);
