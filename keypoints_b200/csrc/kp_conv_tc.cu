@@ -1157,6 +1157,151 @@ wgrad_tc_persist_k(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     }
 }
 
+// CTA-pair weight gradient: D[256 (M channels)][BN (N channels)], each CTA stages its 128 M-channels of one operand and
+// BN/2 N-channels of the other (MN-major boxes of 64 channels x 64 pixels); one M=256 MMA stream issued by the leader.
+template <int BN, int STAGES>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(192, 1)
+wgrad_tc_pair_k(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const WgradTcParams p,
+                   int taps) {
+    constexpr int BOX_BYTES = 64 * 128;
+    constexpr int A_BYTES = 2 * BOX_BYTES;
+    constexpr int B_BYTES = (BN / 128) * BOX_BYTES;           // this CTA's half of the N operand
+    constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* gen_base = smem_raw + (base - smem_u32(smem_raw));
+    const uint32_t bars = base + STAGES * STAGE_BYTES;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gen_base + STAGES * STAGE_BYTES + 8 * (2 * STAGES + 4));
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const bool leader = rank == 0;
+    const int num_m = p.Mtot / 256, num_n = p.Ntot / BN;
+    // work item = (split, tap, n tile, m tile); m fastest so the CTAs of one wave share the same pixel range
+    const int total = num_m * num_n * taps * p.splits;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmA);
+        tma_prefetch_desc(&tmB);
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(bars + 8 * s, 1);
+            mbar_init(bars + 8 * (STAGES + s), 1);
+        }
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(bars + 8 * (2 * STAGES + b), 1);
+            mbar_init(bars + 8 * (2 * STAGES + 2 + b), 2);
+        }
+        fence_barrier_init();
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(2 * BN) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const int nclusters = gridDim.x >> 1, cid = blockIdx.x >> 1;
+
+    auto decode = [&](int t, int& m0, int& n0, int& tap, long long& qbeg, int& nkb) {
+        int mt = t % num_m; t /= num_m;
+        int nt = t % num_n; t /= num_n;
+        tap = t % taps;
+        int split = t / taps;
+        m0 = mt * 256 + (int)rank * 128; n0 = nt * BN + (int)rank * (BN / 2);
+        qbeg = (long long)split * p.kchunk;
+        long long qend = qbeg + p.kchunk;
+        if (qend > p.Q) qend = p.Q;
+        nkb = qend > qbeg ? (int)((qend - qbeg + 63) / 64) : 0;
+    };
+
+    if (warp == 0) {
+        if (elect_one()) {
+            int it = 0;
+            for (int t = cid; t < total; t += nclusters) {
+                int m0, n0, tap, nkb;
+                long long qbeg;
+                decode(t, m0, n0, tap, qbeg, nkb);
+                for (int kb = 0; kb < nkb; ++kb, ++it) {
+                    const int s = it % STAGES, ph = (it / STAGES) & 1;
+                    mbar_wait(bars + 8 * (STAGES + s), ph ^ 1);
+                    const uint32_t full = bars + 8 * s;
+                    if (leader) mbar_expect_tx(full, 2 * STAGE_BYTES);
+                    const long long q = qbeg + (long long)kb * 64;
+                    const uint32_t sa = base + s * STAGE_BYTES;
+#pragma unroll
+                    for (int b = 0; b < 2; ++b)
+                        tma_load_2d_pair(sa + b * BOX_BYTES, &tmA, m0 + b * 64, (int)(q + p.shiftA[tap]), full);
+#pragma unroll
+                    for (int b = 0; b < BN / 128; ++b)
+                        tma_load_2d_pair(sa + A_BYTES + b * BOX_BYTES, &tmB, n0 + b * 64, (int)(q + p.shiftB[tap]), full);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (leader && elect_one()) {
+            constexpr uint32_t idesc = make_idesc_m256(BN) | (1u << 15) | (1u << 16);
+            int it = 0, lt = 0;
+            for (int t = cid; t < total; t += nclusters, ++lt) {
+                int m0, n0, tap, nkb;
+                long long qbeg;
+                decode(t, m0, n0, tap, qbeg, nkb);
+                const int buf = lt & 1;
+                mbar_wait(bars + 8 * (2 * STAGES + 2 + buf), ((lt >> 1) & 1) ^ 1);
+                tc_fence_after();
+                const uint32_t dcol = tmem_base + buf * BN;
+                for (int kb = 0; kb < nkb; ++kb, ++it) {
+                    const int s = it % STAGES, ph = (it / STAGES) & 1;
+                    mbar_wait(bars + 8 * s, ph);
+                    tc_fence_after();
+                    const uint32_t sa = base + s * STAGE_BYTES;
+                    const uint64_t ad = make_desc(sa, BOX_BYTES, 1024), bd = make_desc(sa + A_BYTES, BOX_BYTES, 1024);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) umma_bf16_pair(dcol, ad + 128 * k, bd + 128 * k, idesc, (kb | k) ? 1u : 0u);
+                    umma_commit_pair(bars + 8 * (STAGES + s));
+                }
+                umma_commit_pair(bars + 8 * (2 * STAGES + buf));
+            }
+        }
+    } else {
+        const int wq = warp & 3;
+        const int row = wq * 32 + lane;
+        const int et = threadIdx.x - 64;
+        int lt = 0;
+        for (int t = cid; t < total; t += nclusters, ++lt) {
+            int m0, n0, tap, nkb;
+            long long qbeg;
+            decode(t, m0, n0, tap, qbeg, nkb);
+            const int buf = lt & 1;
+            mbar_wait(bars + 8 * (2 * STAGES + buf), (lt >> 1) & 1);
+            tc_fence_after();
+            if (nkb > 0) {
+                float* dst_row = p.stg + ((long long)tap * p.Mtot + m0 + row) * p.Ntot + (n0 - (int)rank * (BN / 2));
+#pragma unroll 1
+                for (int c = 0; c < BN / 32; ++c) {
+                    uint32_t r[32];
+                    tmem_ld32(tmem_base + ((uint32_t)(wq * 32) << 16) + buf * BN + c * 32, r);
+#pragma unroll
+                    for (int g = 0; g < 8; ++g)
+                        red_add_v4(dst_row + c * 32 + g * 4, __uint_as_float(r[4 * g]), __uint_as_float(r[4 * g + 1]),
+                                   __uint_as_float(r[4 * g + 2]), __uint_as_float(r[4 * g + 3]));
+                }
+            }
+            tc_fence_before();
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            if (et == 0) mbar_arrive_leader(bars + 8 * (2 * STAGES + 2 + buf));
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    if (warp == 1) {
+        __syncwarp();
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(2 * BN) : "memory");
+    }
+}
+
 // staging [t][a][b] -> dw_oihw[co][ci][t] (+=), a/b = (co,ci) or (ci,co)
 __global__ void wgrad_finalize_k(const float* __restrict__ stg, float* __restrict__ dw, int taps, int Cout, int Cin,
                                  int CinStg, int m_is_cout) {
@@ -1299,6 +1444,23 @@ static int launch_conv_resident(cudaStream_t st, const CUtensorMap& a, const CUt
 }
 
 template <int BN, int STAGES>
+static int launch_wgrad_pair(cudaStream_t st, const CUtensorMap& a, const CUtensorMap& b, const WgradTcParams& p, int taps) {
+    constexpr int smem = STAGES * (2 * 8192 + (BN / 128) * 8192) + 8 * (2 * STAGES + 4) + 16 + 1024;
+    static bool attr_done = false;
+    if (!attr_done) {
+        KP_CUDA(cudaFuncSetAttribute(wgrad_tc_pair_k<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        attr_done = true;
+    }
+    long long total = (long long)(p.Mtot / 256) * (p.Ntot / BN) * taps * p.splits;
+    int clusters = kp_sm_count() / 2;
+    if (clusters > total) clusters = (int)total;
+    if (clusters < 1) clusters = 1;
+    wgrad_tc_pair_k<BN, STAGES><<<2 * clusters, 192, smem, st>>>(a, b, p, taps);
+    KP_LAUNCH_CHECK();
+    return KP_OK;
+}
+
+template <int BN, int STAGES>
 static int launch_wgrad_persist(cudaStream_t st, const CUtensorMap& a, const CUtensorMap& b, const WgradTcParams& p, int taps) {
     constexpr int smem = STAGES * (2 * 8192 + (BN / 64) * 8192) + 8 * (2 * STAGES + 4) + 16 + 1024;
     static bool attr_done = false;
@@ -1362,6 +1524,30 @@ extern "C" int kp_conv_tc(kp_stream stream, const void* in_bf16, int64_t Q, int 
     return launch_conv<64, 4>(st, ta, tb, p);
 }
 
+// Split the pixel range so that (tiles * splits) work items fill `workers` persistent CTAs (or clusters) in whole
+// rounds: maximise total / (ceil(total / workers) * workers), prefer fewer splits (longer K per item) on ties.
+static void choose_split(int tiles, int workers, long long blocks64, long long* kchunk, int* splits) {
+    long long max_sp = blocks64 / 8;
+    if (max_sp < 1) max_sp = 1;
+    long long lim = (4LL * workers + tiles - 1) / tiles;
+    if (lim < 1) lim = 1;
+    if (max_sp > lim) max_sp = lim;
+    double best = -1.0;
+    long long best_sp = 1;
+    for (long long sp = 1; sp <= max_sp; ++sp) {
+        long long per = (blocks64 + sp - 1) / sp;
+        long long real = (blocks64 + per - 1) / per;
+        long long total = real * tiles;
+        long long rounds = (total + workers - 1) / workers;
+        double eff = (double)total / (double)(rounds * workers);
+        if (total < workers) eff *= 0.5;                     // not even one full round: keep splitting
+        if (eff > best + 0.02) { best = eff; best_sp = real; }
+    }
+    long long per = (blocks64 + best_sp - 1) / best_sp;
+    *splits = (int)((blocks64 + per - 1) / per);
+    *kchunk = per * 64;
+}
+
 // dw_oihw[co][ci][t] += sum_q dy[q][co] * x[q + shifts[t]][ci];  x: bf16 [Q][CinP] (CinP >= Cin, extra
 // channels ignored), dy: bf16 [Q][Cout] with zero rows wherever the product must not count.
 // stg: fp32 workspace of taps*Cout*CinP floats (zeroed here).
@@ -1388,15 +1574,17 @@ extern "C" int kp_conv_wgrad_tc(kp_stream stream, const void* x_bf16, const void
     }
     const int tiles = (Mtot / 128) * (Ntot / BN) * taps;
     long long blocks64 = (Q + 63) / 64;
-    long long splits = (2LL * kp_sm_count() + tiles - 1) / tiles;
-    if (splits > blocks64 / 8) splits = blocks64 / 8;
-    if (splits < 1) splits = 1;
-    long long per = (blocks64 + splits - 1) / splits;
-    splits = (blocks64 + per - 1) / per;
-    p.kchunk = per * 64;
-    p.splits = (int)splits;
+    choose_split(tiles, kp_sm_count(), blocks64, &p.kchunk, &p.splits);
     KP_CUDA(cudaMemsetAsync(stg, 0, sizeof(float) * (size_t)taps * Mtot * Ntot, st));
-    if (use_persistent()) {
+    static int wpair_on = -1;
+    if (wpair_on < 0) { const char* e = getenv("KP_TC_PAIR"); wpair_on = (e && e[0] == '0') ? 0 : 1; }
+    if (use_persistent() && wpair_on && Mtot % 256 == 0 && BN >= 128) {
+        // recompute the split for 256-row tiles
+        const int tiles2 = (Mtot / 256) * (Ntot / BN) * taps;
+        choose_split(tiles2, kp_sm_count() / 2, blocks64, &p.kchunk, &p.splits);
+        if (BN == 256) rc = launch_wgrad_pair<256, 6>(st, ta, tb, p, taps);
+        else rc = launch_wgrad_pair<128, 8>(st, ta, tb, p, taps);
+    } else if (use_persistent()) {
         if (BN == 256) rc = launch_wgrad_persist<256, 4>(st, ta, tb, p, taps);
         else if (BN == 128) rc = launch_wgrad_persist<128, 6>(st, ta, tb, p, taps);
         else rc = launch_wgrad_persist<64, 8>(st, ta, tb, p, taps);
