@@ -55,6 +55,9 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* tm,
         ::"r"(dst), "l"((uint64_t)tm), "r"(c0), "r"(c1), "r"(bar)
         : "memory");
 }
+__device__ __forceinline__ void tma_prefetch_l2_2d(const CUtensorMap* tm, int c0, int c1) {
+    asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"((uint64_t)tm), "r"(c0), "r"(c1) : "memory");
+}
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* tm) {
     asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)tm) : "memory");
 }
@@ -120,6 +123,7 @@ __host__ __device__ constexpr uint32_t make_idesc(int n, int a_mn_major, int b_m
 }
 
 constexpr int STAGE_A_BYTES = 128 * 128;   // 128 rows x 64 bf16
+constexpr int PF_TILES = 3;                // L2 prefetch distance of the persistent producers, in rounds of tiles
 
 struct ConvTcParams {
     long long Q;
@@ -435,6 +439,15 @@ conv_tc_persist_k(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                 const int n_t = t / num_m, m_t = t - n_t * num_m;
                 const long long q0 = (long long)m_t * 128;
                 const int n0 = n_t * BN;
+                {   // pull the not-yet-touched activation rows of a tile several rounds ahead into L2 (DRAM latency
+                    // is otherwise exposed when the K loop of a tile is short)
+                    const int tp = t + PF_TILES * (int)gridDim.x;
+                    if (tp < total) {
+                        const int mp = tp - (tp / num_m) * num_m;
+                        for (int kc = 0; kc < kchunks; ++kc)
+                            tma_prefetch_l2_2d(&tmA, kc * 64, (int)((long long)mp * 128 + p.shift[p.taps - 1]));
+                    }
+                }
                 for (int kb = 0; kb < num_kb; ++kb, ++it) {
                     const int s = it % STAGES, ph = (it / STAGES) & 1;
                     mbar_wait(bars + 8 * (STAGES + s), ph ^ 1);
@@ -676,6 +689,14 @@ conv_tc_pair_k(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 const int n_t = t / num_m, m_t = t - n_t * num_m;
                 const long long q0 = (long long)m_t * 256 + rank * 128;
                 const int n0 = n_t * BN + rank * (BN / 2);
+                {
+                    const int tp = t + PF_TILES * nclusters;
+                    if (tp < total) {
+                        const int mp = tp - (tp / num_m) * num_m;
+                        for (int kc = 0; kc < kchunks; ++kc)
+                            tma_prefetch_l2_2d(&tmA, kc * 64, (int)((long long)mp * 256 + rank * 128 + p.shift[p.taps - 1]));
+                    }
+                }
                 for (int kb = 0; kb < num_kb; ++kb, ++it) {
                     const int s = it % STAGES, ph = (it / STAGES) & 1;
                     mbar_wait(bars + 8 * (STAGES + s), ph ^ 1);
@@ -880,6 +901,12 @@ conv_tc_resident_k(const __grid_constant__ CUtensorMap tmA, const __grid_constan
             }
             for (int t = blockIdx.x; t < total; t += gridDim.x) {
                 const long long q0 = (long long)t * 128;
+                {
+                    const int tp = t + PF_TILES * (int)gridDim.x;
+                    if (tp < total)
+                        for (int kc = 0; kc < kchunks; ++kc)
+                            tma_prefetch_l2_2d(&tmA, kc * 64, (int)((long long)tp * 128 + p.shift[p.taps - 1]));
+                }
                 for (int kb = 0; kb < num_kb; ++kb, ++it) {
                     const int s = it % STAGES, ph = (it / STAGES) & 1;
                     mbar_wait(bars + 8 * (STAGES + s), ph ^ 1);
