@@ -1,0 +1,103 @@
+"""Turn the ncu outputs in gpurun_out/ into the tracked summaries under profiles/ (run in the build container)."""
+import collections
+import csv
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+OUT = os.path.join(ROOT, 'profiles')
+TAG = sys.argv[1] if len(sys.argv) > 1 else 'r1'
+
+METRICS = ['gpu__time_duration.sum', 'launch__grid_size', 'launch__block_size', 'launch__registers_per_thread',
+           'launch__shared_mem_per_block_dynamic', 'sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed',
+           'sm__throughput.avg.pct_of_peak_sustained_elapsed', 'gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed',
+           'dram__bytes_read.sum', 'dram__bytes_write.sum', 'lts__throughput.avg.pct_of_peak_sustained_elapsed',
+           'l1tex__throughput.avg.pct_of_peak_sustained_elapsed', 'sm__warps_active.avg.pct_of_peak_sustained_active',
+           'smsp__issue_active.avg.pct_of_peak_sustained_active']
+
+
+def launches():
+    path = os.path.join(ROOT, 'gpurun_out', 'launches_graph.csv')
+    if not os.path.exists(path):
+        return
+    rows = list(csv.reader(open(path)))
+    hi = next(i for i, r in enumerate(rows) if r and r[0] == 'ID')
+    hdr = rows[hi]
+    data = [r for r in rows[hi + 1:] if len(r) >= len(hdr) - 1]
+    ki, vi, ui = hdr.index('Kernel Name'), hdr.index('Metric Value'), hdr.index('Metric Unit')
+    names = [r[ki].split('(')[0].replace('void ', '').replace('<unnamed>::', '') for r in data]
+    vals = []
+    for r in data:
+        v = float(r[vi].replace(',', ''))
+        vals.append(v / 1e6 if r[ui] == 'ns' else v / 1e3 if r[ui] == 'us' else v)
+    idx = [i for i, n in enumerate(names) if n.startswith('adam_k')]
+    a, b = idx[-2] + 1, idx[-1] + 1
+    agg = collections.OrderedDict()
+    for n, v in zip(names[a:b], vals[a:b]):
+        d = agg.setdefault(n[:70], [0, 0.0])
+        d[0] += 1
+        d[1] += v
+    tot = sum(vals[a:b])
+    with open(os.path.join(OUT, f'{TAG}_launches_one_step.md'), 'w') as fh:
+        fh.write(f'# One graph-replayed training step, per-kernel device time ({TAG})\n\n')
+        fh.write('Command: `ncu --metrics gpu__time_duration.sum --clock-control none --csv python bench.py --steps 2 --warmup 3 '
+                 '--no-cpu-baseline --no-kernel-timing` (KeyNet F 128x128 K=10, batch 64, bf16).  Launches between the last two '
+                 '`adam_k` launches = one step.  ncu serialises kernels and runs them cold: compare SHARES, not absolutes.\n\n')
+        fh.write(f'{b - a} kernel launches, sum {tot:.3f} ms\n\n| ms | share | launches | kernel |\n|---:|---:|---:|---|\n')
+        for k, d in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+            fh.write(f'| {d[1]:.3f} | {100 * d[1] / tot:.1f}% | {d[0]} | `{k}` |\n')
+        tc = sum(d[1] for k, d in agg.items() if 'tc_' in k)
+        fh.write(f'\ntcgen05 conv family share of the step: {100 * tc / tot:.1f}%\n')
+    with open(os.path.join(OUT, f'{TAG}_launches_one_step.csv'), 'w') as fh:
+        fh.write('kernel,ms\n')
+        for n, v in zip(names[a:b], vals[a:b]):
+            fh.write(f'"{n}",{v:.5f}\n')
+
+
+def reports():
+    lines = [f'# ncu --set full summaries ({TAG})\n',
+             'Captured with `ncu --set full --clock-control none --import-source on -k regex:<kernel> ... python bench.py --steps 1 '
+             '--warmup 3 --no-graph ...` on one B200; values per launch.\n']
+    for f in sorted(os.listdir(os.path.join(ROOT, 'gpurun_out'))):
+        if not f.endswith('.ncu-rep') or not f.startswith('prof_'):
+            continue
+        out = subprocess.run(['ncu', '-i', os.path.join(ROOT, 'gpurun_out', f), '--page', 'raw', '--csv'], capture_output=True,
+                             text=True).stdout
+        rows = list(csv.reader(out.splitlines()))
+        if len(rows) < 3:
+            continue
+        hdr, units = rows[0], rows[1]
+        lines.append(f'\n## {f}\n')
+        for r in rows[2:]:
+            name = r[hdr.index('Kernel Name')][:110]
+            lines.append(f'\n`{name}`\n\n| metric | value |\n|---|---|\n')
+            for m in METRICS:
+                if m in hdr:
+                    i = hdr.index(m)
+                    lines.append(f'| {m} | {r[i]} {units[i]} |\n')
+    with open(os.path.join(OUT, f'{TAG}_ncu_full_summary.md'), 'w') as fh:
+        fh.writelines(lines)
+
+
+def sass():
+    so = os.path.join(ROOT, 'keypoints_b200', 'lib', 'libkeypoints_b200.so')
+    txt = subprocess.run(['cuobjdump', '-sass', so], capture_output=True, text=True).stdout
+    c = collections.Counter()
+    import re
+    for m in re.finditer(r'\b(UTCHMMA[.A-Z0-9]*|UTMALDG[.A-Z0-9_]*|UTMAPF[.A-Z0-9_]*|UTCBAR[.A-Z0-9_]*|LDTM[.A-Z0-9_]*|HMMA[.A-Z0-9_]*|REDG[.A-Z0-9_]*|SYNCS[.A-Z0-9_]*)', txt):
+        c[m.group(1)] += 1
+    with open(os.path.join(OUT, f'{TAG}_sass_evidence.md'), 'w') as fh:
+        fh.write(f'# SASS mnemonics in libkeypoints_b200.so ({TAG})\n\n`cuobjdump -sass keypoints_b200/lib/libkeypoints_b200.so`\n\n| mnemonic | count |\n|---|---:|\n')
+        for k, v in sorted(c.items()):
+            fh.write(f'| {k} | {v} |\n')
+        fh.write('\nUTCHMMA = tcgen05.mma (`.2CTA` = cta_group::2), UTMALDG = cp.async.bulk.tensor (TMA), LDTM = tcgen05.ld, '
+                 'UTCBAR = tcgen05.commit; no HMMA (legacy mma.sync) anywhere.\n')
+
+
+if __name__ == '__main__':
+    os.makedirs(OUT, exist_ok=True)
+    launches()
+    reports()
+    sass()
+    print(os.listdir(OUT))

@@ -72,3 +72,34 @@ def test_checkpoint_roundtrip(built, tmp_path):
     b = transporter.make('VGG_PONG_LAYERNECK', 1, 16, 4, load=str(tmp_path / 'ck'))
     for (k1, v1), (k2, v2) in zip(a.state_dict().items(), b.state_dict().items()):
         assert k1 == k2 and torch.equal(v1, v2)
+
+
+def test_dropin_aliases_reference_import_paths(built):
+    """after dropin.install() the reference scripts' own import statements resolve to this package."""
+    import importlib
+    import sys
+    saved = {k: sys.modules.get(k) for k in ('keypoints', 'keypoints.models', 'tps', 'data_augments', 'apex', 'apex.amp')}
+    try:
+        from keypoints_b200 import dropin
+        dropin.install()
+        from keypoints.models import transporter, keynet, knn, vgg, functional      # noqa: F401  (transporter.py:11-12)
+        from tps import tps_transform, rotate_affine_grid_multi, tps_sample_params    # noqa: F401
+        from data_augments import TpsAndRotate, nop                                   # noqa: F401  (transporter.py:6)
+        from apex import amp
+        net = transporter.make('VGG_PONG_LAYERNECK', 1, 16, 4)
+        assert hasattr(net, 'feature') and hasattr(net, 'keypoint') and hasattr(net, 'decoder') and hasattr(net, 'ssm')
+        m, o = amp.initialize(net, None, opt_level='O0')
+        assert m is net
+        with amp.scale_loss(1.0, None) as sl:
+            assert sl == 1.0
+        assert nop(1, 2) == (1, 2, None)
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v
+        for k in [k for k in sys.modules if k.startswith('keypoints.models.')]:
+            sys.modules.pop(k, None)
+        import keypoints_b200
+        keypoints_b200.set_precision('fp32')

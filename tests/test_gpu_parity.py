@@ -340,3 +340,91 @@ def test_bf16_tensor_core_step_vs_oracle(dev, golden, name, kind, model_type):
     print(f'bf16 end-to-end deviation {name}: k {ek:.3e}  x_hat {ex:.3e}  loss {el:.3e}')
     assert ek < 0.2 and ex < 0.35 and el < 0.1
     assert torch.isfinite(tr.flat_p).all()
+
+
+def test_reference_script_loop_through_dropin(dev):
+    """The reference's inner loop (transporter.py:75-89 / keypoints.py:70-84) written against the reference's own
+    import paths, resolved by keypoints_b200.dropin: augment -> zero_grad -> forward -> L2 loss -> backward -> Adam,
+    three steps in bf16 (tensor-core) mode.  Checks the API contract (shapes, finiteness, loss decreases on a fixed batch)."""
+    import sys
+    import keypoints_b200
+    from keypoints_b200 import dropin
+    saved = {k: sys.modules.get(k) for k in ('keypoints', 'keypoints.models', 'tps', 'data_augments', 'apex', 'apex.amp')}
+    try:
+        dropin.install()
+        from keypoints.models import transporter
+        from data_augments import TpsAndRotate
+        from apex import amp
+        torch.manual_seed(3)
+        net = transporter.make('F', 3, 64, 10).to(dev)
+        optim = torch.optim.Adam(net.parameters(), lr=1e-4)
+        net, optim = amp.initialize(net, optim, opt_level='O2')          # -> bf16 tensor-core mode
+        assert keypoints_b200.get_precision() == 'bf16'
+        augment = TpsAndRotate(4, 0.05, 0.1)
+        x = torch.rand(4, 3, 64, 64, device=dev)
+        torch.manual_seed(5)
+        xa, xb, mask = augment(x, x)
+        losses = []
+        for _ in range(3):
+            optim.zero_grad()
+            x_t, phi, k, m, p, heat, mask_s, mask_t = net(xa, xb)
+            loss = ((x_t - xb) ** 2 * mask).mean()
+            with amp.scale_loss(loss, optim) as scaled:
+                scaled.backward()
+            optim.step()
+            losses.append(float(loss))
+        assert x_t.shape == (4, 3, 64, 64) and phi.shape == (4, 64, 8, 8) and k.shape == (4, 10, 2)
+        assert m.shape == (4, 10, 8, 8) and p[0].shape == (4, 10, 8) and heat.shape == (4, 10, 8, 8)
+        assert mask_s.shape == (4, 1, 8, 8) and mask_t.shape == (4, 1, 8, 8)
+        assert all(np.isfinite(losses)) and float(k.min()) >= 0.0 and float(k.max()) <= 1.0
+        assert losses[-1] < losses[0], losses
+        assert all(p_.grad is not None for n_, p_ in net.named_parameters() if n_.startswith(('decoder', 'keypoint', 'feature')))
+    finally:
+        for kk, v in saved.items():
+            if v is None:
+                sys.modules.pop(kk, None)
+            else:
+                sys.modules[kk] = v
+        for kk in [kk for kk in sys.modules if kk.startswith('keypoints.models.')]:
+            sys.modules.pop(kk, None)
+        keypoints_b200.set_precision('fp32')
+
+
+def _ddp_worker(rank, world, port, out):
+    import os
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    import torch.distributed as dist
+    from keypoints_b200 import parallel
+    from keypoints_b200.models import transporter
+    from keypoints_b200.trainer import Trainer
+    parallel.init_from_env('nccl')
+    dev = torch.device('cuda', rank)
+    torch.manual_seed(0)
+    net = transporter.make('VGG_PONG_LAYERNECK', 1, 16, 4)
+    tr = Trainer(net, precision='fp32', use_graph=False, device=dev)
+    g = torch.Generator().manual_seed(100 + rank)
+    a, b = torch.rand(2, 1, 40, 40, generator=g) * 2 - 1, torch.rand(2, 1, 40, 40, generator=g) * 2 - 1
+    tr._whole(a.to(dev), b.to(dev), None)
+    local = tr.flat_g.clone()
+    tr._allreduce()
+    gathered = [torch.zeros_like(local) for _ in range(world)]
+    dist.all_gather(gathered, local)
+    torch.cuda.synchronize()
+    err = float((tr.flat_g - sum(gathered)).abs().max() / sum(gathered).abs().max())
+    tr._adam()
+    out[rank] = (err, tr.flat_p.cpu())
+    dist.destroy_process_group()
+
+
+def test_ddp_two_gpus_allreduce_and_replicas_stay_identical(dev):
+    """World-size-2 NCCL run: the bucketed all-reduce equals the sum of the per-rank gradients and both replicas hold
+    identical parameters after the Adam step (needs 2 GPUs; skipped otherwise)."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip('needs 2 GPUs')
+    import socket
+    import torch.multiprocessing as mp
+    s = socket.socket(); s.bind(('127.0.0.1', 0)); port = s.getsockname()[1]; s.close()
+    out = mp.Manager().dict()
+    mp.spawn(_ddp_worker, args=(2, port, out), nprocs=2, join=True)
+    assert out[0][0] < 1e-6 and out[1][0] < 1e-6
+    assert torch.equal(out[0][1], out[1][1])
