@@ -66,7 +66,7 @@ class ClockSampler:
              'clocks_event_reasons.sw_power_cap')
         try:
             self.proc = subprocess.Popen(['nvidia-smi', f'--query-gpu={q}', '--format=csv,noheader,nounits', '-i', str(index),
-                                          '-lms', '100'], stdout=open(self.path, 'w'), stderr=subprocess.DEVNULL)
+                                          '-lms', '20'], stdout=open(self.path, 'w'), stderr=subprocess.DEVNULL)
         except OSError:
             self.proc = None
 

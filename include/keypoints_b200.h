@@ -98,6 +98,9 @@ int kp_conv_wgrad_tc(kp_stream stream, const void* x_bf16, const void* dy_bf16, 
  * ci_pad >= Cin pads the input-channel axis with zeros (KeyNet decoder: 74 -> 128). */
 int kp_pack_weights(kp_stream stream, const float* w_oihw, int Cout, int Cin, int ks, int ci_pad,
                     float* simt_f, float* simt_d, void* tc_f, void* tc_d);
+/* The same for n_layers tensors in ONE launch.  table_dev: device array of n_layers records of nine 64-bit
+ * fields {w, simt_f, simt_d, tc_f, tc_d (pointers, 0 = skip), Cout, Cin, ks, ci_pad}. */
+int kp_pack_weights_multi(kp_stream stream, const void* table_dev, int n_layers);
 
 /* ---------------------------------------------------------------------------------------------
  * Train-mode BatchNorm statistics -> per-channel affine (nn.BatchNorm2d, vgg.py:35, knn.py:117).
@@ -123,14 +126,24 @@ int kp_bn_act_fwd(kp_stream stream, const kp_view* y, const kp_view* out, const 
  * Pass 1 (reduce): dz = d/d(BatchNorm output) — fold + pool/upsample backward + activation backward — is written to
  * dy (nullable), and sums[0:C] += sum dz, sums[C:2C] += sum dz * xhat (double).  For layers without BatchNorm
  * (scale/shift/mean/invstd NULL) dy is the final gradient and sums[0:C] the bias gradient.
- * Pass 2 (apply, BatchNorm only), in place: dy = scale * (dy - sums[0]/count - xhat * sums[1]/count). */
+ * Pass 2 (apply, BatchNorm only), in place: dy = scale * (dy - sums[0]/count - xhat * sums[1]/count);
+ * dgamma / dbeta (nullable) receive sums[C:2C] / sums[0:C] (fused kp_bn_grad_finalize). */
 int kp_bn_act_bwd_reduce(kp_stream stream, const kp_view* dout, const kp_view* y, const kp_view* dy,
                          const float* scale, const float* shift, const float* mean,
                          const float* invstd, double* sums, int act, int post, int pad, int N,
                          int H, int W, int C);
 int kp_bn_act_bwd_apply(kp_stream stream, const kp_view* y, const kp_view* dy, const float* scale,
                         const float* mean, const float* invstd, const double* sums, double count,
-                        int N, int H, int W, int C);
+                        int N, int H, int W, int C, float* dgamma, float* dbeta);
+/* kp_bn_finalize + kp_bn_act_fwd in one launch when the vectorised path applies (otherwise the two
+ * kernels are launched back to back): every block derives its channels' affine from the batch
+ * statistics, block 0 publishes scale/shift/mean/invstd and updates the running statistics. */
+int kp_bn_finalize_act_fwd(kp_stream stream, const double* stats, double count, const float* gamma,
+                           const float* beta, float eps, float momentum, float* running_mean,
+                           float* running_var, int64_t* num_batches_tracked, float* scale,
+                           float* shift, float* save_mean, float* save_invstd, const kp_view* y,
+                           const kp_view* out, int act, int post, int pad, int N, int H, int W,
+                           int C);
 /* dgamma[c] = sums[C+c], dbeta[c] = sums[c] (any nullable; fp32, overwritten). */
 int kp_bn_grad_finalize(kp_stream stream, const double* sums, int C, float* dgamma, float* dbeta);
 

@@ -428,7 +428,44 @@ static int thin_grid(long long M) {
     return (int)(tiles < cap ? (tiles < 1 ? 1 : tiles) : cap);
 }
 
+// multi-tensor variant: one launch repacks every layer (blockIdx.y = layer), descriptors live in device memory
+struct PackDesc {
+    const float* w;
+    float* simt_f;
+    float* simt_d;
+    bf16* tc_f;
+    bf16* tc_d;
+    long long cout, cin, ks, ci_pad;
+};
+__global__ void pack_weights_multi_k(const PackDesc* __restrict__ table) {
+    const PackDesc d = table[blockIdx.y];
+    const int T = (int)(d.ks * d.ks), Cout = (int)d.cout, Cin = (int)d.cin, ci_pad = (int)d.ci_pad;
+    const long long total = (long long)T * Cout * ci_pad;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        int ci = (int)(i % ci_pad);
+        long long r = i / ci_pad;
+        int co = (int)(r % Cout);
+        int t = (int)(r / Cout);
+        float v = ci < Cin ? d.w[((long long)co * Cin + ci) * T + t] : 0.f;
+        int tf = T - 1 - t;
+        if (ci < Cin) {
+            if (d.simt_f) d.simt_f[((long long)t * Cin + ci) * Cout + co] = v;
+            if (d.simt_d) d.simt_d[((long long)tf * Cout + co) * Cin + ci] = v;
+        }
+        if (d.tc_f) d.tc_f[((long long)t * Cout + co) * ci_pad + ci] = __float2bfloat16_rn(v);
+        if (d.tc_d) d.tc_d[((long long)tf * ci_pad + ci) * Cout + co] = __float2bfloat16_rn(v);
+    }
+}
+
 }  // namespace
+
+extern "C" int kp_pack_weights_multi(kp_stream stream, const void* table_dev, int n_layers) {
+    KP_CHECK_ARG(table_dev && n_layers > 0 && n_layers <= 65535, "kp_pack_weights_multi: bad arguments");
+    dim3 grid((unsigned)(kp_sm_count() * 2), (unsigned)n_layers, 1);
+    pack_weights_multi_k<<<grid, 256, 0, (cudaStream_t)stream>>>((const PackDesc*)table_dev);
+    KP_LAUNCH_CHECK();
+    return KP_OK;
+}
 
 extern "C" int kp_conv_simt(kp_stream stream, const kp_view* in, const float* wk, const float* bias,
                             const kp_view* out, double* stats, int N, int OH, int OW, int IH, int IW, int Cin,

@@ -291,6 +291,50 @@ bn_act_bwd_reduce_k(View<TG> dout, View<TY> y, View<TD> dy, const float* __restr
 constexpr int V8 = 8;
 constexpr int UNR = 4;
 
+// Optional fused BatchNorm finalize: when stats != nullptr the forward kernels derive the per-channel affine from
+// the batch statistics themselves (every block recomputes its 8 channels; block 0 publishes scale / shift / mean /
+// invstd for the backward pass and updates the running statistics) — removes one dependent launch per layer.
+struct BnFuse {
+    const double* stats;
+    double count;
+    const float* gamma;
+    const float* beta;
+    float eps, momentum;
+    float* rmean;
+    float* rvar;
+    long long* nbt;
+    float* scale;
+    float* shift;
+    float* mean;
+    float* invstd;
+};
+
+__device__ __forceinline__ void fused_affine(const BnFuse& f, int C, int c0, bool publish, float (&sc)[8], float (&sh)[8]) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int c = c0 + i;
+        const double mean = f.stats[c] / f.count;
+        double var = f.stats[C + c] / f.count - mean * mean;
+        if (var < 0) var = 0;
+        const float invstd = (float)(1.0 / sqrt(var + (double)f.eps));
+        const float g = f.gamma ? f.gamma[c] : 1.f, b = f.beta ? f.beta[c] : 0.f;
+        sc[i] = g * invstd;
+        sh[i] = b - (float)mean * sc[i];
+        if (publish) {
+            f.scale[c] = sc[i];
+            f.shift[c] = sh[i];
+            if (f.mean) f.mean[c] = (float)mean;
+            if (f.invstd) f.invstd[c] = invstd;
+            if (f.rmean) f.rmean[c] = (1.f - f.momentum) * f.rmean[c] + f.momentum * (float)mean;
+            if (f.rvar) {
+                const double unb = f.count > 1 ? var * f.count / (f.count - 1) : var;
+                f.rvar[c] = (1.f - f.momentum) * f.rvar[c] + f.momentum * (float)unb;
+            }
+            if (c == 0 && f.nbt) *f.nbt += 1;
+        }
+    }
+}
+
 struct RowFold {   // rows / columns of a replicate-padded gradient that fold into one unpadded coordinate
     int n, v[3];
     __device__ __forceinline__ RowFold(int o, int O, int pad) {
@@ -324,14 +368,17 @@ __device__ __forceinline__ void raw_act(const typename Vec<T, V8>::Raw& r, const
 template <typename TI, typename TO, int POST>
 __global__ void __launch_bounds__(256, 2)
 bn_act_fwd_rows_k(View<TI> y, View<TO> out, const float* __restrict__ scale, const float* __restrict__ shift, int act,
-                  int pad, int N, int H, int W, int C, int OH, int OW, int cg_shift) {
+                  int pad, int N, int H, int W, int C, int OH, int OW, int cg_shift, const BnFuse fuse) {
     using RawI = typename Vec<TI, V8>::Raw;
     const int ncg = C >> 3;
     const int cg = threadIdx.x & (ncg - 1), c0 = cg * V8;
     const int x0 = threadIdx.x >> cg_shift, xstep = 256 >> cg_shift;
     float sc[V8], sh[V8];
+    if (fuse.stats) fused_affine(fuse, C, c0, blockIdx.x == 0 && x0 == 0, sc, sh);
+    else {
 #pragma unroll
-    for (int i = 0; i < V8; ++i) { sc[i] = scale ? scale[c0 + i] : 1.f; sh[i] = shift ? shift[c0 + i] : 0.f; }
+        for (int i = 0; i < V8; ++i) { sc[i] = scale ? scale[c0 + i] : 1.f; sh[i] = shift ? shift[c0 + i] : 0.f; }
+    }
     const int PH = OH + 2 * pad, PW = OW + 2 * pad, rows = N * PH;
     const float ry = (OH > 1) ? (float)(H - 1) / (float)(OH - 1) : 0.f;
     const float rx = (OW > 1) ? (float)(W - 1) / (float)(OW - 1) : 0.f;
@@ -577,7 +624,7 @@ template <typename TY, typename TD>
 __global__ void __launch_bounds__(256, 2)
 bn_bwd_apply_rows_k(View<TY> y, View<TD> dy, const float* __restrict__ scale, const float* __restrict__ mean,
                     const float* __restrict__ invstd, const double* __restrict__ sums, double count, int N, int H, int W,
-                    int C, int cg_shift) {
+                    int C, int cg_shift, float* dgamma, float* dbeta) {
     using RawY = typename Vec<TY, V8>::Raw;
     using RawD = typename Vec<TD, V8>::Raw;
     const int ncg = C >> 3;
@@ -591,6 +638,10 @@ bn_bwd_apply_rows_k(View<TY> y, View<TD> dy, const float* __restrict__ scale, co
         a0[i] = sc;
         a1[i] = -sc * is * m2;
         a2[i] = -sc * m1 + sc * is * m2 * mu;
+        if (blockIdx.x == 0 && x0 == 0) {           // fused kp_bn_grad_finalize
+            if (dbeta) dbeta[c0 + i] = (float)sums[c0 + i];
+            if (dgamma) dgamma[c0 + i] = (float)sums[C + c0 + i];
+        }
     }
     const int rows = N * H;
     for (int row = blockIdx.x; row < rows; row += gridDim.x) {
@@ -652,7 +703,7 @@ __device__ __forceinline__ float actf(float z, float slope) { return fmaxf(z, sl
 template <typename TI, typename TO>
 __global__ void __launch_bounds__(256, 2)
 bn_act_fwd_up_quad_k(View<TI> y, View<TO> out, const float* __restrict__ scale, const float* __restrict__ shift,
-                     float slope, int pad, int N, int H, int W, int C, int cg_shift) {
+                     float slope, int pad, int N, int H, int W, int C, int cg_shift, const BnFuse fuse) {
     // Outputs (2k, 2k+1) x (2j, 2j+1).  With src = r * dst, r = (H-1)/(2H-1): floor(r*2k) = k-1 (k >= 1) and
     // floor(r*(2k+1)) = k, so output row 2k blends input rows (k-1, k) and row 2k+1 blends (k, k+1): a fixed
     // 3x3 window, no index selects.  The fractions come from the same float formula PyTorch uses.
@@ -662,8 +713,11 @@ bn_act_fwd_up_quad_k(View<TI> y, View<TO> out, const float* __restrict__ scale, 
     const int cg = threadIdx.x & (ncg - 1), c0 = cg * V8;
     const int x0 = threadIdx.x >> cg_shift, xstep = 256 >> cg_shift;
     float sc[V8], sh[V8];
+    if (fuse.stats) fused_affine(fuse, C, c0, blockIdx.x == 0 && x0 == 0, sc, sh);
+    else {
 #pragma unroll
-    for (int i = 0; i < V8; ++i) { sc[i] = scale ? scale[c0 + i] : 1.f; sh[i] = shift ? shift[c0 + i] : 0.f; }
+        for (int i = 0; i < V8; ++i) { sc[i] = scale ? scale[c0 + i] : 1.f; sh[i] = shift ? shift[c0 + i] : 0.f; }
+    }
     const float ry = (float)(H - 1) / (float)(OH - 1);
     const float rx = (float)(W - 1) / (float)(OW - 1);
     const int rows = N * H;
@@ -878,8 +932,11 @@ extern "C" int kp_bn_grad_finalize(kp_stream stream, const double* sums, int C, 
     return KP_OK;
 }
 
-extern "C" int kp_bn_act_fwd(kp_stream stream, const kp_view* y, const kp_view* out, const float* scale,
-                             const float* shift, int act, int post, int pad, int N, int H, int W, int C) {
+// fuse == nullptr: plain normalise/activate.  Otherwise the fast kernels do the BatchNorm finalize themselves and
+// *fused_done is set; if the fast path does not apply nothing is launched and *fused_done stays 0.
+static int bn_act_fwd_impl(kp_stream stream, const kp_view* y, const kp_view* out, const float* scale,
+                           const float* shift, int act, int post, int pad, int N, int H, int W, int C,
+                           const BnFuse* fuse, int* fused_done) {
     KP_CHECK_ARG(y && out && y->ptr && out->ptr && N > 0 && H > 0 && W > 0 && C > 0, "kp_bn_act_fwd: bad arguments");
     KP_CHECK_ARG(post != KP_POST_POOL || (H >= 2 && W >= 2), "kp_bn_act_fwd: pool needs H,W >= 2");
     int OH, OW;
@@ -890,15 +947,21 @@ extern "C" int kp_bn_act_fwd(kp_stream stream, const kp_view* y, const kp_view* 
         return dispatch1(out->dtype, [&](auto to) -> int {
             using TI = decltype(ti);
             using TO = decltype(to);
+            BnFuse nofuse;
+            nofuse.stats = nullptr;
+            const BnFuse fz = fuse ? *fuse : nofuse;
             if (vec && fast_ok(C, P * C)) {
                 const int g = rows_grid((long long)N * (OH + 2 * pad)), sh = ilog2(C / 8);
                 cudaStream_t st = (cudaStream_t)stream;
-#define KP_FWD(POSTV) bn_act_fwd_rows_k<TI, TO, POSTV><<<g, 256, 0, st>>>(make_view<TI>(y), make_view<TO>(out), scale, shift, act, pad, N, H, W, C, OH, OW, sh)
+#define KP_FWD(POSTV) bn_act_fwd_rows_k<TI, TO, POSTV><<<g, 256, 0, st>>>(make_view<TI>(y), make_view<TO>(out), scale, shift, act, pad, N, H, W, C, OH, OW, sh, fz)
                 if (post == KP_POST_NONE) KP_FWD(KP_POST_NONE);
                 else if (post == KP_POST_POOL) KP_FWD(KP_POST_POOL);
                 else if (H < 2 || W < 2) KP_FWD(KP_POST_UP);
-                else bn_act_fwd_up_quad_k<TI, TO><<<rows_grid((long long)N * H), 256, 0, st>>>(make_view<TI>(y), make_view<TO>(out), scale, shift, act_slope(act), pad, N, H, W, C, sh);
+                else bn_act_fwd_up_quad_k<TI, TO><<<rows_grid((long long)N * H), 256, 0, st>>>(make_view<TI>(y), make_view<TO>(out), scale, shift, act_slope(act), pad, N, H, W, C, sh, fz);
 #undef KP_FWD
+                if (fuse && fused_done) *fused_done = 1;
+            } else if (fuse) {
+                return (int)KP_OK;                              // caller falls back to finalize + plain forward
             } else if (vec) {
                 Launch2D l = plan2d(P, C, 8);
                 bn_act_fwd_k<TI, TO, 8><<<l.grid, l.block, 0, (cudaStream_t)stream>>>(
@@ -912,6 +975,30 @@ extern "C" int kp_bn_act_fwd(kp_stream stream, const kp_view* y, const kp_view* 
             return (int)KP_OK;
         });
     });
+}
+
+extern "C" int kp_bn_act_fwd(kp_stream stream, const kp_view* y, const kp_view* out, const float* scale,
+                             const float* shift, int act, int post, int pad, int N, int H, int W, int C) {
+    return bn_act_fwd_impl(stream, y, out, scale, shift, act, post, pad, N, H, W, C, nullptr, nullptr);
+}
+
+extern "C" int kp_bn_finalize_act_fwd(kp_stream stream, const double* stats, double count, const float* gamma,
+                                      const float* beta, float eps, float momentum, float* running_mean,
+                                      float* running_var, int64_t* nbt, float* scale, float* shift, float* save_mean,
+                                      float* save_invstd, const kp_view* y, const kp_view* out, int act, int post,
+                                      int pad, int N, int H, int W, int C) {
+    KP_CHECK_ARG(stats && scale && shift && count > 0, "kp_bn_finalize_act_fwd: bad arguments");
+    BnFuse f;
+    f.stats = stats; f.count = count; f.gamma = gamma; f.beta = beta; f.eps = eps; f.momentum = momentum;
+    f.rmean = running_mean; f.rvar = running_var; f.nbt = (long long*)nbt; f.scale = scale; f.shift = shift;
+    f.mean = save_mean; f.invstd = save_invstd;
+    int done = 0;
+    int rc = bn_act_fwd_impl(stream, y, out, scale, shift, act, post, pad, N, H, W, C, &f, &done);
+    if (rc || done) return rc;
+    rc = kp_bn_finalize(stream, stats, C, count, gamma, beta, eps, momentum, running_mean, running_var, nbt, scale, shift,
+                        save_mean, save_invstd);
+    if (rc) return rc;
+    return bn_act_fwd_impl(stream, y, out, scale, shift, act, post, pad, N, H, W, C, nullptr, nullptr);
 }
 
 extern "C" int kp_bn_act_bwd_reduce(kp_stream stream, const kp_view* dout, const kp_view* y, const kp_view* dy,
@@ -961,7 +1048,7 @@ extern "C" int kp_bn_act_bwd_reduce(kp_stream stream, const kp_view* dout, const
 
 extern "C" int kp_bn_act_bwd_apply(kp_stream stream, const kp_view* y, const kp_view* dy, const float* scale,
                                    const float* mean, const float* invstd, const double* sums, double count, int N,
-                                   int H, int W, int C) {
+                                   int H, int W, int C, float* dgamma, float* dbeta) {
     KP_CHECK_ARG(y && dy && y->ptr && dy->ptr && sums && scale && mean && invstd && count > 0 && N > 0 && H > 0 &&
                      W > 0 && C > 0,
                  "kp_bn_act_bwd_apply: bad arguments");
@@ -974,8 +1061,10 @@ extern "C" int kp_bn_act_bwd_apply(kp_stream stream, const kp_view* y, const kp_
             using TD = decltype(td);
             if (vec && fast_ok(C, P * C)) {
                 bn_bwd_apply_rows_k<TY, TD><<<rows_grid((long long)N * H), 256, 0, st>>>(
-                    make_view<TY>(y), make_view<TD>(dy), scale, mean, invstd, sums, count, N, H, W, C, ilog2(C / 8));
+                    make_view<TY>(y), make_view<TD>(dy), scale, mean, invstd, sums, count, N, H, W, C, ilog2(C / 8), dgamma,
+                    dbeta);
             } else {
+                if (dgamma || dbeta) bn_grad_finalize_k<<<(C + 127) / 128, 128, 0, st>>>(sums, C, dgamma, dbeta);
                 long long total = P * C;
                 long long g = (total + 255) / 256;
                 if (g > (long long)kp_sm_count() * 16) g = (long long)kp_sm_count() * 16;

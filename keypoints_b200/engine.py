@@ -119,21 +119,27 @@ def uses_tc(spec: ConvSpec, cinp: int, precision: str) -> bool:
             and (spec.cout % 128 == 0 or cinp % 128 == 0))
 
 
-def pack_layer(spec: ConvSpec, p: LayerParams, cinp: int, precision: str, alloc, tag) -> dict:
-    """OIHW fp32 master weights -> the layouts the kernels read (kp_pack_weights)."""
+def pack_layer(spec: ConvSpec, p: LayerParams, cinp: int, precision: str, alloc, tag, launch: bool = True) -> dict:
+    """OIHW fp32 master weights -> the layouts the kernels read (kp_pack_weights).  With launch=False only the
+    buffers are created and ``out['desc']`` holds the record for kp_pack_weights_multi."""
     dev = p.w.device
     T = spec.k * spec.k
     out = {}
     if uses_tc(spec, cinp, precision):
         out['tc_f'] = alloc(f'{tag}.tc_f', (T, spec.cout, cinp), torch.bfloat16, dev)
         out['tc_d'] = alloc(f'{tag}.tc_d', (T, cinp, spec.cout), torch.bfloat16, dev)
-        L.call('kp_pack_weights', L.stream(), L.ptr(p.w), spec.cout, spec.cin, spec.k, cinp, None, None,
-               L.ptr(out['tc_f']), L.ptr(out['tc_d']))
+        out['desc'] = [p.w.data_ptr(), 0, 0, out['tc_f'].data_ptr(), out['tc_d'].data_ptr(), spec.cout, spec.cin, spec.k, cinp]
+        if launch:
+            L.call('kp_pack_weights', L.stream(), L.ptr(p.w), spec.cout, spec.cin, spec.k, cinp, None, None,
+                   L.ptr(out['tc_f']), L.ptr(out['tc_d']))
     else:
         out['simt_f'] = alloc(f'{tag}.simt_f', (T, spec.cin, spec.cout), torch.float32, dev)
         out['simt_d'] = alloc(f'{tag}.simt_d', (T, spec.cout, spec.cin), torch.float32, dev)
-        L.call('kp_pack_weights', L.stream(), L.ptr(p.w), spec.cout, spec.cin, spec.k, spec.cin,
-               L.ptr(out['simt_f']), L.ptr(out['simt_d']), None, None)
+        out['desc'] = [p.w.data_ptr(), out['simt_f'].data_ptr(), out['simt_d'].data_ptr(), 0, 0, spec.cout, spec.cin, spec.k,
+                       spec.cin]
+        if launch:
+            L.call('kp_pack_weights', L.stream(), L.ptr(p.w), spec.cout, spec.cin, spec.k, spec.cin,
+                   L.ptr(out['simt_f']), L.ptr(out['simt_d']), None, None)
     return out
 
 
@@ -192,19 +198,6 @@ def unit_forward(specs: List[ConvSpec], params: List[LayerParams], x_pad: torch.
             L.call('kp_conv_simt', st, L.view(src), L.ptr(pk['simt_f']), L.ptr(p.b), L.view(y[:, :h, :w, :]),
                    L.ptr(stats), N, h, w, PH if s.k == 3 else h, PW if s.k == 3 else w, s.cin, s.cout, s.k, 0)
         c = LayerCtx(x=cur, y=y, h=h, w=w, tc=tc, pack=pk)
-        if s.bn:
-            c.scale = alloc(f'{tag}.scale{i}', (s.cout,), torch.float32, dev)
-            c.shift = alloc(f'{tag}.shift{i}', (s.cout,), torch.float32, dev)
-            if training:
-                c.mean = alloc(f'{tag}.mean{i}', (s.cout,), torch.float32, dev)
-                c.invstd = alloc(f'{tag}.invstd{i}', (s.cout,), torch.float32, dev)
-                L.call('kp_bn_finalize', st, L.ptr(stats), s.cout, float(N * h * w), L.ptr(p.gamma), L.ptr(p.beta),
-                       BN_EPS, BN_MOMENTUM, L.ptr(p.rmean), L.ptr(p.rvar), L.ptr(p.nbt), L.ptr(c.scale),
-                       L.ptr(c.shift), L.ptr(c.mean), L.ptr(c.invstd))
-            else:   # eval: running statistics (host-side plumbing on [C] vectors)
-                inv = torch.rsqrt(p.rvar + BN_EPS)
-                c.scale.copy_(p.gamma * inv)
-                c.shift.copy_(p.beta - p.rmean * p.gamma * inv)
         oh, ow = post_dims(s.post, h, w)
         if last:
             dst, pad = out, out_pad
@@ -212,8 +205,24 @@ def unit_forward(specs: List[ConvSpec], params: List[LayerParams], x_pad: torch.
             cp = pitch(s.cout, precision)
             nxt = alloc(f'{tag}.x{i + 1}', (N, oh + 2, ow + 2, cp), T, dev, zero=cp != s.cout)
             dst, pad = nxt[..., :s.cout], 1
-        L.call('kp_bn_act_fwd', st, L.view(y[:, :h, :w, :]), L.view(dst), L.ptr(c.scale), L.ptr(c.shift), L.ACTS[s.act],
-               L.POSTS[s.post], pad, N, h, w, s.cout, tag=f'{tag}{i} {s.cin}->{s.cout}@{h}x{w} {s.post}')
+        ltag = f'{tag}{i} {s.cin}->{s.cout}@{h}x{w} {s.post}'
+        if s.bn:
+            c.scale = alloc(f'{tag}.scale{i}', (s.cout,), torch.float32, dev)
+            c.shift = alloc(f'{tag}.shift{i}', (s.cout,), torch.float32, dev)
+            if training:
+                c.mean = alloc(f'{tag}.mean{i}', (s.cout,), torch.float32, dev)
+                c.invstd = alloc(f'{tag}.invstd{i}', (s.cout,), torch.float32, dev)
+                L.call('kp_bn_finalize_act_fwd', st, L.ptr(stats), float(N * h * w), L.ptr(p.gamma), L.ptr(p.beta),
+                       BN_EPS, BN_MOMENTUM, L.ptr(p.rmean), L.ptr(p.rvar), L.ptr(p.nbt), L.ptr(c.scale), L.ptr(c.shift),
+                       L.ptr(c.mean), L.ptr(c.invstd), L.view(y[:, :h, :w, :]), L.view(dst), L.ACTS[s.act], L.POSTS[s.post],
+                       pad, N, h, w, s.cout, tag=ltag)
+            else:   # eval: running statistics (host-side plumbing on [C] vectors)
+                inv = torch.rsqrt(p.rvar + BN_EPS)
+                c.scale.copy_(p.gamma * inv)
+                c.shift.copy_(p.beta - p.rmean * p.gamma * inv)
+        if not (s.bn and training):
+            L.call('kp_bn_act_fwd', st, L.view(y[:, :h, :w, :]), L.view(dst), L.ptr(c.scale), L.ptr(c.shift), L.ACTS[s.act],
+                   L.POSTS[s.post], pad, N, h, w, s.cout, tag=ltag)
         ctxs.append(c)
         if not last:
             cur, h, w = nxt, oh, ow
@@ -254,8 +263,8 @@ def unit_backward(specs: List[ConvSpec], params: List[LayerParams], grads: List[
                    L.ptr(c.mean), L.ptr(c.invstd), L.ptr(sums), a, po, dout_pad, N, h, w, s.cout,
                    tag=f'{tag}{i} {s.cin}->{s.cout}@{h}x{w} {s.post}')
             L.call('kp_bn_act_bwd_apply', st, L.view(yv), L.view(dy_int), L.ptr(c.scale), L.ptr(c.mean), L.ptr(c.invstd),
-                   L.ptr(sums), float(N * h * w), N, h, w, s.cout, tag=f'{tag}{i} {s.cin}->{s.cout}@{h}x{w} {s.post}')
-            L.call('kp_bn_grad_finalize', st, L.ptr(sums), s.cout, L.ptr(g.dgamma), L.ptr(g.dbeta))
+                   L.ptr(sums), float(N * h * w), N, h, w, s.cout, L.ptr(g.dgamma), L.ptr(g.dbeta),
+                   tag=f'{tag}{i} {s.cin}->{s.cout}@{h}x{w} {s.post}')
             # the bias of a conv feeding train-mode BatchNorm has an exactly zero gradient
         else:
             L.call('kp_bn_act_bwd_reduce', st, L.view(dout), L.view(yv), L.view(dy_int), None, None, None, None,

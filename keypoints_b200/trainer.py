@@ -111,9 +111,17 @@ class Trainer:
 
     # ------------------------------------------------------------------------------------------
     def _pack(self, shapes):
-        for u in self.units.values():
-            u.packs = [engine.pack_layer(s, p, cp, self.precision, u.alloc, f'pk{i}')
-                       for i, (s, p, cp) in enumerate(zip(u.specs, u.params, shapes[u.name]))]
+        """Repack every layer's master weights for the kernels: one multi-tensor launch over a device-resident table."""
+        key = tuple((n, tuple(v)) for n, v in sorted(shapes.items()))
+        if getattr(self, '_pack_key', None) != key:
+            rows = []
+            for u in self.units.values():
+                u.packs = [engine.pack_layer(s, p, cp, self.precision, u.alloc, f'pk{i}', launch=False)
+                           for i, (s, p, cp) in enumerate(zip(u.specs, u.params, shapes[u.name]))]
+                rows += [pk['desc'] for pk in u.packs]
+            self._pack_table = torch.tensor(rows, dtype=torch.int64).to(self.device)
+            self._pack_key = key
+        L.call('kp_pack_weights_multi', L.stream(), L.ptr(self._pack_table), self._pack_table.shape[0])
 
     def _pitches(self, u: _UnitState, cin_pitch):
         out, cp = [], cin_pitch

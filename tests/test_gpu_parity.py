@@ -376,7 +376,7 @@ def test_reference_script_loop_through_dropin(dev):
         assert x_t.shape == (4, 3, 64, 64) and phi.shape == (4, 64, 8, 8) and k.shape == (4, 10, 2)
         assert m.shape == (4, 10, 8, 8) and p[0].shape == (4, 10, 8) and heat.shape == (4, 10, 8, 8)
         assert mask_s.shape == (4, 1, 8, 8) and mask_t.shape == (4, 1, 8, 8)
-        assert all(np.isfinite(losses)) and float(k.min()) >= 0.0 and float(k.max()) <= 1.0
+        assert all(np.isfinite(losses)) and float(k.min()) >= -1e-5 and float(k.max()) <= 1.0 + 1e-5
         assert losses[-1] < losses[0], losses
         assert all(p_.grad is not None for n_, p_ in net.named_parameters() if n_.startswith(('decoder', 'keypoint', 'feature')))
     finally:
