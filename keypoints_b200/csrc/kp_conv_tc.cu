@@ -58,6 +58,16 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* tm,
 __device__ __forceinline__ void tma_prefetch_l2_2d(const CUtensorMap* tm, int c0, int c1) {
     asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"((uint64_t)tm), "r"(c0), "r"(c1) : "memory");
 }
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* tm, uint32_t src, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];"
+                 ::"l"((uint64_t)tm), "r"(c0), "r"(c1), "r"(src) : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+template <int N> __device__ __forceinline__ void bulk_wait_read() {
+    asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* tm) {
     asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)tm) : "memory");
 }
@@ -123,6 +133,7 @@ __host__ __device__ constexpr uint32_t make_idesc(int n, int a_mn_major, int b_m
 }
 
 constexpr int STAGE_A_BYTES = 128 * 128;   // 128 rows x 64 bf16
+constexpr int SLAB_BYTES = 128 * 128;       // epilogue staging slab: 128 rows x 64 bf16, SWIZZLE_128B, x2 buffers
 constexpr int PF_TILES = 3;                // L2 prefetch distance of the persistent producers, in rounds of tiles
 
 struct ConvTcParams {
@@ -135,143 +146,6 @@ struct ConvTcParams {
     int PH, PW, VH, VW;
 };
 
-// ------------------------------------------------------------------------------------------------
-// fprop / dgrad: D[128 pixels][BN channels] = sum over (tap, 64-channel chunk) A[pix][ci] * B[co][ci]
-// ------------------------------------------------------------------------------------------------
-template <int BN, int STAGES>
-__global__ void __launch_bounds__(192, 1)
-conv_tc_k(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const ConvTcParams p) {
-    constexpr int STAGE_B_BYTES = BN * 128;
-    constexpr int STAGE_BYTES = STAGE_A_BYTES + STAGE_B_BYTES;
-    extern __shared__ uint8_t smem_raw[];
-    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-    uint8_t* gen_base = smem_raw + (base - smem_u32(smem_raw));
-    const uint32_t bars = base + STAGES * STAGE_BYTES;          // full[S], empty[S], tmem_full
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gen_base + STAGES * STAGE_BYTES + 8 * (2 * STAGES + 1));
-
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const long long q0 = (long long)blockIdx.x * 128;
-    const int n0 = blockIdx.y * BN;
-    const int kchunks = p.Cin / 64;
-    const int num_kb = p.taps * kchunks;
-
-    if (warp == 0 && lane == 0) {
-        tma_prefetch_desc(&tmA);
-        tma_prefetch_desc(&tmB);
-        for (int s = 0; s < STAGES; ++s) {
-            mbar_init(bars + 8 * s, 1);
-            mbar_init(bars + 8 * (STAGES + s), 1);
-        }
-        mbar_init(bars + 8 * (2 * STAGES), 1);
-        fence_barrier_init();
-    }
-    if (warp == 1) tmem_alloc(smem_u32(tmem_slot), BN);
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
-
-    if (warp == 0) {
-        if (elect_one()) {
-            for (int kb = 0; kb < num_kb; ++kb) {
-                const int s = kb % STAGES, ph = (kb / STAGES) & 1;
-                mbar_wait(bars + 8 * (STAGES + s), ph ^ 1);
-                const uint32_t full = bars + 8 * s;
-                mbar_expect_tx(full, STAGE_BYTES);
-                const int tap = kb / kchunks, kc = kb - tap * kchunks;
-                const uint32_t sa = base + s * STAGE_BYTES;
-                tma_load_2d(sa, &tmA, kc * 64, (int)(q0 + p.shift[tap]), full);
-                tma_load_2d(sa + STAGE_A_BYTES, &tmB, kc * 64, tap * p.Cout + n0, full);
-            }
-        }
-    } else if (warp == 1) {
-        if (elect_one()) {
-            constexpr uint32_t idesc = make_idesc(BN, 0, 0);
-            for (int kb = 0; kb < num_kb; ++kb) {
-                const int s = kb % STAGES, ph = (kb / STAGES) & 1;
-                mbar_wait(bars + 8 * s, ph);
-                tc_fence_after();
-                const uint32_t sa = base + s * STAGE_BYTES;
-                const uint64_t ad = make_desc(sa, 16, 1024), bd = make_desc(sa + STAGE_A_BYTES, 16, 1024);
-#pragma unroll
-                for (int k = 0; k < 4; ++k)       // UMMA_K = 16 bf16 = 32 bytes inside the 128-byte swizzled row
-                    umma_bf16(tmem_base, ad + 2 * k, bd + 2 * k, idesc, (kb | k) ? 1u : 0u);
-                umma_commit(bars + 8 * (STAGES + s));
-            }
-            umma_commit(bars + 8 * (2 * STAGES));
-        }
-    } else {
-        // epilogue: TMEM lane group of this warp = warp % 4
-        const int wq = warp & 3;
-        const int row = wq * 32 + lane;
-        const long long q = q0 + row;
-        bool valid = q < p.Q;
-        if (valid && p.stats) {
-            int x = (int)(q % p.PW);
-            int y = (int)((q / p.PW) % p.PH);
-            valid = x < p.VW && y < p.VH;
-        }
-        float* tile = reinterpret_cast<float*>(gen_base) + wq * (32 * 33);              // reuse pipeline smem
-        float* part = reinterpret_cast<float*>(gen_base) + 4 * 32 * 33 + wq * (2 * BN);  // per-warp column sums
-        mbar_wait(bars + 8 * (2 * STAGES), 0);
-        tc_fence_after();
-#pragma unroll 1
-        for (int c = 0; c < BN / 32; ++c) {
-            uint32_t r[32];
-            tmem_ld32(tmem_base + ((uint32_t)(wq * 32) << 16) + c * 32, r);
-            float v[32];
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) + (p.bias ? p.bias[n0 + c * 32 + j] : 0.f);
-            if (q < p.Q) {
-                uint4* dst = reinterpret_cast<uint4*>(p.out + q * p.Cout + n0 + c * 32);
-#pragma unroll
-                for (int g = 0; g < 4; ++g) {
-                    uint4 u;
-                    __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) h[e] = __floats2bfloat162_rn(v[g * 8 + 2 * e], v[g * 8 + 2 * e + 1]);
-                    dst[g] = u;
-                }
-            }
-            if (p.stats) {
-#pragma unroll
-                for (int j = 0; j < 32; ++j) tile[lane * 33 + j] = valid ? v[j] : 0.f;
-                __syncwarp();
-                float s1 = 0.f, s2 = 0.f;
-#pragma unroll
-                for (int rr = 0; rr < 32; ++rr) {
-                    float t = tile[rr * 33 + lane];
-                    s1 += t;
-                    s2 = fmaf(t, t, s2);
-                }
-                part[c * 32 + lane] = s1;
-                part[BN + c * 32 + lane] = s2;
-                __syncwarp();
-            }
-        }
-        if (p.stats) {
-            asm volatile("bar.sync 1, 128;" ::: "memory");
-            const float* pp = reinterpret_cast<float*>(gen_base) + 4 * 32 * 33;
-            for (int ch = (warp - 2) * 32 + lane; ch < BN; ch += 128) {
-                float s1 = 0.f, s2 = 0.f;
-#pragma unroll
-                for (int w = 0; w < 4; ++w) { s1 += pp[w * 2 * BN + ch]; s2 += pp[w * 2 * BN + BN + ch]; }
-                atomicAdd(&p.stats[n0 + ch], (double)s1);
-                atomicAdd(&p.stats[p.Cout + n0 + ch], (double)s2);
-            }
-        }
-    }
-    tc_fence_before();
-    __syncthreads();
-    if (warp == 1) {
-        __syncwarp();
-        tmem_dealloc(tmem_base, BN);
-    }
-}
-
-// ------------------------------------------------------------------------------------------------
-// wgrad: D[128 (M channels)][BN (N channels)] = sum over pixels A[pix][m] * B[pix + shift][n], MN-major
-// ------------------------------------------------------------------------------------------------
 struct WgradTcParams {
     long long Q;            // flat pixels
     long long kchunk;       // pixels per split (multiple of 64)
@@ -280,105 +154,6 @@ struct WgradTcParams {
     int Mtot, Ntot;         // staging is [taps][Mtot][Ntot] fp32
     float* stg;
 };
-
-template <int BN, int STAGES>
-__global__ void __launch_bounds__(192, 1)
-wgrad_tc_k(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const WgradTcParams p) {
-    constexpr int BOX_BYTES = 64 * 128;            // 64 pixels x 64 channels bf16
-    constexpr int A_BYTES = 2 * BOX_BYTES;         // M = 128 channels
-    constexpr int B_BYTES = (BN / 64) * BOX_BYTES;
-    constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-    extern __shared__ uint8_t smem_raw[];
-    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-    uint8_t* gen_base = smem_raw + (base - smem_u32(smem_raw));
-    const uint32_t bars = base + STAGES * STAGE_BYTES;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gen_base + STAGES * STAGE_BYTES + 8 * (2 * STAGES + 1));
-
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int m0 = blockIdx.x * 128, n0 = blockIdx.y * BN;
-    const int tap = blockIdx.z / p.splits, split = blockIdx.z % p.splits;
-    const long long qbeg = (long long)split * p.kchunk;
-    long long qend = qbeg + p.kchunk;
-    if (qend > p.Q) qend = p.Q;
-    const int num_kb = qend > qbeg ? (int)((qend - qbeg + 63) / 64) : 0;
-
-    if (warp == 0 && lane == 0) {
-        tma_prefetch_desc(&tmA);
-        tma_prefetch_desc(&tmB);
-        for (int s = 0; s < STAGES; ++s) {
-            mbar_init(bars + 8 * s, 1);
-            mbar_init(bars + 8 * (STAGES + s), 1);
-        }
-        mbar_init(bars + 8 * (2 * STAGES), 1);
-        fence_barrier_init();
-    }
-    if (warp == 1) tmem_alloc(smem_u32(tmem_slot), BN);
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
-
-    if (num_kb > 0) {
-        if (warp == 0) {
-            if (elect_one()) {
-                for (int kb = 0; kb < num_kb; ++kb) {
-                    const int s = kb % STAGES, ph = (kb / STAGES) & 1;
-                    mbar_wait(bars + 8 * (STAGES + s), ph ^ 1);
-                    const uint32_t full = bars + 8 * s;
-                    mbar_expect_tx(full, STAGE_BYTES);
-                    const long long q = qbeg + (long long)kb * 64;
-                    const uint32_t sa = base + s * STAGE_BYTES;
-                    // NOTE: the last block of a split may run past qend into the next split's pixels; that
-                    // would double count, so splits are sized in whole 64-pixel blocks (kchunk % 64 == 0)
-                    // and only the global tail (>= Q, zero-filled by TMA) is ever partial.
-#pragma unroll
-                    for (int b = 0; b < 2; ++b)
-                        tma_load_2d(sa + b * BOX_BYTES, &tmA, m0 + b * 64, (int)(q + p.shiftA[tap]), full);
-#pragma unroll
-                    for (int b = 0; b < BN / 64; ++b)
-                        tma_load_2d(sa + A_BYTES + b * BOX_BYTES, &tmB, n0 + b * 64, (int)(q + p.shiftB[tap]), full);
-                }
-            }
-        } else if (warp == 1) {
-            if (elect_one()) {
-                constexpr uint32_t idesc = make_idesc(BN, 1, 1);
-                for (int kb = 0; kb < num_kb; ++kb) {
-                    const int s = kb % STAGES, ph = (kb / STAGES) & 1;
-                    mbar_wait(bars + 8 * s, ph);
-                    tc_fence_after();
-                    const uint32_t sa = base + s * STAGE_BYTES;
-                    const uint64_t ad = make_desc(sa, BOX_BYTES, 1024), bd = make_desc(sa + A_BYTES, BOX_BYTES, 1024);
-#pragma unroll
-                    for (int k = 0; k < 4; ++k)   // UMMA_K = 16 pixels = two 8-row groups = 2048 bytes
-                        umma_bf16(tmem_base, ad + 128 * k, bd + 128 * k, idesc, (kb | k) ? 1u : 0u);
-                    umma_commit(bars + 8 * (STAGES + s));
-                }
-                umma_commit(bars + 8 * (2 * STAGES));
-            }
-        } else {
-            const int wq = warp & 3;
-            const int row = wq * 32 + lane;
-            mbar_wait(bars + 8 * (2 * STAGES), 0);
-            tc_fence_after();
-            float* dst_row = p.stg + ((long long)tap * p.Mtot + m0 + row) * p.Ntot + n0;
-#pragma unroll 1
-            for (int c = 0; c < BN / 32; ++c) {
-                uint32_t r[32];
-                tmem_ld32(tmem_base + ((uint32_t)(wq * 32) << 16) + c * 32, r);
-#pragma unroll
-                for (int g = 0; g < 8; ++g)
-                    red_add_v4(dst_row + c * 32 + g * 4, __uint_as_float(r[4 * g]), __uint_as_float(r[4 * g + 1]),
-                               __uint_as_float(r[4 * g + 2]), __uint_as_float(r[4 * g + 3]));
-            }
-        }
-    }
-    tc_fence_before();
-    __syncthreads();
-    if (warp == 1) {
-        __syncwarp();
-        tmem_dealloc(tmem_base, BN);
-    }
-}
 
 // ================================================================================================
 // Persistent variants: one CTA per SM walks a static round-robin list of output tiles.  The accumulator is double
@@ -392,16 +167,18 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 
 template <int BN, int STAGES>
 __global__ void __launch_bounds__(320, 1)
-conv_tc_persist_k(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const ConvTcParams p) {
+conv_tc_persist_k(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmO, const ConvTcParams p) {
     constexpr int STAGE_B_BYTES = BN * 128;
     constexpr int STAGE_BYTES = STAGE_A_BYTES + STAGE_B_BYTES;
     constexpr int EPI_FLOATS = 8 * 32 * 17 + 4 * 2 * BN;   // per-warp 32x16 transpose tiles, per-lane-group running column sums
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* gen_base = smem_raw + (base - smem_u32(smem_raw));
-    float* epi = reinterpret_cast<float*>(gen_base + STAGES * STAGE_BYTES);
-    const uint32_t bars = base + STAGES * STAGE_BYTES + EPI_FLOATS * 4;   // full[S], empty[S], tfull[2], tempty[2]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gen_base + STAGES * STAGE_BYTES + EPI_FLOATS * 4 + 8 * (2 * STAGES + 4));
+    const uint32_t slab = base + STAGES * STAGE_BYTES;                 // 2 x SLAB_BYTES, 1024-byte aligned
+    uint8_t* slab_gen = gen_base + STAGES * STAGE_BYTES;
+    float* epi = reinterpret_cast<float*>(gen_base + STAGES * STAGE_BYTES + 2 * SLAB_BYTES);
+    const uint32_t bars = base + STAGES * STAGE_BYTES + 2 * SLAB_BYTES + EPI_FLOATS * 4;   // full[S], empty[S], tfull[2], tempty[2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gen_base + STAGES * STAGE_BYTES + 2 * SLAB_BYTES + EPI_FLOATS * 4 + 8 * (2 * STAGES + 4));
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int kchunks = p.Cin / 64;
@@ -412,6 +189,7 @@ conv_tc_persist_k(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmA);
         tma_prefetch_desc(&tmB);
+        tma_prefetch_desc(&tmO);
         for (int s = 0; s < STAGES; ++s) {
             mbar_init(bars + 8 * s, 1);
             mbar_init(bars + 8 * (STAGES + s), 1);
@@ -490,7 +268,7 @@ conv_tc_persist_k(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         float* tile = epi + (warp - 2) * (32 * 17);
         float* wsum_all = epi + 8 * 32 * 17;                   // [4 lane groups][2*BN] running column sums of this CTA
         float* wsum = wsum_all + wq * (2 * BN);
-        int lt = 0, cur_n = -1;
+        int lt = 0, cur_n = -1, slabs = 0;
         auto flush = [&](int n_tile) {                         // all 128 epilogue threads
             asm volatile("bar.sync 1, 256;" ::: "memory");
             for (int ch = et; ch < BN; ch += 256) {
@@ -513,7 +291,8 @@ conv_tc_persist_k(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             const int buf = lt & 1;
             if (p.stats && cur_n >= 0 && cur_n != n_t) flush(cur_n);
             cur_n = n_t;
-            const long long q = (long long)m_t * 128 + row;
+            const long long q_tile = (long long)m_t * 128;
+            const long long q = q_tile + row;
             bool valid = q < p.Q;
             if (valid && p.stats) {
                 int x = (int)(q % p.PW);
@@ -539,16 +318,24 @@ conv_tc_persist_k(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 #pragma unroll
                     for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) + (p.bias ? p.bias[n0 + c * 32 + j] : 0.f);
                 }
-                if (q < p.Q) {
-                    uint4* dst = reinterpret_cast<uint4*>(p.out + q * p.Cout + n0 + c * 32);
+                {   // stage this warp's 32 rows x 32 columns into the 128-row x 64-column slab (128-byte swizzle: the
+                    // 16-byte chunk j of row r lives at chunk j ^ (r & 7)), then ONE TMA store writes the slab
+                    const int sb = slabs & 1;
+                    if (et == 0) bulk_wait_read<1>();          // the store that last read this buffer is done with it
+                    asm volatile("bar.sync 1, 256;" ::: "memory");
+                    uint8_t* drow = slab_gen + sb * SLAB_BYTES + row * 128;
 #pragma unroll
                     for (int g = 0; g < 4; ++g) {
                         uint4 u;
                         __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
 #pragma unroll
                         for (int e = 0; e < 4; ++e) h[e] = __floats2bfloat162_rn(v[g * 8 + 2 * e], v[g * 8 + 2 * e + 1]);
-                        dst[g] = u;
+                        *reinterpret_cast<uint4*>(drow + (((half * 4 + g) ^ (row & 7)) << 4)) = u;
                     }
+                    fence_async_smem();
+                    asm volatile("bar.sync 1, 256;" ::: "memory");
+                    if (et == 0) tma_store_2d(&tmO, slab + sb * SLAB_BYTES, n0 + (c >> 1) * 64, (int)q_tile);
+                    ++slabs;
                 }
                 if (p.stats) {
                     // column sums over the warp's 32 rows, 16 columns at a time through a 32x17 shared tile: lane l sums
@@ -582,6 +369,7 @@ conv_tc_persist_k(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             if (et == 0) mbar_arrive(bars + 8 * (2 * STAGES + 2 + buf));
         }
         if (p.stats && cur_n >= 0) flush(cur_n);
+        if (et == 0) bulk_wait_all();                          // every TMA store has completed before the CTA exits
     }
     tc_fence_before();
     __syncthreads();
@@ -635,16 +423,18 @@ __host__ __device__ constexpr uint32_t make_idesc_m256(int n) {
 
 template <int BN, int STAGES>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(320, 1)
-conv_tc_pair_k(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const ConvTcParams p) {
+conv_tc_pair_k(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmO, const ConvTcParams p) {
     constexpr int STAGE_B_BYTES = (BN / 2) * 128;              // this CTA's half of the weight tile
     constexpr int STAGE_BYTES = STAGE_A_BYTES + STAGE_B_BYTES;
     constexpr int EPI_FLOATS = 8 * 32 * 17 + 4 * 2 * BN;   // per-warp 32x16 transpose tiles, per-lane-group running column sums
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* gen_base = smem_raw + (base - smem_u32(smem_raw));
-    float* epi = reinterpret_cast<float*>(gen_base + STAGES * STAGE_BYTES);
-    const uint32_t bars = base + STAGES * STAGE_BYTES + EPI_FLOATS * 4;   // full[S], empty[S], tfull[2], tempty[2]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gen_base + STAGES * STAGE_BYTES + EPI_FLOATS * 4 + 8 * (2 * STAGES + 4));
+    const uint32_t slab = base + STAGES * STAGE_BYTES;                 // 2 x SLAB_BYTES, 1024-byte aligned
+    uint8_t* slab_gen = gen_base + STAGES * STAGE_BYTES;
+    float* epi = reinterpret_cast<float*>(gen_base + STAGES * STAGE_BYTES + 2 * SLAB_BYTES);
+    const uint32_t bars = base + STAGES * STAGE_BYTES + 2 * SLAB_BYTES + EPI_FLOATS * 4;   // full[S], empty[S], tfull[2], tempty[2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gen_base + STAGES * STAGE_BYTES + 2 * SLAB_BYTES + EPI_FLOATS * 4 + 8 * (2 * STAGES + 4));
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = cluster_ctarank();
@@ -657,6 +447,7 @@ conv_tc_pair_k(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmA);
         tma_prefetch_desc(&tmB);
+        tma_prefetch_desc(&tmO);
         for (int s = 0; s < STAGES; ++s) {
             mbar_init(bars + 8 * s, 1);
             mbar_init(bars + 8 * (STAGES + s), 1);
@@ -739,7 +530,7 @@ conv_tc_pair_k(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         float* tile = epi + (warp - 2) * (32 * 17);
         float* wsum_all = epi + 8 * 32 * 17;                   // [4 lane groups][2*BN] running column sums of this CTA
         float* wsum = wsum_all + wq * (2 * BN);
-        int lt = 0, cur_n = -1;
+        int lt = 0, cur_n = -1, slabs = 0;
         auto flush = [&](int n_tile) {                         // all 128 epilogue threads
             asm volatile("bar.sync 1, 256;" ::: "memory");
             for (int ch = et; ch < BN; ch += 256) {
@@ -762,7 +553,8 @@ conv_tc_pair_k(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const int buf = lt & 1;
             if (p.stats && cur_n >= 0 && cur_n != n_t) flush(cur_n);
             cur_n = n_t;
-            const long long q = (long long)m_t * 256 + rank * 128 + row;
+            const long long q_tile = (long long)m_t * 256 + rank * 128;
+            const long long q = q_tile + row;
             bool valid = q < p.Q;
             if (valid && p.stats) {
                 int x = (int)(q % p.PW);
@@ -788,16 +580,24 @@ conv_tc_pair_k(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
                     for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) + (p.bias ? p.bias[n0 + c * 32 + j] : 0.f);
                 }
-                if (q < p.Q) {
-                    uint4* dst = reinterpret_cast<uint4*>(p.out + q * p.Cout + n0 + c * 32);
+                {   // stage this warp's 32 rows x 32 columns into the 128-row x 64-column slab (128-byte swizzle: the
+                    // 16-byte chunk j of row r lives at chunk j ^ (r & 7)), then ONE TMA store writes the slab
+                    const int sb = slabs & 1;
+                    if (et == 0) bulk_wait_read<1>();          // the store that last read this buffer is done with it
+                    asm volatile("bar.sync 1, 256;" ::: "memory");
+                    uint8_t* drow = slab_gen + sb * SLAB_BYTES + row * 128;
 #pragma unroll
                     for (int g = 0; g < 4; ++g) {
                         uint4 u;
                         __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
 #pragma unroll
                         for (int e = 0; e < 4; ++e) h[e] = __floats2bfloat162_rn(v[g * 8 + 2 * e], v[g * 8 + 2 * e + 1]);
-                        dst[g] = u;
+                        *reinterpret_cast<uint4*>(drow + (((half * 4 + g) ^ (row & 7)) << 4)) = u;
                     }
+                    fence_async_smem();
+                    asm volatile("bar.sync 1, 256;" ::: "memory");
+                    if (et == 0) tma_store_2d(&tmO, slab + sb * SLAB_BYTES, n0 + (c >> 1) * 64, (int)q_tile);
+                    ++slabs;
                 }
                 if (p.stats) {
                     // column sums over the warp's 32 rows, 16 columns at a time through a 32x17 shared tile: lane l sums
@@ -831,6 +631,7 @@ conv_tc_pair_k(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             if (et == 0) mbar_arrive_leader(bars + 8 * (2 * STAGES + 2 + buf));
         }
         if (p.stats && cur_n >= 0) flush(cur_n);
+        if (et == 0) bulk_wait_all();                          // every TMA store has completed before the CTA exits
     }
     tc_fence_before();
     __syncthreads();
@@ -838,214 +639,6 @@ conv_tc_pair_k(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (warp == 1) {
         __syncwarp();
         asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(2 * BN) : "memory");
-    }
-}
-
-// Variant for thin layers (taps*Cin*BN*2 bytes <= RES_BYTES): the whole weight tile set of this CTA's channel tile stays
-// RESIDENT in shared memory (loaded once), the ring streams only the activation tiles.  Halves the L2->SM traffic of
-// the 64/128-channel layers at 128x128 and removes the all-SMs-read-the-same-16KB hot spot on the weight lines.
-template <int BN, int STAGES, int RES_BYTES>
-__global__ void __launch_bounds__(320, 1)
-conv_tc_resident_k(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const ConvTcParams p) {
-    constexpr int STAGE_B_BYTES = BN * 128;
-    constexpr int STAGE_BYTES = STAGE_A_BYTES;
-    constexpr int EPI_FLOATS = 8 * 32 * 17 + 4 * 2 * BN;   // per-warp 32x16 transpose tiles, per-lane-group running column sums
-    extern __shared__ uint8_t smem_raw[];
-    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-    uint8_t* gen_base = smem_raw + (base - smem_u32(smem_raw));
-    const uint32_t resb = base + STAGES * STAGE_BYTES;              // resident weights: [num_kb][BN rows x 128 B]
-    float* epi = reinterpret_cast<float*>(gen_base + STAGES * STAGE_BYTES + RES_BYTES);
-    const uint32_t bars = base + STAGES * STAGE_BYTES + RES_BYTES + EPI_FLOATS * 4;   // full[S], empty[S], tfull[2], tempty[2], wfull
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gen_base + STAGES * STAGE_BYTES + RES_BYTES + EPI_FLOATS * 4 + 8 * (2 * STAGES + 5));
-
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int kchunks = p.Cin / 64;
-    const int num_kb = p.taps * kchunks;
-    const int num_m = (int)((p.Q + 127) / 128);
-    const int total = num_m;                                  // tiles of this CTA column: channel tile = blockIdx.y
-
-    if (warp == 0 && lane == 0) {
-        tma_prefetch_desc(&tmA);
-        tma_prefetch_desc(&tmB);
-        for (int s = 0; s < STAGES; ++s) {
-            mbar_init(bars + 8 * s, 1);
-            mbar_init(bars + 8 * (STAGES + s), 1);
-        }
-        for (int b = 0; b < 2; ++b) {
-            mbar_init(bars + 8 * (2 * STAGES + b), 1);        // tmem full  (tcgen05.commit)
-            mbar_init(bars + 8 * (2 * STAGES + 2 + b), 1);    // tmem empty (one elected epilogue thread)
-        }
-        mbar_init(bars + 8 * (2 * STAGES + 4), 1);            // resident weights landed
-        fence_barrier_init();
-    }
-    if (warp == 1) tmem_alloc(smem_u32(tmem_slot), 2 * BN);
-    if (threadIdx.x >= 64) {
-        float* wsum0 = epi + 8 * 32 * 17;
-        for (int i = threadIdx.x - 64; i < 4 * 2 * BN; i += 256) wsum0[i] = 0.f;
-    }
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
-
-    if (warp == 0) {
-        if (elect_one()) {
-            int it = 0;
-            {   // all weight tiles of channel tile blockIdx.y, once
-                const uint32_t wfull = bars + 8 * (2 * STAGES + 4);
-                mbar_expect_tx(wfull, (uint32_t)(num_kb * STAGE_B_BYTES));
-                for (int kb = 0; kb < num_kb; ++kb) {
-                    const int tap = kb / kchunks, kc = kb - tap * kchunks;
-                    tma_load_2d(resb + kb * STAGE_B_BYTES, &tmB, kc * 64, tap * p.Cout + (int)blockIdx.y * BN, wfull);
-                }
-            }
-            for (int t = blockIdx.x; t < total; t += gridDim.x) {
-                const long long q0 = (long long)t * 128;
-                {
-                    const int tp = t + PF_TILES * (int)gridDim.x;
-                    if (tp < total)
-                        for (int kc = 0; kc < kchunks; ++kc)
-                            tma_prefetch_l2_2d(&tmA, kc * 64, (int)((long long)tp * 128 + p.shift[p.taps - 1]));
-                }
-                for (int kb = 0; kb < num_kb; ++kb, ++it) {
-                    const int s = it % STAGES, ph = (it / STAGES) & 1;
-                    mbar_wait(bars + 8 * (STAGES + s), ph ^ 1);
-                    const uint32_t full = bars + 8 * s;
-                    mbar_expect_tx(full, STAGE_BYTES);
-                    const int tap = kb / kchunks, kc = kb - tap * kchunks;
-                    tma_load_2d(base + s * STAGE_BYTES, &tmA, kc * 64, (int)(q0 + p.shift[tap]), full);
-                }
-            }
-        }
-    } else if (warp == 1) {
-        if (elect_one()) {
-            constexpr uint32_t idesc = make_idesc(BN, 0, 0);
-            int it = 0, lt = 0;
-            mbar_wait(bars + 8 * (2 * STAGES + 4), 0);
-            for (int t = blockIdx.x; t < total; t += gridDim.x, ++lt) {
-                const int buf = lt & 1;
-                mbar_wait(bars + 8 * (2 * STAGES + 2 + buf), ((lt >> 1) & 1) ^ 1);
-                tc_fence_after();
-                const uint32_t dcol = tmem_base + buf * BN;
-                for (int kb = 0; kb < num_kb; ++kb, ++it) {
-                    const int s = it % STAGES, ph = (it / STAGES) & 1;
-                    mbar_wait(bars + 8 * s, ph);
-                    tc_fence_after();
-                    const uint32_t sa = base + s * STAGE_BYTES;
-                    const uint64_t ad = make_desc(sa, 16, 1024), bd = make_desc(resb + kb * STAGE_B_BYTES, 16, 1024);
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) umma_bf16(dcol, ad + 2 * k, bd + 2 * k, idesc, (kb | k) ? 1u : 0u);
-                    umma_commit(bars + 8 * (STAGES + s));
-                }
-                umma_commit(bars + 8 * (2 * STAGES + buf));
-            }
-        }
-    } else {
-        const int wq = warp & 3;
-        const int row = wq * 32 + lane;
-        const int et = threadIdx.x - 64;                       // 0..255: 8 epilogue warps, 2 per TMEM lane group
-        const int half = (warp - 2) >> 2;                      // which interleaved set of 32-column chunks
-        float* tile = epi + (warp - 2) * (32 * 17);
-        float* wsum_all = epi + 8 * 32 * 17;                   // [4 lane groups][2*BN] running column sums of this CTA
-        float* wsum = wsum_all + wq * (2 * BN);
-        int lt = 0, cur_n = -1;
-        auto flush = [&](int n_tile) {                         // all 128 epilogue threads
-            asm volatile("bar.sync 1, 256;" ::: "memory");
-            for (int ch = et; ch < BN; ch += 256) {
-                float s1 = 0.f, s2 = 0.f;
-#pragma unroll
-                for (int w = 0; w < 4; ++w) {
-                    s1 += wsum_all[w * 2 * BN + ch];
-                    s2 += wsum_all[w * 2 * BN + BN + ch];
-                    wsum_all[w * 2 * BN + ch] = 0.f;
-                    wsum_all[w * 2 * BN + BN + ch] = 0.f;
-                }
-                atomicAdd(&p.stats[n_tile * BN + ch], (double)s1);
-                atomicAdd(&p.stats[p.Cout + n_tile * BN + ch], (double)s2);
-            }
-            asm volatile("bar.sync 1, 256;" ::: "memory");
-        };
-        for (int t = blockIdx.x; t < total; t += gridDim.x, ++lt) {
-            const int n_t = blockIdx.y, m_t = t;
-            const int n0 = n_t * BN;
-            const int buf = lt & 1;
-            if (p.stats && cur_n >= 0 && cur_n != n_t) flush(cur_n);
-            cur_n = n_t;
-            const long long q = (long long)m_t * 128 + row;
-            bool valid = q < p.Q;
-            if (valid && p.stats) {
-                int x = (int)(q % p.PW);
-                int y = (int)((q / p.PW) % p.PH);
-                valid = x < p.VW && y < p.VH;
-            }
-            mbar_wait(bars + 8 * (2 * STAGES + buf), (lt >> 1) & 1);
-            tc_fence_after();
-#pragma unroll 1
-            for (int c = half; c < BN / 32; c += 2) {
-                uint32_t r[32];
-                tmem_ld32(tmem_base + ((uint32_t)(wq * 32) << 16) + buf * BN + c * 32, r);
-                float v[32];
-                if (p.bias && ((reinterpret_cast<uintptr_t>(p.bias) & 15) == 0)) {
-                    const float4* bp = reinterpret_cast<const float4*>(p.bias + n0 + c * 32);
-#pragma unroll
-                    for (int g = 0; g < 8; ++g) {
-                        const float4 bv = bp[g];
-                        v[4 * g] = __uint_as_float(r[4 * g]) + bv.x; v[4 * g + 1] = __uint_as_float(r[4 * g + 1]) + bv.y;
-                        v[4 * g + 2] = __uint_as_float(r[4 * g + 2]) + bv.z; v[4 * g + 3] = __uint_as_float(r[4 * g + 3]) + bv.w;
-                    }
-                } else {
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) + (p.bias ? p.bias[n0 + c * 32 + j] : 0.f);
-                }
-                if (q < p.Q) {
-                    uint4* dst = reinterpret_cast<uint4*>(p.out + q * p.Cout + n0 + c * 32);
-#pragma unroll
-                    for (int g = 0; g < 4; ++g) {
-                        uint4 u;
-                        __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
-#pragma unroll
-                        for (int e = 0; e < 4; ++e) h[e] = __floats2bfloat162_rn(v[g * 8 + 2 * e], v[g * 8 + 2 * e + 1]);
-                        dst[g] = u;
-                    }
-                }
-                if (p.stats) {
-                    // column sums over the warp's 32 rows, 16 columns at a time through a 32x17 shared tile: lane l sums
-                    // column (l & 15) over rows [16 (l >> 4), +16), the two row halves are combined with one shuffle
-#pragma unroll
-                    for (int hc = 0; hc < 2; ++hc) {
-#pragma unroll
-                        for (int j = 0; j < 16; ++j) tile[lane * 17 + j] = valid ? v[hc * 16 + j] : 0.f;
-                        __syncwarp();
-                        float s1 = 0.f, s2 = 0.f;
-                        const int col = lane & 15, r0 = (lane >> 4) * 16;
-#pragma unroll
-                        for (int rr = 0; rr < 16; ++rr) {
-                            float tv = tile[(r0 + rr) * 17 + col];
-                            s1 += tv;
-                            s2 = fmaf(tv, tv, s2);
-                        }
-                        s1 += __shfl_xor_sync(0xffffffffu, s1, 16);
-                        s2 += __shfl_xor_sync(0xffffffffu, s2, 16);
-                        if (lane < 16) {
-                            wsum[c * 32 + hc * 16 + col] += s1;
-                            wsum[BN + c * 32 + hc * 16 + col] += s2;
-                        }
-                        __syncwarp();
-                    }
-                }
-            }
-            // every epilogue thread has drained its TMEM rows: release the accumulator buffer to the MMA warp
-            tc_fence_before();
-            asm volatile("bar.sync 1, 256;" ::: "memory");
-            if (et == 0) mbar_arrive(bars + 8 * (2 * STAGES + 2 + buf));
-        }
-        if (p.stats && cur_n >= 0) flush(cur_n);
-    }
-    tc_fence_before();
-    __syncthreads();
-    if (warp == 1) {
-        __syncwarp();
-        tmem_dealloc(tmem_base, 2 * BN);
     }
 }
 
@@ -1378,45 +971,8 @@ static int make_map(CUtensorMap* tm, const void* ptr, long long rows, long long 
 }
 
 template <int BN, int STAGES>
-static int launch_conv(cudaStream_t st, const CUtensorMap& a, const CUtensorMap& b, const ConvTcParams& p) {
-    constexpr int smem = STAGES * (STAGE_A_BYTES + BN * 128) + 8 * (2 * STAGES + 1) + 16 + 1024;
-    static bool attr_done = false;
-    if (!attr_done) {
-        KP_CUDA(cudaFuncSetAttribute(conv_tc_k<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        attr_done = true;
-    }
-    dim3 grid((unsigned)((p.Q + 127) / 128), (unsigned)(p.Cout / BN), 1);
-    conv_tc_k<BN, STAGES><<<grid, 192, smem, st>>>(a, b, p);
-    KP_LAUNCH_CHECK();
-    return KP_OK;
-}
-
-template <int BN, int STAGES>
-static int launch_wgrad(cudaStream_t st, const CUtensorMap& a, const CUtensorMap& b, const WgradTcParams& p, int taps) {
-    constexpr int smem = STAGES * (2 * 8192 + (BN / 64) * 8192) + 8 * (2 * STAGES + 1) + 16 + 1024;
-    static bool attr_done = false;
-    if (!attr_done) {
-        KP_CUDA(cudaFuncSetAttribute(wgrad_tc_k<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        attr_done = true;
-    }
-    dim3 grid((unsigned)(p.Mtot / 128), (unsigned)(p.Ntot / BN), (unsigned)(taps * p.splits));
-    wgrad_tc_k<BN, STAGES><<<grid, 192, smem, st>>>(a, b, p);
-    KP_LAUNCH_CHECK();
-    return KP_OK;
-}
-
-static bool use_persistent() {
-    static int v = -1;
-    if (v < 0) {
-        const char* e = getenv("KP_TC_PERSIST");
-        v = (e && e[0] == '0') ? 0 : 1;
-    }
-    return v == 1;
-}
-
-template <int BN, int STAGES>
-static int launch_conv_persist(cudaStream_t st, const CUtensorMap& a, const CUtensorMap& b, const ConvTcParams& p) {
-    constexpr int smem = STAGES * (STAGE_A_BYTES + BN * 128) + (8 * 32 * 17 + 4 * 2 * BN) * 4 +
+static int launch_conv_persist(cudaStream_t st, const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& o, const ConvTcParams& p) {
+    constexpr int smem = STAGES * (STAGE_A_BYTES + BN * 128) + 2 * SLAB_BYTES + (8 * 32 * 17 + 4 * 2 * BN) * 4 +
                          8 * (2 * STAGES + 4) + 16 + 1024;
     static_assert(smem <= 227 * 1024, "shared memory budget");
     static bool attr_done = false;
@@ -1426,14 +982,14 @@ static int launch_conv_persist(cudaStream_t st, const CUtensorMap& a, const CUte
     }
     long long total = ((p.Q + 127) / 128) * (p.Cout / BN);
     int grid = (int)(total < kp_sm_count() ? total : kp_sm_count());
-    conv_tc_persist_k<BN, STAGES><<<grid, 320, smem, st>>>(a, b, p);
+    conv_tc_persist_k<BN, STAGES><<<grid, 320, smem, st>>>(a, b, o, p);
     KP_LAUNCH_CHECK();
     return KP_OK;
 }
 
 template <int BN, int STAGES>
-static int launch_conv_pair(cudaStream_t st, const CUtensorMap& a, const CUtensorMap& b, const ConvTcParams& p) {
-    constexpr int smem = STAGES * (STAGE_A_BYTES + (BN / 2) * 128) + (8 * 32 * 17 + 4 * 2 * BN) * 4 +
+static int launch_conv_pair(cudaStream_t st, const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& o, const ConvTcParams& p) {
+    constexpr int smem = STAGES * (STAGE_A_BYTES + (BN / 2) * 128) + 2 * SLAB_BYTES + (8 * 32 * 17 + 4 * 2 * BN) * 4 +
                          8 * (2 * STAGES + 4) + 16 + 1024;
     static_assert(smem <= 227 * 1024, "shared memory budget");
     static bool attr_done = false;
@@ -1445,27 +1001,7 @@ static int launch_conv_pair(cudaStream_t st, const CUtensorMap& a, const CUtenso
     int clusters = kp_sm_count() / 2;
     if (clusters > total) clusters = (int)total;
     if (clusters < 1) clusters = 1;
-    conv_tc_pair_k<BN, STAGES><<<2 * clusters, 320, smem, st>>>(a, b, p);
-    KP_LAUNCH_CHECK();
-    return KP_OK;
-}
-
-template <int BN, int STAGES, int RES_BYTES>
-static int launch_conv_resident(cudaStream_t st, const CUtensorMap& a, const CUtensorMap& b, const ConvTcParams& p) {
-    constexpr int smem = STAGES * STAGE_A_BYTES + RES_BYTES + (8 * 32 * 17 + 4 * 2 * BN) * 4 + 8 * (2 * STAGES + 5) + 16 + 1024;
-    static_assert(smem <= 227 * 1024, "shared memory budget");
-    static bool attr_done = false;
-    if (!attr_done) {
-        KP_CUDA(cudaFuncSetAttribute(conv_tc_resident_k<BN, STAGES, RES_BYTES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        attr_done = true;
-    }
-    const int ny = p.Cout / BN;
-    long long num_m = (p.Q + 127) / 128;
-    int gx = kp_sm_count() / ny;
-    if (gx < 1) gx = 1;
-    if (gx > num_m) gx = (int)num_m;
-    dim3 grid((unsigned)gx, (unsigned)ny, 1);
-    conv_tc_resident_k<BN, STAGES, RES_BYTES><<<grid, 320, smem, st>>>(a, b, p);
+    conv_tc_pair_k<BN, STAGES><<<2 * clusters, 320, smem, st>>>(a, b, o, p);
     KP_LAUNCH_CHECK();
     return KP_OK;
 }
@@ -1524,31 +1060,21 @@ extern "C" int kp_conv_tc(kp_stream stream, const void* in_bf16, int64_t Q, int 
     for (int i = 0; i < 9; ++i) p.shift[i] = i < taps ? shifts[i] : 0;
     p.bias = bias; p.out = (bf16*)out_bf16; p.stats = stats; p.PH = PH; p.PW = PW; p.VH = VH; p.VW = VW;
     cudaStream_t st = (cudaStream_t)stream;
-    if (use_persistent()) {
-        constexpr int RES = 9 * 16384;                         // 144 KB of resident weights
-        const long long wbytes = (long long)taps * Cin * BN * 2;
-        static int res_on = -1;
-        if (res_on < 0) { const char* e = getenv("KP_TC_RESIDENT"); res_on = (e && e[0] == '0') ? 0 : 1; }
-        if (res_on && wbytes <= RES && Q >= 128LL * kp_sm_count()) {
-            if (BN == 128) return launch_conv_resident<128, 3, RES>(st, ta, tb, p);
-            if (BN == 64) return launch_conv_resident<64, 3, RES>(st, ta, tb, p);
-        }
-        static int pair_on = -1;
-        if (pair_on < 0) { const char* e = getenv("KP_TC_PAIR"); pair_on = (e && e[0] == '0') ? 0 : 1; }
-        if (pair_on && BN >= 128 && Q >= 256) {
-            CUtensorMap tbh;                                   // each CTA of the pair loads half of the weight tile
-            rc = make_map(&tbh, wt_bf16, (long long)taps * Cout, Cin, BN / 2);
-            if (rc) return rc;
-            if (BN == 256) return launch_conv_pair<256, 6>(st, ta, tbh, p);
-            return launch_conv_pair<128, 8>(st, ta, tbh, p);
-        }
-        if (BN == 256) return launch_conv_persist<256, 4>(st, ta, tb, p);
-        if (BN == 128) return launch_conv_persist<128, 5>(st, ta, tb, p);
-        return launch_conv_persist<64, 6>(st, ta, tb, p);
+    CUtensorMap to;                                            // epilogue TMA store: 64 channels x 128 pixels per slab
+    rc = make_map(&to, out_bf16, Q, Cout, 128);
+    if (rc) return rc;
+    static int pair_on = -1;
+    if (pair_on < 0) { const char* e = getenv("KP_TC_PAIR"); pair_on = (e && e[0] == '0') ? 0 : 1; }
+    if (pair_on && BN >= 128 && Q >= 256) {
+        CUtensorMap tbh;                                       // each CTA of the pair loads half of the weight tile
+        rc = make_map(&tbh, wt_bf16, (long long)taps * Cout, Cin, BN / 2);
+        if (rc) return rc;
+        if (BN == 256) return launch_conv_pair<256, 5>(st, ta, tbh, to, p);
+        return launch_conv_pair<128, 7>(st, ta, tbh, to, p);
     }
-    if (BN == 256) return launch_conv<256, 4>(st, ta, tb, p);
-    if (BN == 128) return launch_conv<128, 4>(st, ta, tb, p);
-    return launch_conv<64, 4>(st, ta, tb, p);
+    if (BN == 256) return launch_conv_persist<256, 3>(st, ta, tb, to, p);
+    if (BN == 128) return launch_conv_persist<128, 5>(st, ta, tb, to, p);
+    return launch_conv_persist<64, 6>(st, ta, tb, to, p);
 }
 
 // Split the pixel range so that (tiles * splits) work items fill `workers` persistent CTAs (or clusters) in whole
@@ -1605,19 +1131,15 @@ extern "C" int kp_conv_wgrad_tc(kp_stream stream, const void* x_bf16, const void
     KP_CUDA(cudaMemsetAsync(stg, 0, sizeof(float) * (size_t)taps * Mtot * Ntot, st));
     static int wpair_on = -1;
     if (wpair_on < 0) { const char* e = getenv("KP_TC_PAIR"); wpair_on = (e && e[0] == '0') ? 0 : 1; }
-    if (use_persistent() && wpair_on && Mtot % 256 == 0 && BN >= 128) {
+    if (wpair_on && Mtot % 256 == 0 && BN >= 128) {
         // recompute the split for 256-row tiles
         const int tiles2 = (Mtot / 256) * (Ntot / BN) * taps;
         choose_split(tiles2, kp_sm_count() / 2, blocks64, &p.kchunk, &p.splits);
         if (BN == 256) rc = launch_wgrad_pair<256, 6>(st, ta, tb, p, taps);
         else rc = launch_wgrad_pair<128, 8>(st, ta, tb, p, taps);
-    } else if (use_persistent()) {
-        if (BN == 256) rc = launch_wgrad_persist<256, 4>(st, ta, tb, p, taps);
-        else if (BN == 128) rc = launch_wgrad_persist<128, 6>(st, ta, tb, p, taps);
-        else rc = launch_wgrad_persist<64, 8>(st, ta, tb, p, taps);
-    } else if (BN == 256) rc = launch_wgrad<256, 4>(st, ta, tb, p, taps);
-    else if (BN == 128) rc = launch_wgrad<128, 4>(st, ta, tb, p, taps);
-    else rc = launch_wgrad<64, 4>(st, ta, tb, p, taps);
+    } else if (BN == 256) rc = launch_wgrad_persist<256, 4>(st, ta, tb, p, taps);
+    else if (BN == 128) rc = launch_wgrad_persist<128, 6>(st, ta, tb, p, taps);
+    else rc = launch_wgrad_persist<64, 8>(st, ta, tb, p, taps);
     if (rc) return rc;
     long long total = (long long)Cout * Cin * taps;
     int blocks = (int)((total + 255) / 256);
