@@ -246,15 +246,16 @@ def main():
     pk = peaks()
     if rank == 0 and not args.no_kernel_timing and args.precision == 'bf16':
         tr2 = tr
-        was = tr2.use_graph
+        was, was2 = tr2.use_graph, tr2.two_streams
         tr2.use_graph = False
+        tr2.two_streams = False                    # time every kernel alone on one stream
         one_step()
         torch.cuda.synchronize()
         L.timing = []
         one_step()
         torch.cuda.synchronize()
         rec, L.timing = L.timing, None
-        tr2.use_graph = was
+        tr2.use_graph, tr2.two_streams = was, was2
         agg = {}
         calls = []
         for name, fl, a, b, tg in rec:

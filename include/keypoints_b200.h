@@ -135,6 +135,13 @@ int kp_bn_act_bwd_reduce(kp_stream stream, const kp_view* dout, const kp_view* y
 int kp_bn_act_bwd_apply(kp_stream stream, const kp_view* y, const kp_view* dy, const float* scale,
                         const float* mean, const float* invstd, const double* sums, double count,
                         int N, int H, int W, int C, float* dgamma, float* dbeta);
+/* Alternative pass 2 for post = none / pool on the vectorised NHWC path: repeats the gather of pass 1 (called with
+ * dy = NULL) and writes dy directly, so dz never round-trips through HBM.  KP_ERR_UNSUPPORTED if not applicable. */
+int kp_bn_act_bwd_apply_gather(kp_stream stream, const kp_view* dout, const kp_view* y,
+                               const kp_view* dy, const float* scale, const float* shift,
+                               const float* mean, const float* invstd, const double* sums,
+                               double count, int act, int post, int pad, int N, int H, int W, int C,
+                               float* dgamma, float* dbeta);
 /* kp_bn_finalize + kp_bn_act_fwd in one launch when the vectorised path applies (otherwise the two
  * kernels are launched back to back): every block derives its channels' affine from the batch
  * statistics, block 0 publishes scale/shift/mean/invstd and updates the running statistics. */

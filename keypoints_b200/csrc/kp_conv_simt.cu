@@ -231,10 +231,23 @@ __device__ __forceinline__ void store2(bf16* p, float a, float b) {
     *reinterpret_cast<__nv_bfloat162*>(p) = __floats2bfloat162_rn(a, b);
 }
 
-// stage the thin values of TILE_PX pixels: thin[p][kk], kk = t*Cthin + c, gathered at (y + t/ks + off, x + t%ks + off)
+// stage the thin values of TILE_PX pixels: thin[p][kk], kk = t*Cthin + c, gathered at (y + t/ks + off, x + t%ks + off).
+// The per-kk element offsets / tap coordinates are tabulated once per block (sm_koff, sm_kyx) so the gather loop has
+// no integer divisions.
+__device__ __forceinline__ void build_koff(long long* sm_koff, int* sm_kyx, long long sy, long long sx, long long sc,
+                                           int Cthin, int ks, int off, int KK, int KKP) {
+    for (int kk = threadIdx.x; kk < KKP; kk += blockDim.x) {
+        int t = kk / Cthin, c = kk - t * Cthin;
+        int dy = t / ks + off, dx = t % ks + off;
+        sm_koff[kk] = kk < KK ? dy * sy + dx * sx + c * sc : 0;
+        sm_kyx[kk] = kk < KK ? ((dy & 0xffff) << 16) | (dx & 0xffff) : 0x7fff7fff;
+    }
+}
+
 template <typename TT>
-__device__ __forceinline__ void stage_thin(const View<TT>& thin, float* sm_thin, int* sm_xy, long long p0, long long M, int OH,
-                                           int OW, int IH, int IW, int Cthin, int ks, int off, int KK, int KKP) {
+__device__ __forceinline__ void stage_thin(const View<TT>& thin, float* sm_thin, int* sm_xy, const long long* sm_koff,
+                                           const int* sm_kyx, long long p0, long long M, int OH, int OW, int IH, int IW,
+                                           int KK, int KKP, bool inbounds) {
     const int tid = threadIdx.x;
     long long p = p0 + tid;
     int n = 0, y = 0, x = 0;
@@ -249,14 +262,19 @@ __device__ __forceinline__ void stage_thin(const View<TT>& thin, float* sm_thin,
     sm_xy[tid * 3 + 1] = y;
     sm_xy[tid * 3 + 2] = x;
     float* dst = sm_thin + tid * KKP;
-    for (int kk = 0; kk < KKP; ++kk) {
-        float v = 0.f;
-        if (ok && kk < KK) {
-            int t = kk / Cthin, c = kk - t * Cthin;
-            int iy = y + t / ks + off, ix = x + t % ks + off;
-            if (iy >= 0 && iy < IH && ix >= 0 && ix < IW) v = to_f(*thin.at(n, iy, ix, c));
+    const TT* base = thin.at(n, y, x, 0);
+    if (ok && inbounds) {
+        for (int kk = 0; kk < KKP; ++kk) dst[kk] = kk < KK ? to_f(base[sm_koff[kk]]) : 0.f;
+    } else {
+        for (int kk = 0; kk < KKP; ++kk) {
+            float v = 0.f;
+            if (ok && kk < KK) {
+                const int pk = sm_kyx[kk];
+                const int iy = y + (int)(short)(pk >> 16), ix = x + (int)(short)(pk & 0xffff);
+                if (iy >= 0 && iy < IH && ix >= 0 && ix < IW) v = to_f(base[sm_koff[kk]]);
+            }
+            dst[kk] = v;
         }
-        dst[kk] = v;
     }
 }
 
@@ -268,6 +286,8 @@ thin_fprop_k(View<TT> thin, const float* __restrict__ wk, const float* __restric
     __shared__ __align__(16) float sm_thin[TILE_PX * KKP];
     __shared__ int sm_xy[TILE_PX * 3];
     __shared__ float sm_red[8][2][64];
+    __shared__ long long sm_koff[KKP];
+    __shared__ int sm_kyx[KKP];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int KK = ks * ks * Cthin;
     const int c0 = blockIdx.y * 64 + lane * 2;
@@ -281,9 +301,11 @@ thin_fprop_k(View<TT> thin, const float* __restrict__ wk, const float* __restric
     const float b0 = bias ? bias[c0] : 0.f, b1 = bias ? bias[c0 + 1] : 0.f;
     float s1a = 0.f, s1b = 0.f, s2a = 0.f, s2b = 0.f;
     const long long ntiles = (M + TILE_PX - 1) / TILE_PX;
+    build_koff(sm_koff, sm_kyx, thin.sy, thin.sx, thin.sc, Cthin, ks, off, KK, KKP);
+    const bool inb = off >= 0 && OH + off + ks - 1 <= IH && OW + off + ks - 1 <= IW;
     for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         __syncthreads();
-        stage_thin<TT>(thin, sm_thin, sm_xy, tile * TILE_PX, M, OH, OW, IH, IW, Cthin, ks, off, KK, KKP);
+        stage_thin<TT>(thin, sm_thin, sm_xy, sm_koff, sm_kyx, tile * TILE_PX, M, OH, OW, IH, IW, KK, KKP, inb);
         __syncthreads();
         for (int i = 0; i < 32; ++i) {
             const int pp = warp * 32 + i;
@@ -323,17 +345,21 @@ thin_wgrad_k(View<TT> thin, View<TW> wide, float* dw, int N, int OH, int OW, int
              int cdiv, long long sa, long long sb, long long sc) {
     __shared__ __align__(16) float sm_thin[TILE_PX * KKP];
     __shared__ int sm_xy[TILE_PX * 3];
+    __shared__ long long sm_koff[KKP];
+    __shared__ int sm_kyx[KKP];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int KK = ks * ks * Cthin;
     const int c0 = blockIdx.y * 64 + lane * 2;
     const long long M = (long long)N * OH * OW;
+    build_koff(sm_koff, sm_kyx, thin.sy, thin.sx, thin.sc, Cthin, ks, off, KK, KKP);
+    const bool inb = off >= 0 && OH + off + ks - 1 <= IH && OW + off + ks - 1 <= IW;
     float g0[KKP], g1[KKP];
 #pragma unroll
     for (int kk = 0; kk < KKP; ++kk) { g0[kk] = 0.f; g1[kk] = 0.f; }
     const long long ntiles = (M + TILE_PX - 1) / TILE_PX;
     for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         __syncthreads();
-        stage_thin<TT>(thin, sm_thin, sm_xy, tile * TILE_PX, M, OH, OW, IH, IW, Cthin, ks, off, KK, KKP);
+        stage_thin<TT>(thin, sm_thin, sm_xy, sm_koff, sm_kyx, tile * TILE_PX, M, OH, OW, IH, IW, KK, KKP, inb);
         __syncthreads();
         for (int i = 0; i < 32; ++i) {
             const int pp = warp * 32 + i;

@@ -443,11 +443,14 @@ bn_act_fwd_rows_k(View<TI> y, View<TO> out, const float* __restrict__ scale, con
 
 // Backward pass 1: dz = gradient w.r.t. the BatchNorm output (replicate-pad fold + pool/upsample backward +
 // activation backward), written to dy; per-channel sums of dz and dz*xhat accumulated.
-template <typename TG, typename TY, typename TD, int POST>
+// APPLY = false: pass 1 (dz written if dy given, sums accumulated).  APPLY = true: "recompute" pass 2 — the gather is
+// repeated and dy = scale (dz - mean(dz) - xhat mean(dz xhat)) is written directly, so dz never round-trips through HBM
+// (cheaper whenever d(out) is not larger than y: post = none / pool).
+template <typename TG, typename TY, typename TD, int POST, bool APPLY>
 __global__ void __launch_bounds__(256, 2)
 bn_act_bwd_rows_k(View<TG> dout, View<TY> y, View<TD> dy, const float* __restrict__ scale,
                   const float* __restrict__ shift, const float* __restrict__ mean, const float* __restrict__ invstd,
-                  double* sums, int act, int pad, int N, int H, int W, int C, int OH, int OW, int cg_shift) {
+                  double* sums, double count, int act, int pad, int N, int H, int W, int C, int OH, int OW, int cg_shift) {
     using RawG = typename Vec<TG, V8>::Raw;
     using RawY = typename Vec<TY, V8>::Raw;
     __shared__ float red[2][256 * V8];
@@ -459,12 +462,22 @@ bn_act_bwd_rows_k(View<TG> dout, View<TY> y, View<TD> dy, const float* __restric
     for (int i = 0; i < V8; ++i) {
         sc[i] = scale ? scale[c0 + i] : 1.f; sh[i] = shift ? shift[c0 + i] : 0.f;
         mu[i] = mean ? mean[c0 + i] : 0.f; is[i] = invstd ? invstd[c0 + i] : 1.f;
-        s1[i] = 0.f; s2[i] = 0.f;
+        if (APPLY) { s1[i] = (float)(sums[c0 + i] / count); s2[i] = (float)(sums[C + c0 + i] / count); }
+        else { s1[i] = 0.f; s2[i] = 0.f; }
     }
     const float ry = (OH > 1) ? (float)(H - 1) / (float)(OH - 1) : 0.f;
     const float rx = (OW > 1) ? (float)(W - 1) / (float)(OW - 1) : 0.f;
     // consume one element: g = gradient w.r.t. the activation output, yv = raw conv output
     auto emit = [&](int n, int yy, int xx, float (&g)[V8], const float (&yv)[V8]) {
+        if (APPLY) {
+#pragma unroll
+            for (int i = 0; i < V8; ++i) {
+                const float dz = g[i] * act_grad(fmaf(yv[i], sc[i], sh[i]), act);
+                g[i] = sc[i] * (dz - s1[i] - (yv[i] - mu[i]) * is[i] * s2[i]);
+            }
+            Vec<TD, V8>::store(dy.at(n, yy, xx, c0), g);
+            return;
+        }
 #pragma unroll
         for (int i = 0; i < V8; ++i) {
             g[i] *= act_grad(fmaf(yv[i], sc[i], sh[i]), act);
@@ -606,6 +619,7 @@ bn_act_bwd_rows_k(View<TG> dout, View<TY> y, View<TD> dy, const float* __restric
             }
         }
     }
+    if (APPLY) return;
 #pragma unroll
     for (int i = 0; i < V8; ++i) { red[0][threadIdx.x * V8 + i] = s1[i]; red[1][threadIdx.x * V8 + i] = s2[i]; }
     __syncthreads();
@@ -1024,7 +1038,7 @@ extern "C" int kp_bn_act_bwd_reduce(kp_stream stream, const kp_view* dout, const
                     const long long cap = 2LL * kp_sm_count();
                     const int g = (int)(rows < cap ? rows : cap), sh = ilog2(C / 8);
                     cudaStream_t st = (cudaStream_t)stream;
-#define KP_BWD(POSTV) bn_act_bwd_rows_k<TG, TY, TD, POSTV><<<g, 256, 0, st>>>(make_view<TG>(dout), make_view<TY>(y), make_view<TD>(dyv), scale, shift, mean, invstd, sums, act, pad, N, H, W, C, OH, OW, sh)
+#define KP_BWD(POSTV) bn_act_bwd_rows_k<TG, TY, TD, POSTV, false><<<g, 256, 0, st>>>(make_view<TG>(dout), make_view<TY>(y), make_view<TD>(dyv), scale, shift, mean, invstd, sums, 1.0, act, pad, N, H, W, C, OH, OW, sh)
                     if (post == KP_POST_NONE) KP_BWD(KP_POST_NONE);
                     else if (post == KP_POST_POOL) KP_BWD(KP_POST_POOL);
                     else if (H < 2 || W < 2) KP_BWD(KP_POST_UP);
@@ -1046,6 +1060,48 @@ extern "C" int kp_bn_act_bwd_reduce(kp_stream stream, const kp_view* dout, const
             });
         });
     });
+}
+
+extern "C" int kp_bn_act_bwd_apply_gather(kp_stream stream, const kp_view* dout, const kp_view* y, const kp_view* dy,
+                                          const float* scale, const float* shift, const float* mean,
+                                          const float* invstd, const double* sums, double count, int act, int post,
+                                          int pad, int N, int H, int W, int C, float* dgamma, float* dbeta) {
+    KP_CHECK_ARG(dout && y && dy && dout->ptr && y->ptr && dy->ptr && sums && scale && shift && mean && invstd &&
+                     count > 0 && N > 0 && H > 0 && W > 0 && C > 0 && (post == KP_POST_NONE || post == KP_POST_POOL),
+                 "kp_bn_act_bwd_apply_gather: bad arguments");
+    int OH, OW;
+    out_dims(post, H, W, &OH, &OW);
+    const long long P = (long long)N * H * W;
+    if (!(view_vec8_ok(y, C) && view_vec8_ok(dout, C) && view_vec8_ok(dy, C) && fast_ok(C, P * C))) {
+        kp_set_error("kp_bn_act_bwd_apply_gather: only the vectorised NHWC path is implemented (C=%d)", C);
+        return KP_ERR_UNSUPPORTED;
+    }
+    const long long rows = post == KP_POST_POOL ? (long long)N * ((H + 1) / 2) : (long long)N * H;
+    const int g = rows_grid(rows), sh = ilog2(C / 8);
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = dispatch1(dout->dtype, [&](auto tg) -> int {
+        return dispatch1(y->dtype, [&](auto ty) -> int {
+            return dispatch1(dy->dtype, [&](auto td) -> int {
+                using TG = decltype(tg);
+                using TY = decltype(ty);
+                using TD = decltype(td);
+                if (post == KP_POST_NONE)
+                    bn_act_bwd_rows_k<TG, TY, TD, KP_POST_NONE, true><<<g, 256, 0, st>>>(
+                        make_view<TG>(dout), make_view<TY>(y), make_view<TD>(dy), scale, shift, mean, invstd,
+                        const_cast<double*>(sums), count, act, pad, N, H, W, C, OH, OW, sh);
+                else
+                    bn_act_bwd_rows_k<TG, TY, TD, KP_POST_POOL, true><<<g, 256, 0, st>>>(
+                        make_view<TG>(dout), make_view<TY>(y), make_view<TD>(dy), scale, shift, mean, invstd,
+                        const_cast<double*>(sums), count, act, pad, N, H, W, C, OH, OW, sh);
+                KP_LAUNCH_CHECK();
+                return KP_OK;
+            });
+        });
+    });
+    if (rc) return rc;
+    if (dgamma || dbeta) bn_grad_finalize_k<<<(C + 127) / 128, 128, 0, st>>>(sums, C, dgamma, dbeta);
+    KP_LAUNCH_CHECK();
+    return KP_OK;
 }
 
 extern "C" int kp_bn_act_bwd_apply(kp_stream stream, const kp_view* y, const kp_view* dy, const float* scale,

@@ -259,12 +259,19 @@ def unit_backward(specs: List[ConvSpec], params: List[LayerParams], grads: List[
         if s.bn:
             if c.mean is None:
                 raise NotImplementedError('backward through eval-mode BatchNorm is not supported')
-            L.call('kp_bn_act_bwd_reduce', st, L.view(dout), L.view(yv), L.view(dy_int), L.ptr(c.scale), L.ptr(c.shift),
-                   L.ptr(c.mean), L.ptr(c.invstd), L.ptr(sums), a, po, dout_pad, N, h, w, s.cout,
-                   tag=f'{tag}{i} {s.cin}->{s.cout}@{h}x{w} {s.post}')
-            L.call('kp_bn_act_bwd_apply', st, L.view(yv), L.view(dy_int), L.ptr(c.scale), L.ptr(c.mean), L.ptr(c.invstd),
-                   L.ptr(sums), float(N * h * w), N, h, w, s.cout, L.ptr(g.dgamma), L.ptr(g.dbeta),
-                   tag=f'{tag}{i} {s.cin}->{s.cout}@{h}x{w} {s.post}')
+            ltag = f'{tag}{i} {s.cin}->{s.cout}@{h}x{w} {s.post}'
+            ncg = s.cout // 8
+            regather = (precision == 'bf16' and s.post in ('none', 'pool') and s.cout % 8 == 0 and ncg & (ncg - 1) == 0
+                        and ncg <= 256 and dout.stride(3) == 1 and dout.dtype == torch.bfloat16)
+            L.call('kp_bn_act_bwd_reduce', st, L.view(dout), L.view(yv), None if regather else L.view(dy_int), L.ptr(c.scale),
+                   L.ptr(c.shift), L.ptr(c.mean), L.ptr(c.invstd), L.ptr(sums), a, po, dout_pad, N, h, w, s.cout, tag=ltag)
+            if regather:     # pass 2 repeats the (cheap) gather instead of reading dz back
+                L.call('kp_bn_act_bwd_apply_gather', st, L.view(dout), L.view(yv), L.view(dy_int), L.ptr(c.scale),
+                       L.ptr(c.shift), L.ptr(c.mean), L.ptr(c.invstd), L.ptr(sums), float(N * h * w), a, po, dout_pad,
+                       N, h, w, s.cout, L.ptr(g.dgamma), L.ptr(g.dbeta), tag=ltag)
+            else:
+                L.call('kp_bn_act_bwd_apply', st, L.view(yv), L.view(dy_int), L.ptr(c.scale), L.ptr(c.mean), L.ptr(c.invstd),
+                       L.ptr(sums), float(N * h * w), N, h, w, s.cout, L.ptr(g.dgamma), L.ptr(g.dbeta), tag=ltag)
             # the bias of a conv feeding train-mode BatchNorm has an exactly zero gradient
         else:
             L.call('kp_bn_act_bwd_reduce', st, L.view(dout), L.view(yv), L.view(dy_int), None, None, None, None,

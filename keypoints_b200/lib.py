@@ -47,6 +47,7 @@ SIGNATURES = {
     'kp_bn_act_fwd': [_P, _VP, _VP, _P, _P, _I, _I, _I, _I, _I, _I, _I],
     'kp_bn_act_bwd_reduce': [_P, _VP, _VP, _VP, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I],
     'kp_bn_act_bwd_apply': [_P, _VP, _VP, _P, _P, _P, _P, _D, _I, _I, _I, _I, _P, _P],
+    'kp_bn_act_bwd_apply_gather': [_P, _VP, _VP, _VP, _P, _P, _P, _P, _P, _D, _I, _I, _I, _I, _I, _I, _I, _P, _P],
     'kp_bn_finalize_act_fwd': [_P, _P, _D, _P, _P, _F, _F, _P, _P, _P, _P, _P, _P, _P, _VP, _VP, _I, _I, _I, _I, _I, _I, _I],
     'kp_bn_grad_finalize': [_P, _P, _I, _P, _P],
     'kp_spatial_softmax_fwd': [_P, _P, _I, _I, _I, _P, _P, _P],

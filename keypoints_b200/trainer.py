@@ -67,6 +67,8 @@ class Trainer:
                       'encoder': _UnitState('encoder', first)}
         self._flatten()
         self.misc = CachedAlloc('misc')
+        self.side = torch.cuda.Stream(device=self.device)     # encoder branch runs beside the keypoint branch
+        self.two_streams = True
         self.graph = None
         self.graph_key = None
         self.steps_done = 0
@@ -138,6 +140,20 @@ class Trainer:
         return engine.unit_backward(u.specs, u.params, u.grads, u.ctxs, dout, dout_pad, self.precision, need_dx,
                                     alloc=u.alloc, tag='b')
 
+    def _fork(self):
+        """Run the following block on the side stream, ordered after everything issued so far (captured as a parallel
+        branch of the CUDA graph): the memory-bound BatchNorm passes of one Unit overlap the tensor-core convolutions
+        of the other."""
+        if not self.two_streams:
+            import contextlib
+            return contextlib.nullcontext()
+        self.side.wait_stream(torch.cuda.current_stream())
+        return torch.cuda.stream(self.side)
+
+    def _join(self):
+        if self.two_streams:
+            torch.cuda.current_stream().wait_stream(self.side)
+
     def _bottleneck_dims(self, H, W):
         h, w = H, W
         for s in self.units['encoder'].specs:
@@ -204,12 +220,14 @@ class Trainer:
             m = self.misc('m', (n, K, h, w), f32, dev)
             xe = engine.to_padded(xa, prec, self.misc, 'xe')
             xk = engine.to_padded(xb, prec, self.misc, 'xk')
-            self._fwd_unit(enc, xe, H, W, dec_in[..., :C], 1)
+            with self._fork():
+                self._fwd_unit(enc, xe, H, W, dec_in[..., :C], 1)
             self._fwd_unit(kp, xk, H, W, heat.permute(0, 2, 3, 1), 0)
             L.call('kp_spatial_softmax_fwd', st, L.ptr(heat), n * K, h, w, L.ptr(k_t), L.ptr(p_h), L.ptr(p_w))
             L.call('kp_gaussian_fwd', st, L.ptr(k_t), n * K, h, w, sig, eps, L.ptr(m))
             L.call('kp_bn_act_fwd', st, L.nchw(m), L.view(dec_in[..., C:C + K]), None, None, L.ACT_NONE, L.POST_NONE, 1,
                    n, h, w, K)
+            self._join()
         else:
             phi_s = self.misc('phi_s', (n, h, w, C), self.T, dev)
             phi_t = self.misc('phi_t', (n, h, w, C), self.T, dev)
@@ -220,12 +238,16 @@ class Trainer:
             xs = engine.to_padded(xa, prec, self.misc, 'xs')
             xt = engine.to_padded(xb, prec, self.misc, 'xt')
             # source frame: constants, but its BatchNorm running statistics update (transporter.py:36-37)
-            self._fwd_unit(enc, xs, H, W, phi_s, 0)
+            with self._fork():
+                self._fwd_unit(enc, xs, H, W, phi_s, 0)
             self._fwd_unit(kp, xs, H, W, heat.permute(0, 2, 3, 1), 0)
             L.call('kp_spatial_softmax_fwd', st, L.ptr(heat), n * K, h, w, L.ptr(k_s), None, None)
-            self._fwd_unit(enc, xt, H, W, phi_t, 0)
+            self._join()
+            with self._fork():
+                self._fwd_unit(enc, xt, H, W, phi_t, 0)
             self._fwd_unit(kp, xt, H, W, heat.permute(0, 2, 3, 1), 0)
             L.call('kp_spatial_softmax_fwd', st, L.ptr(heat), n * K, h, w, L.ptr(k_t), L.ptr(p_h), L.ptr(p_w))
+            self._join()
             L.call('kp_transport_fwd', st, L.view(phi_s), L.view(phi_t), L.ptr(k_s), L.ptr(k_t), L.view(dec_in[..., :C]),
                    1, L.ptr(mask_s), L.ptr(mask_t), L.ptr(amax), n, h, w, C, K, sig, eps)
         self._fwd_unit(dec, dec_in, h, w, xhat.permute(0, 2, 3, 1), 0)
@@ -244,9 +266,11 @@ class Trainer:
         if self.kind == 'keynet':
             L.call('kp_gaussian_bwd', st, L.view(ddec[..., C:C + K]), 1, L.ptr(k_t), None, n, K, h, w, sig, eps, L.ptr(dk))
             L.call('kp_spatial_softmax_bwd', st, L.ptr(dk), L.ptr(k_t), L.ptr(p_h), L.ptr(p_w), n * K, h, w, L.ptr(dheat))
+            with self._fork():
+                self._bwd_unit(enc, ddec[..., :C], 1, False)
             self._bwd_unit(kp, dheat.permute(0, 2, 3, 1), 0, False)
+            self._join()
             self._bucket_ready('keypoint')
-            self._bwd_unit(enc, ddec[..., :C], 1, False)
             self._bucket_ready('encoder')
         else:
             dphi = self.misc('dphi_t', (n, h, w, C), self.T, dev)
@@ -255,9 +279,11 @@ class Trainer:
                    L.ptr(mask_t), L.view(dphi), L.ptr(dmask), n, h, w, C)
             L.call('kp_gaussian_bwd', st, L.view(dmask), 0, L.ptr(k_t), L.ptr(amax), n, K, h, w, sig, eps, L.ptr(dk))
             L.call('kp_spatial_softmax_bwd', st, L.ptr(dk), L.ptr(k_t), L.ptr(p_h), L.ptr(p_w), n * K, h, w, L.ptr(dheat))
+            with self._fork():
+                self._bwd_unit(enc, dphi, 0, False)
             self._bwd_unit(kp, dheat.permute(0, 2, 3, 1), 0, False)
+            self._join()
             self._bucket_ready('keypoint')
-            self._bwd_unit(enc, dphi, 0, False)
             self._bucket_ready('encoder')
 
     # ------------------------------------------------------------------------------------------
