@@ -18,7 +18,11 @@ import torch
 
 from . import lib as L
 
+import os
+
 BN_EPS = 1e-5
+REGATHER = os.environ.get('KP_BN_REGATHER', '0') != '0'     # measured slower than the dz round trip
+REGATHER_POSTS = tuple(os.environ.get('KP_BN_REGATHER_POSTS', 'none,pool').split(','))
 BN_MOMENTUM = 0.1
 
 
@@ -261,7 +265,7 @@ def unit_backward(specs: List[ConvSpec], params: List[LayerParams], grads: List[
                 raise NotImplementedError('backward through eval-mode BatchNorm is not supported')
             ltag = f'{tag}{i} {s.cin}->{s.cout}@{h}x{w} {s.post}'
             ncg = s.cout // 8
-            regather = (precision == 'bf16' and s.post in ('none', 'pool') and s.cout % 8 == 0 and ncg & (ncg - 1) == 0
+            regather = (REGATHER and precision == 'bf16' and s.post in REGATHER_POSTS and s.cout % 8 == 0 and ncg & (ncg - 1) == 0
                         and ncg <= 256 and dout.stride(3) == 1 and dout.dtype == torch.bfloat16)
             L.call('kp_bn_act_bwd_reduce', st, L.view(dout), L.view(yv), None if regather else L.view(dy_int), L.ptr(c.scale),
                    L.ptr(c.shift), L.ptr(c.mean), L.ptr(c.invstd), L.ptr(sums), a, po, dout_pad, N, h, w, s.cout, tag=ltag)
