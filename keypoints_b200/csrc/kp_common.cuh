@@ -125,3 +125,12 @@ __device__ __forceinline__ float act_grad(float z, int act) {
 }
 
 int kp_sm_count();
+
+// mma.sync kernels for the first (Cin <= 3) convolution of a Unit in bf16 mode (kp_conv_thin_mma.cu)
+bool kp_thin_mma_fprop_ok(const kp_view* in, const kp_view* out, int OH, int OW, int IH, int IW, int Cin, int Cout, int ks,
+                          int off);
+int kp_thin_mma_fprop(cudaStream_t st, const kp_view* in, const float* wk, const float* bias, const kp_view* out,
+                      double* stats, int N, int OH, int OW, int Cin, int Cout);
+bool kp_thin_mma_wgrad_ok(const kp_view* x, const kp_view* dy, int W, int Cin, int Cout, int ks);
+int kp_thin_mma_wgrad(cudaStream_t st, const kp_view* x, const kp_view* dy, float* dw, int N, int H, int W, int Cin,
+                      int Cout);

@@ -448,6 +448,14 @@ static bool thin_fast_enabled() {
     }
     return v == 1;
 }
+static bool thin_mma_enabled() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("KP_THIN_MMA");
+        v = (e && e[0] == '0') ? 0 : 1;
+    }
+    return v == 1;
+}
 static int thin_grid(long long M) {
     long long tiles = (M + TILE_PX - 1) / TILE_PX;
     long long cap = (long long)kp_sm_count() * 4;
@@ -503,6 +511,8 @@ extern "C" int kp_conv_simt(kp_stream stream, const kp_view* in, const float* wk
     dim3 grid((unsigned)((M + BM - 1) / BM), (unsigned)((Cout + BN - 1) / BN), 1);
     const int KKt = ks * ks * Cin;
     const bool out2 = out->sc == 1 && (((uintptr_t)out->ptr) % 8) == 0 && out->sx % 2 == 0 && out->sy % 2 == 0 && out->sn % 2 == 0;
+    if (thin_mma_enabled() && out->dtype == KP_BF16 && kp_thin_mma_fprop_ok(in, out, OH, OW, IH, IW, Cin, Cout, ks, off))
+        return kp_thin_mma_fprop((cudaStream_t)stream, in, wk, bias, out, stats, N, OH, OW, Cin, Cout);
     if (thin_fast_enabled() && KKt <= THIN_MAX && Cout % 64 == 0 && out2) {      // thin-K: first conv / dgrad of a thin head
         dim3 g2((unsigned)thin_grid(M), (unsigned)(Cout / 64), 1);
         return dispatch1(in->dtype, [&](auto ti) -> int {
@@ -557,6 +567,8 @@ extern "C" int kp_conv_wgrad_simt(kp_stream stream, const kp_view* x, const kp_v
     auto pair_ok = [](const kp_view* v) {
         return v->sc == 1 && (((uintptr_t)v->ptr) % 8) == 0 && v->sx % 2 == 0 && v->sy % 2 == 0 && v->sn % 2 == 0;
     };
+    if (thin_mma_enabled() && dy->dtype == KP_BF16 && kp_thin_mma_wgrad_ok(x, dy, W, Cin, Cout, ks))
+        return kp_thin_mma_wgrad((cudaStream_t)stream, x, dy, dw_oihw, N, H, W, Cin, Cout);
     if (thin_fast_enabled() && KK <= THIN_MAX && Cout % 64 == 0 && pair_ok(dy)) {
         // thin = x patches (kk = t*Cin + ci), wide = dy (co): dw[co][ci][t]
         dim3 g2((unsigned)thin_grid(P), (unsigned)(Cout / 64), 1);

@@ -289,7 +289,13 @@ bn_act_bwd_reduce_k(View<TG> dout, View<TY> y, View<TD> dy, const float* __restr
 // before the first use so each thread keeps 4-10 independent 16-byte requests in flight.
 // ================================================================================================
 constexpr int V8 = 8;
-constexpr int UNR = 4;
+#ifndef KP_EW_UNR
+#define KP_EW_UNR 4
+#endif
+#ifndef KP_EW_MINB
+#define KP_EW_MINB 2
+#endif
+constexpr int UNR = KP_EW_UNR;
 
 // Optional fused BatchNorm finalize: when stats != nullptr the forward kernels derive the per-channel affine from
 // the batch statistics themselves (every block recomputes its 8 channels; block 0 publishes scale / shift / mean /
@@ -366,7 +372,7 @@ __device__ __forceinline__ void raw_act(const typename Vec<T, V8>::Raw& r, const
 }
 
 template <typename TI, typename TO, int POST>
-__global__ void __launch_bounds__(256, 2)
+__global__ void __launch_bounds__(256, KP_EW_MINB)
 bn_act_fwd_rows_k(View<TI> y, View<TO> out, const float* __restrict__ scale, const float* __restrict__ shift, int act,
                   int pad, int N, int H, int W, int C, int OH, int OW, int cg_shift, const BnFuse fuse) {
     using RawI = typename Vec<TI, V8>::Raw;
@@ -447,7 +453,7 @@ bn_act_fwd_rows_k(View<TI> y, View<TO> out, const float* __restrict__ scale, con
 // repeated and dy = scale (dz - mean(dz) - xhat mean(dz xhat)) is written directly, so dz never round-trips through HBM
 // (cheaper whenever d(out) is not larger than y: post = none / pool).
 template <typename TG, typename TY, typename TD, int POST, bool APPLY>
-__global__ void __launch_bounds__(256, 2)
+__global__ void __launch_bounds__(256, KP_EW_MINB)
 bn_act_bwd_rows_k(View<TG> dout, View<TY> y, View<TD> dy, const float* __restrict__ scale,
                   const float* __restrict__ shift, const float* __restrict__ mean, const float* __restrict__ invstd,
                   double* sums, double count, int act, int pad, int N, int H, int W, int C, int OH, int OW, int cg_shift) {
@@ -635,7 +641,7 @@ bn_act_bwd_rows_k(View<TG> dout, View<TY> y, View<TD> dy, const float* __restric
 
 // Backward pass 2 (BatchNorm only), in place: dy = scale * (dz - mean(dz) - xhat * mean(dz * xhat))
 template <typename TY, typename TD>
-__global__ void __launch_bounds__(256, 2)
+__global__ void __launch_bounds__(256, KP_EW_MINB)
 bn_bwd_apply_rows_k(View<TY> y, View<TD> dy, const float* __restrict__ scale, const float* __restrict__ mean,
                     const float* __restrict__ invstd, const double* __restrict__ sums, double count, int N, int H, int W,
                     int C, int cg_shift, float* dgamma, float* dbeta) {
@@ -715,7 +721,7 @@ __global__ void bn_bwd_apply_generic_k(View<TY> y, View<TD> dy, const float* __r
 __device__ __forceinline__ float actf(float z, float slope) { return fmaxf(z, slope * z); }
 
 template <typename TI, typename TO>
-__global__ void __launch_bounds__(256, 2)
+__global__ void __launch_bounds__(256, KP_EW_MINB)
 bn_act_fwd_up_quad_k(View<TI> y, View<TO> out, const float* __restrict__ scale, const float* __restrict__ shift,
                      float slope, int pad, int N, int H, int W, int C, int cg_shift, const BnFuse fuse) {
     // Outputs (2k, 2k+1) x (2j, 2j+1).  With src = r * dst, r = (H-1)/(2H-1): floor(r*2k) = k-1 (k >= 1) and
@@ -792,7 +798,7 @@ bn_act_fwd_up_quad_k(View<TI> y, View<TO> out, const float* __restrict__ scale, 
 }
 
 template <typename TG, typename TY, typename TD>
-__global__ void __launch_bounds__(256, 2)
+__global__ void __launch_bounds__(256, KP_EW_MINB)
 bn_act_bwd_up_k(View<TG> dout, View<TY> y, View<TD> dy, const float* __restrict__ scale,
                 const float* __restrict__ shift, const float* __restrict__ mean, const float* __restrict__ invstd,
                 double* sums, float slope, int pad, int N, int H, int W, int C, int cg_shift) {

@@ -12,7 +12,7 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'lib', 'libkeypoints_b200.so')
+LIB_PATH = os.environ.get('KP_LIB') or os.path.join(_HERE, 'lib', 'libkeypoints_b200.so')   # KP_LIB: experiment builds
 
 F32, BF16 = 0, 1
 ACT_NONE, ACT_LEAKY, ACT_RELU = 0, 1, 2
