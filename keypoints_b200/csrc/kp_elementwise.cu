@@ -4,6 +4,7 @@
 // channel per block for the reductions.
 #include "kp_common.cuh"
 #include <type_traits>
+#include <stdlib.h>
 
 namespace {
 
@@ -340,6 +341,16 @@ __device__ __forceinline__ void fused_affine(const BnFuse& f, int C, int c0, boo
         }
     }
 }
+
+#include "kp_bn_lean.cuh"
+#include "kp_bn_pipe.cuh"
+
+#define KP_ACT_SWITCH(actv_, CALL)                          \
+    do {                                                    \
+        if ((actv_) == KP_ACT_LEAKY) { CALL(KP_ACT_LEAKY); }  \
+        else if ((actv_) == KP_ACT_RELU) { CALL(KP_ACT_RELU); } \
+        else { CALL(KP_ACT_NONE); }                          \
+    } while (0)
 
 struct RowFold {   // rows / columns of a replicate-padded gradient that fold into one unpadded coordinate
     int n, v[3];
@@ -919,6 +930,32 @@ static bool fast_ok(int C, long long rows_px) {
     int ncg = C / 8;
     return ncg >= 1 && ncg <= 256 && (ncg & (ncg - 1)) == 0 && rows_px < (1LL << 31);
 }
+static bool lean_enabled() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("KP_BN_LEAN"); v = (e && e[0] == '0') ? 0 : 1; }
+    return v == 1;
+}
+static bool pipe_enabled() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("KP_BN_PIPE"); v = (e && e[0] == '0') ? 0 : 1; }
+    return v == 1;
+}
+// dense bf16 NHWC rows the bulk-async kernels can stream: pixel stride == C, 512-item chunks
+static bool pipe_view_ok(const kp_view* v, int C) { return v->dtype == KP_BF16 && v->sx == C && view_vec8_ok(v, C); }
+static bool pipe_shape_ok(int C, int W) {
+    if (C % 8) return false;
+    const int ncg = C / 8;
+    return (ncg & (ncg - 1)) == 0 && ncg <= 64 && ((long long)W * ncg) % pipe::IPC == 0;   // C <= 512 (PIPE_EXT)
+}
+template <typename K>
+static int pipe_attr(K kernel, int smem) {
+    KP_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    return KP_OK;
+}
+static int pipe_grid(long long units) {
+    const long long cap = 2LL * kp_sm_count();
+    return (int)(units < cap ? units : cap);
+}
 static int ilog2(int v) { int s = 0; while ((1 << s) < v) ++s; return s; }
 static int rows_grid(long long rows) {
     long long cap = (long long)kp_sm_count() * 8;
@@ -970,7 +1007,38 @@ static int bn_act_fwd_impl(kp_stream stream, const kp_view* y, const kp_view* ou
             BnFuse nofuse;
             nofuse.stats = nullptr;
             const BnFuse fz = fuse ? *fuse : nofuse;
-            if (vec && fast_ok(C, P * C)) {
+            if (pipe_enabled() && post == KP_POST_NONE && pipe_shape_ok(C, W) && pipe_view_ok(y, C) && pipe_view_ok(out, C)) {
+                const int cpr = (int)((long long)W * (C / 8) / pipe::IPC), sh = ilog2(C / 8);
+                const long long units = (long long)N * (H + 2 * pad) * cpr;
+                constexpr int smem = pipe_smem_bytes<PIPE_FWD_STAGE, PIPE_FWD_STAGES>();
+                cudaStream_t st = (cudaStream_t)stream;
+#define KP_FWDP(ACTV)                                                                                                  \
+    do {                                                                                                               \
+        int rc_ = pipe_attr(bn_fwd_none_pipe_k<ACTV>, smem);                                                           \
+        if (rc_) return rc_;                                                                                           \
+        bn_fwd_none_pipe_k<ACTV><<<pipe_grid(units), pipe::THREADS, smem, st>>>(                                       \
+            make_rows<const bf16>(y), make_rows<bf16>(out), scale, shift, pad, N, H, W, C, sh, cpr, fz);               \
+    } while (0)
+                KP_ACT_SWITCH(act, KP_FWDP);
+#undef KP_FWDP
+                if (fuse && fused_done) *fused_done = 1;
+            } else if (vec && fast_ok(C, P * C) && std::is_same<TI, TO>::value && lean_enabled() &&
+                (post == KP_POST_NONE || post == KP_POST_POOL)) {
+                const int g = rows_grid((long long)N * (OH + 2 * pad)), sh = ilog2(C / 8);
+                cudaStream_t st = (cudaStream_t)stream;
+#define KP_FWDL(ACTV)                                                                                                   \
+    do {                                                                                                                \
+        if (post == KP_POST_NONE)                                                                                       \
+            bn_fwd_lean_k<TI, KP_POST_NONE, ACTV><<<g, 256, 0, st>>>(make_rows<const TI>(y), make_rows<TI>(out), scale, \
+                                                                    shift, pad, N, H, W, C, OH, OW, sh, fz);            \
+        else                                                                                                            \
+            bn_fwd_lean_k<TI, KP_POST_POOL, ACTV><<<g, 256, 0, st>>>(make_rows<const TI>(y), make_rows<TI>(out), scale, \
+                                                                    shift, pad, N, H, W, C, OH, OW, sh, fz);            \
+    } while (0)
+                KP_ACT_SWITCH(act, KP_FWDL);
+#undef KP_FWDL
+                if (fuse && fused_done) *fused_done = 1;
+            } else if (vec && fast_ok(C, P * C)) {
                 const int g = rows_grid((long long)N * (OH + 2 * pad)), sh = ilog2(C / 8);
                 cudaStream_t st = (cudaStream_t)stream;
 #define KP_FWD(POSTV) bn_act_fwd_rows_k<TI, TO, POSTV><<<g, 256, 0, st>>>(make_view<TI>(y), make_view<TO>(out), scale, shift, act, pad, N, H, W, C, OH, OW, sh, fz)
@@ -1038,7 +1106,42 @@ extern "C" int kp_bn_act_bwd_reduce(kp_stream stream, const kp_view* dout, const
                 using TG = decltype(tg);
                 using TY = decltype(ty);
                 using TD = decltype(td);
-                if (vec && fast_ok(C, P * C)) {
+                if (pipe_enabled() && post == KP_POST_NONE && pipe_shape_ok(C, W) && pipe_view_ok(dout, C) &&
+                    pipe_view_ok(y, C) && dyv->ptr != nullptr && pipe_view_ok(dyv, C)) {
+                    const int cpr = (int)((long long)W * (C / 8) / pipe::IPC), sh = ilog2(C / 8);
+                    const long long units = (long long)N * H * cpr;
+                    constexpr int smem = pipe_smem_bytes<PIPE_BWD_STAGE, PIPE_BWD_STAGES>();
+                    cudaStream_t st = (cudaStream_t)stream;
+#define KP_BWDP(ACTV)                                                                                                  \
+    do {                                                                                                               \
+        int rc_ = pipe_attr(bn_bwd_none_pipe_k<ACTV>, smem);                                                           \
+        if (rc_) return rc_;                                                                                           \
+        bn_bwd_none_pipe_k<ACTV><<<pipe_grid(units), pipe::THREADS, smem, st>>>(                                       \
+            make_rows<const bf16>(dout), make_rows<const bf16>(y), make_rows<bf16>(dyv), scale, shift, mean, invstd,   \
+            sums, pad, N, H, W, C, sh, cpr);                                                                           \
+    } while (0)
+                    KP_ACT_SWITCH(act, KP_BWDP);
+#undef KP_BWDP
+                } else if (vec && fast_ok(C, P * C) && std::is_same<TG, TY>::value && std::is_same<TY, TD>::value &&
+                    lean_enabled() && (post == KP_POST_NONE || post == KP_POST_POOL)) {
+                    const long long rows = post == KP_POST_POOL ? (long long)N * ((H + 1) / 2) : (long long)N * H;
+                    const long long cap = 2LL * kp_sm_count();
+                    const int g = (int)(rows < cap ? rows : cap), sh = ilog2(C / 8);
+                    cudaStream_t st = (cudaStream_t)stream;
+#define KP_BWDL(ACTV)                                                                                                   \
+    do {                                                                                                                \
+        if (post == KP_POST_NONE)                                                                                       \
+            bn_bwd_lean_k<TY, KP_POST_NONE, ACTV, false><<<g, 256, 0, st>>>(                                            \
+                make_rows<const TY>(dout), make_rows<const TY>(y), make_rows<TY>(dyv), scale, shift, mean, invstd, sums, \
+                1.0, pad, N, H, W, C, OH, OW, sh);                                                                      \
+        else                                                                                                            \
+            bn_bwd_lean_k<TY, KP_POST_POOL, ACTV, false><<<g, 256, 0, st>>>(                                            \
+                make_rows<const TY>(dout), make_rows<const TY>(y), make_rows<TY>(dyv), scale, shift, mean, invstd, sums, \
+                1.0, pad, N, H, W, C, OH, OW, sh);                                                                      \
+    } while (0)
+                    KP_ACT_SWITCH(act, KP_BWDL);
+#undef KP_BWDL
+                } else if (vec && fast_ok(C, P * C)) {
                     const long long rows = post == KP_POST_POOL ? (long long)N * ((H + 1) / 2) : (long long)N * H;
                     // one resident wave (2 blocks / SM at 128 registers): every block ends with 2C double atomics
                     const long long cap = 2LL * kp_sm_count();
@@ -1123,7 +1226,16 @@ extern "C" int kp_bn_act_bwd_apply(kp_stream stream, const kp_view* y, const kp_
         return dispatch1(dy->dtype, [&](auto td) -> int {
             using TY = decltype(ty);
             using TD = decltype(td);
-            if (vec && fast_ok(C, P * C)) {
+            if (pipe_enabled() && pipe_shape_ok(C, W) && pipe_view_ok(y, C) && pipe_view_ok(dy, C)) {
+                const int cpr = (int)((long long)W * (C / 8) / pipe::IPC);
+                const long long units = (long long)N * H * cpr;
+                constexpr int smem = pipe_smem_bytes<PIPE_APPLY_STAGE, PIPE_APPLY_STAGES>();
+                int rc_ = pipe_attr(bn_bwd_apply_pipe_k, smem);
+                if (rc_) return rc_;
+                bn_bwd_apply_pipe_k<<<pipe_grid(units), pipe::THREADS, smem, st>>>(
+                    make_rows<const bf16>(y), make_rows<bf16>(dy), scale, mean, invstd, sums, count, N, H, W, C, ilog2(C / 8),
+                    cpr, dgamma, dbeta);
+            } else if (vec && fast_ok(C, P * C)) {
                 bn_bwd_apply_rows_k<TY, TD><<<rows_grid((long long)N * H), 256, 0, st>>>(
                     make_view<TY>(y), make_view<TD>(dy), scale, mean, invstd, sums, count, N, H, W, C, ilog2(C / 8), dgamma,
                     dbeta);
