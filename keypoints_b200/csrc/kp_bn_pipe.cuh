@@ -330,3 +330,180 @@ bn_bwd_apply_pipe_k(Rows<const bf16> y, Rows<bf16> dy, const float* __restrict__
     };
     pipe_run<PIPE_APPLY_STAGE, PIPE_APPLY_STAGES>(smem, units, H, cpr, issue, body);
 }
+
+// ------------------------------------------------------------------------------------------------
+// 2x2 max-pool variants.  A unit is one output row x 256 output items (pixel, channel group): the two source rows of
+// y arrive as 2 x 8 KB spans (the 2x2 windows of a run of output pixels are contiguous in each source row).
+// ------------------------------------------------------------------------------------------------
+constexpr int PIPE_POOL_ITEMS = 256;
+constexpr int PIPE_POOL_YBYTES = 2 * PIPE_POOL_ITEMS * 16;                  // one source row span
+constexpr int PIPE_FPOOL_STAGE = 2 * PIPE_POOL_YBYTES, PIPE_FPOOL_STAGES = 5;
+constexpr int PIPE_BPOOL_STAGE = 2 * PIPE_POOL_YBYTES + PIPE_POOL_ITEMS * 16 + 2 * PIPE_EXT, PIPE_BPOOL_STAGES = 4;
+
+// forward: out[py][px] = max over the window of act(scale * y + shift); H, W even; OH = H/2, OW = W/2
+template <int ACT>
+__global__ void __launch_bounds__(pipe::THREADS, 2)
+bn_fwd_pool_pipe_k(Rows<const bf16> y, Rows<bf16> out, const float* __restrict__ scale, const float* __restrict__ shift,
+                   int pad, int N, int OH, int OW, int C, int cg_shift, int cpr, const BnFuse fuse) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    const int tid = threadIdx.x;
+    const int ncg = C >> 3;
+    const int cg = tid & (ncg - 1), c0 = cg * 8;
+    float2 sc[4], sh[4];
+    if (tid < pipe::CONSUMERS) {
+        if (fuse.stats) {
+            float a[8], b[8];
+            fused_affine(fuse, C, c0, blockIdx.x == 0 && (tid >> cg_shift) == 0, a, b);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) { sc[i] = make_float2(a[2 * i], a[2 * i + 1]); sh[i] = make_float2(b[2 * i], b[2 * i + 1]); }
+        } else {
+            load_c8(scale, c0, 1.f, sc);
+            load_c8(shift, c0, 0.f, sh);
+        }
+    }
+    const int PH = OH + 2 * pad;
+    const int units = N * PH * cpr;
+    auto issue = [&](const Cursor& cu, uint32_t stage, uint32_t full) {
+        const int oy = min(max(cu.yy - pad, 0), OH - 1);
+        const bf16* r0 = y.row(cu.n, 2 * oy) + cu.ch * (2 * PIPE_POOL_ITEMS * 8);
+        pipe::mbar_expect_tx(full, 2 * PIPE_POOL_YBYTES);
+        pipe::bulk_g2s(stage, r0, PIPE_POOL_YBYTES, full);
+        pipe::bulk_g2s(stage + PIPE_POOL_YBYTES, r0 + y.sy, PIPE_POOL_YBYTES, full);
+    };
+    const int pl = tid >> cg_shift;                              // output pixel of this thread inside the chunk
+    const int yoff = ((2 * pl) << cg_shift | cg) * 16;           // its window's left pixel inside a source row span
+    auto body = [&](const Cursor& cu, const uint8_t* st) {
+        const uint4 r00 = pipe::lds16(st + yoff), r01 = pipe::lds16(st + yoff + ncg * 16);
+        const uint4 r10 = pipe::lds16(st + PIPE_POOL_YBYTES + yoff), r11 = pipe::lds16(st + PIPE_POOL_YBYTES + yoff + ncg * 16);
+        float2 v[4], a[4];
+        auto act8 = [&](const uint4& r, float2 (&o)[4]) {
+            P8<bf16>::up(r, o);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float2 z = fma2(o[i], sc[i], sh[i]);
+                o[i] = make_float2(actv<ACT>(z.x), actv<ACT>(z.y));
+            }
+        };
+        act8(r00, v);
+        act8(r01, a);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) v[i] = make_float2(fmaxf(v[i].x, a[i].x), fmaxf(v[i].y, a[i].y));
+        act8(r10, a);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) v[i] = make_float2(fmaxf(v[i].x, a[i].x), fmaxf(v[i].y, a[i].y));
+        act8(r11, a);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) v[i] = make_float2(fmaxf(v[i].x, a[i].x), fmaxf(v[i].y, a[i].y));
+        const int ox = cu.ch * (PIPE_POOL_ITEMS >> cg_shift) + pl;
+        bf16* dst = out.row(cu.n, cu.yy) + (ox + pad) * C + c0;
+        const uint4 o = make_uint4(P8<bf16>::pk(v[0]), P8<bf16>::pk(v[1]), P8<bf16>::pk(v[2]), P8<bf16>::pk(v[3]));
+        *reinterpret_cast<uint4*>(dst) = o;
+        if (pad) {
+            if (ox == 0) *reinterpret_cast<uint4*>(dst - C) = o;
+            if (ox == OW - 1) *reinterpret_cast<uint4*>(dst + C) = o;
+        }
+    };
+    pipe_run<PIPE_FPOOL_STAGE, PIPE_FPOOL_STAGES>(smem, units, PH, cpr, issue, body);
+}
+
+// backward pass 1: the gradient of a pooled pixel goes to the first maximum of its window (row-major), zeros elsewhere
+template <int ACT>
+__global__ void __launch_bounds__(pipe::THREADS, 2)
+bn_bwd_pool_pipe_k(Rows<const bf16> dout, Rows<const bf16> y, Rows<bf16> dy, const float* __restrict__ scale,
+                   const float* __restrict__ shift, const float* __restrict__ mean, const float* __restrict__ invstd,
+                   double* sums, int pad, int N, int OH, int OW, int C, int cg_shift, int cpr) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    const int tid = threadIdx.x;
+    const int ncg = C >> 3;
+    const int cg = tid & (ncg - 1), c0 = cg * 8;
+    float2 sc[4], sh[4], nmu[4], s1[4], s2[4];
+    load_c8(scale, c0, 1.f, sc);
+    load_c8(shift, c0, 0.f, sh);
+    load_c8(mean, c0, 0.f, nmu);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        nmu[i] = make_float2(-nmu[i].x, -nmu[i].y);
+        s1[i] = make_float2(0.f, 0.f); s2[i] = make_float2(0.f, 0.f);
+    }
+    const int units = N * OH * cpr;
+    const int ext = pad ? C * 2 : 0;
+    constexpr int DOFF = 2 * PIPE_POOL_YBYTES + PIPE_EXT;       // dout chunk inside the stage
+    auto issue = [&](const Cursor& cu, uint32_t stage, uint32_t full) {
+        const bf16* r0 = y.row(cu.n, 2 * cu.yy) + cu.ch * (2 * PIPE_POOL_ITEMS * 8);
+        const bf16* d = dout.row(cu.n, cu.yy + pad) + pad * dout.sx + cu.ch * (PIPE_POOL_ITEMS * 8);
+        pipe::mbar_expect_tx(full, 2 * PIPE_POOL_YBYTES + PIPE_POOL_ITEMS * 16 + 2 * ext);
+        pipe::bulk_g2s(stage, r0, PIPE_POOL_YBYTES, full);
+        pipe::bulk_g2s(stage + PIPE_POOL_YBYTES, r0 + y.sy, PIPE_POOL_YBYTES, full);
+        pipe::bulk_g2s(stage + DOFF - ext, reinterpret_cast<const uint8_t*>(d) - ext, PIPE_POOL_ITEMS * 16 + 2 * ext, full);
+    };
+    const int pl = tid >> cg_shift;
+    const int yoff = ((2 * pl) << cg_shift | cg) * 16;
+    auto body = [&](const Cursor& cu, const uint8_t* st) {
+        uint4 ry[4];
+        ry[0] = pipe::lds16(st + yoff); ry[1] = pipe::lds16(st + yoff + ncg * 16);
+        ry[2] = pipe::lds16(st + PIPE_POOL_YBYTES + yoff); ry[3] = pipe::lds16(st + PIPE_POOL_YBYTES + yoff + ncg * 16);
+        float2 t[4];
+        P8<bf16>::up(pipe::lds16(st + DOFF + tid * 16), t);
+        const int oy = cu.yy;
+        const int ox = cu.ch * (PIPE_POOL_ITEMS >> cg_shift) + pl;
+        if (pad) {
+            if (oy == 0 || oy == OH - 1) {
+                add_fold<bf16>(dout, cu.n, oy, ox, OH, OW, c0, t);
+            } else if (ox == 0 || ox == OW - 1) {
+                float2 e[4];
+                P8<bf16>::up(pipe::lds16(st + DOFF + tid * 16 + (ox == 0 ? -ext : ext)), e);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) t[i] = add2(t[i], e[i]);
+            }
+        }
+        float2 best[4];
+        int bi[8];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            float2 yq[4];
+            P8<bf16>::up(ry[q], yq);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float2 z = fma2(yq[i], sc[i], sh[i]);
+                const float ax = actv<ACT>(z.x), ay = actv<ACT>(z.y);
+                if (q == 0 || ax > best[i].x) { best[i].x = ax; bi[2 * i] = q; }
+                if (q == 0 || ay > best[i].y) { best[i].y = ay; bi[2 * i + 1] = q; }
+            }
+        }
+        bf16* o0 = dy.row(cu.n, 2 * oy) + (2 * ox) * C + c0;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            float2 g[4], yq[4];
+            P8<bf16>::up(ry[q], yq);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float2 z = fma2(yq[i], sc[i], sh[i]);
+                const float2 dz = make_float2(bi[2 * i] == q ? actg<ACT>(z.x, t[i].x) : 0.f,
+                                              bi[2 * i + 1] == q ? actg<ACT>(z.y, t[i].y) : 0.f);
+                g[i] = dz;
+                s1[i] = add2(s1[i], dz);
+                s2[i] = fma2(dz, add2(yq[i], nmu[i]), s2[i]);
+            }
+            P8<bf16>::st(o0 + (q >> 1) * dy.sy + (q & 1) * C, g);
+        }
+    };
+    pipe_run<PIPE_BPOOL_STAGE, PIPE_BPOOL_STAGES>(smem, units, OH, cpr, issue, body);
+    if (tid >= pipe::CONSUMERS) return;
+    pipe::consumer_sync();
+    float* red = reinterpret_cast<float*>(smem);
+    float2 is[4];
+    load_c8(invstd, c0, 1.f, is);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        red[tid * 8 + 2 * i] = s1[i].x; red[tid * 8 + 2 * i + 1] = s1[i].y;
+        red[2048 + tid * 8 + 2 * i] = s2[i].x * is[i].x; red[2048 + tid * 8 + 2 * i + 1] = s2[i].y * is[i].y;
+    }
+    pipe::consumer_sync();
+    for (int ch = tid; ch < C; ch += pipe::CONSUMERS) {
+        const int g8 = ch >> 3, i = ch & 7;
+        float a = 0.f, b = 0.f;
+        for (int t = g8; t < pipe::CONSUMERS; t += ncg) { a += red[t * 8 + i]; b += red[2048 + t * 8 + i]; }
+        atomicAdd(&sums[ch], (double)a);
+        atomicAdd(&sums[C + ch], (double)b);
+    }
+}

@@ -471,23 +471,43 @@ struct PackDesc {
     bf16* tc_d;
     long long cout, cin, ks, ci_pad;
 };
-__global__ void pack_weights_multi_k(const PackDesc* __restrict__ table) {
+// One block repacks 32 (co) x 32 (ci) x T tiles through shared memory so that the OIHW master weights are read in
+// contiguous runs of 32*T floats and every destination layout is written in contiguous 32-element segments.
+__global__ void __launch_bounds__(256)
+pack_weights_multi_k(const PackDesc* __restrict__ table) {
+    __shared__ float sm[32][32 * 9 + 1];
     const PackDesc d = table[blockIdx.y];
     const int T = (int)(d.ks * d.ks), Cout = (int)d.cout, Cin = (int)d.cin, ci_pad = (int)d.ci_pad;
-    const long long total = (long long)T * Cout * ci_pad;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        int ci = (int)(i % ci_pad);
-        long long r = i / ci_pad;
-        int co = (int)(r % Cout);
-        int t = (int)(r / Cout);
-        float v = ci < Cin ? d.w[((long long)co * Cin + ci) * T + t] : 0.f;
-        int tf = T - 1 - t;
-        if (ci < Cin) {
-            if (d.simt_f) d.simt_f[((long long)t * Cin + ci) * Cout + co] = v;
-            if (d.simt_d) d.simt_d[((long long)tf * Cout + co) * Cin + ci] = v;
+    const int tiles_ci = (ci_pad + 31) / 32, tiles = ((Cout + 31) / 32) * tiles_ci;
+    const int row = 32 * T;
+    for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+        const int co0 = (tile / tiles_ci) * 32, ci0 = (tile % tiles_ci) * 32;
+#pragma unroll 4
+        for (int idx = threadIdx.x; idx < 32 * row; idx += 256) {
+            const int r = idx / row, j = idx - r * row;
+            const int co = co0 + r, ci = ci0 + j / T;
+            sm[r][j] = (co < Cout && ci < Cin) ? d.w[((long long)co * Cin + ci0) * T + j] : 0.f;
         }
-        if (d.tc_f) d.tc_f[((long long)t * Cout + co) * ci_pad + ci] = __float2bfloat16_rn(v);
-        if (d.tc_d) d.tc_d[((long long)tf * ci_pad + ci) * Cout + co] = __float2bfloat16_rn(v);
+        __syncthreads();
+        for (int idx = threadIdx.x; idx < 1024 * T; idx += 256) {       // ci fastest: [t][co][ci] layouts
+            const int c = idx & 31, r = (idx >> 5) & 31, t = idx >> 10;
+            const int co = co0 + r, ci = ci0 + c, tf = T - 1 - t;
+            const float v = sm[r][c * T + t];
+            if (co < Cout && ci < ci_pad) {
+                if (d.tc_f) d.tc_f[((long long)t * Cout + co) * ci_pad + ci] = __float2bfloat16_rn(v);
+                if (d.simt_d && ci < Cin) d.simt_d[((long long)tf * Cout + co) * Cin + ci] = v;
+            }
+        }
+        for (int idx = threadIdx.x; idx < 1024 * T; idx += 256) {       // co fastest: [t][ci][co] layouts
+            const int r = idx & 31, c = (idx >> 5) & 31, t = idx >> 10;
+            const int co = co0 + r, ci = ci0 + c, tf = T - 1 - t;
+            const float v = sm[r][c * T + t];
+            if (co < Cout && ci < ci_pad) {
+                if (d.tc_d) d.tc_d[((long long)tf * ci_pad + ci) * Cout + co] = __float2bfloat16_rn(v);
+                if (d.simt_f && ci < Cin) d.simt_f[((long long)t * Cin + ci) * Cout + co] = v;
+            }
+        }
+        __syncthreads();
     }
 }
 
@@ -495,7 +515,7 @@ __global__ void pack_weights_multi_k(const PackDesc* __restrict__ table) {
 
 extern "C" int kp_pack_weights_multi(kp_stream stream, const void* table_dev, int n_layers) {
     KP_CHECK_ARG(table_dev && n_layers > 0 && n_layers <= 65535, "kp_pack_weights_multi: bad arguments");
-    dim3 grid((unsigned)(kp_sm_count() * 2), (unsigned)n_layers, 1);
+    dim3 grid(256u, (unsigned)n_layers, 1);
     pack_weights_multi_k<<<grid, 256, 0, (cudaStream_t)stream>>>((const PackDesc*)table_dev);
     KP_LAUNCH_CHECK();
     return KP_OK;

@@ -947,6 +947,11 @@ static bool pipe_shape_ok(int C, int W) {
     const int ncg = C / 8;
     return (ncg & (ncg - 1)) == 0 && ncg <= 64 && ((long long)W * ncg) % pipe::IPC == 0;   // C <= 512 (PIPE_EXT)
 }
+static bool pipe_pool_shape_ok(int C, int OW) {
+    if (C % 8) return false;
+    const int ncg = C / 8;
+    return (ncg & (ncg - 1)) == 0 && ncg <= 64 && ((long long)OW * ncg) % PIPE_POOL_ITEMS == 0;
+}
 template <typename K>
 static int pipe_attr(K kernel, int smem) {
     KP_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
@@ -1021,6 +1026,22 @@ static int bn_act_fwd_impl(kp_stream stream, const kp_view* y, const kp_view* ou
     } while (0)
                 KP_ACT_SWITCH(act, KP_FWDP);
 #undef KP_FWDP
+                if (fuse && fused_done) *fused_done = 1;
+            } else if (pipe_enabled() && post == KP_POST_POOL && H % 2 == 0 && W % 2 == 0 && pipe_pool_shape_ok(C, OW) &&
+                       pipe_view_ok(y, C) && pipe_view_ok(out, C)) {
+                const int cpr = (int)((long long)OW * (C / 8) / PIPE_POOL_ITEMS), sh = ilog2(C / 8);
+                const long long units = (long long)N * (OH + 2 * pad) * cpr;
+                constexpr int smem = pipe_smem_bytes<PIPE_FPOOL_STAGE, PIPE_FPOOL_STAGES>();
+                cudaStream_t st = (cudaStream_t)stream;
+#define KP_FWDPP(ACTV)                                                                                                 \
+    do {                                                                                                               \
+        int rc_ = pipe_attr(bn_fwd_pool_pipe_k<ACTV>, smem);                                                           \
+        if (rc_) return rc_;                                                                                           \
+        bn_fwd_pool_pipe_k<ACTV><<<pipe_grid(units), pipe::THREADS, smem, st>>>(                                       \
+            make_rows<const bf16>(y), make_rows<bf16>(out), scale, shift, pad, N, OH, OW, C, sh, cpr, fz);             \
+    } while (0)
+                KP_ACT_SWITCH(act, KP_FWDPP);
+#undef KP_FWDPP
                 if (fuse && fused_done) *fused_done = 1;
             } else if (vec && fast_ok(C, P * C) && std::is_same<TI, TO>::value && lean_enabled() &&
                 (post == KP_POST_NONE || post == KP_POST_POOL)) {
@@ -1122,6 +1143,22 @@ extern "C" int kp_bn_act_bwd_reduce(kp_stream stream, const kp_view* dout, const
     } while (0)
                     KP_ACT_SWITCH(act, KP_BWDP);
 #undef KP_BWDP
+                } else if (pipe_enabled() && post == KP_POST_POOL && H % 2 == 0 && W % 2 == 0 && pipe_pool_shape_ok(C, OW) &&
+                           pipe_view_ok(dout, C) && pipe_view_ok(y, C) && dyv->ptr != nullptr && pipe_view_ok(dyv, C)) {
+                    const int cpr = (int)((long long)OW * (C / 8) / PIPE_POOL_ITEMS), sh = ilog2(C / 8);
+                    const long long units = (long long)N * OH * cpr;
+                    constexpr int smem = pipe_smem_bytes<PIPE_BPOOL_STAGE, PIPE_BPOOL_STAGES>();
+                    cudaStream_t st = (cudaStream_t)stream;
+#define KP_BWDPP(ACTV)                                                                                                 \
+    do {                                                                                                               \
+        int rc_ = pipe_attr(bn_bwd_pool_pipe_k<ACTV>, smem);                                                           \
+        if (rc_) return rc_;                                                                                           \
+        bn_bwd_pool_pipe_k<ACTV><<<pipe_grid(units), pipe::THREADS, smem, st>>>(                                       \
+            make_rows<const bf16>(dout), make_rows<const bf16>(y), make_rows<bf16>(dyv), scale, shift, mean, invstd,   \
+            sums, pad, N, OH, OW, C, sh, cpr);                                                                         \
+    } while (0)
+                    KP_ACT_SWITCH(act, KP_BWDPP);
+#undef KP_BWDPP
                 } else if (vec && fast_ok(C, P * C) && std::is_same<TG, TY>::value && std::is_same<TY, TD>::value &&
                     lean_enabled() && (post == KP_POST_NONE || post == KP_POST_POOL)) {
                     const long long rows = post == KP_POST_POOL ? (long long)N * ((H + 1) / 2) : (long long)N * H;
