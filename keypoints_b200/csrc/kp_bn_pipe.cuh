@@ -179,23 +179,44 @@ bn_fwd_none_pipe_k(Rows<const bf16> y, Rows<bf16> out, const float* __restrict__
 // ------------------------------------------------------------------------------------------------
 // backward pass 1, post = none: dz = act'(z) * fold(dout) -> dy, per-channel sums of dz and dz * xhat
 // ------------------------------------------------------------------------------------------------
-template <int ACT>
+// MODE: PASS1_WRITE = sums + dz written to dy; PASS1_SUMS = sums only (dz is recomputed by pass 2);
+//       PASS2_GATHER = the gather is repeated and dy = scale (dz - mean(dz) - xhat mean(dz xhat)) is written, so dz never
+//       round-trips through HBM (10 instead of 12 bytes per element over the two passes).
+enum { PASS1_WRITE = 0, PASS1_SUMS = 1, PASS2_GATHER = 2 };
+
+// per-channel constants of the two backward passes; in PASS2_GATHER s1 / s2 hold -sc*mean(dz) / -sc*invstd*mean(dz*xhat)
+__device__ __forceinline__ void bwd_consts(int MODE, const float* scale, const float* shift, const float* mean,
+                                           const float* invstd, const double* sums, double count, int C, int c0,
+                                           float2 (&sc)[4], float2 (&sh)[4], float2 (&nmu)[4], float2 (&s1)[4], float2 (&s2)[4]) {
+    load_c8(scale, c0, 1.f, sc);
+    load_c8(shift, c0, 0.f, sh);
+    load_c8(mean, c0, 0.f, nmu);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        nmu[i] = make_float2(-nmu[i].x, -nmu[i].y);
+        if (MODE == PASS2_GATHER) {
+            const int c = c0 + 2 * i;
+            const float m1x = (float)(sums[c] / count), m1y = (float)(sums[c + 1] / count);
+            const float m2x = (float)(sums[C + c] / count), m2y = (float)(sums[C + c + 1] / count);
+            s1[i] = make_float2(-sc[i].x * m1x, -sc[i].y * m1y);
+            s2[i] = make_float2(-sc[i].x * invstd[c] * m2x, -sc[i].y * invstd[c + 1] * m2y);
+        } else {
+            s1[i] = make_float2(0.f, 0.f); s2[i] = make_float2(0.f, 0.f);
+        }
+    }
+}
+
+template <int ACT, int MODE>
 __global__ void __launch_bounds__(pipe::THREADS, 2)
 bn_bwd_none_pipe_k(Rows<const bf16> dout, Rows<const bf16> y, Rows<bf16> dy, const float* __restrict__ scale,
                    const float* __restrict__ shift, const float* __restrict__ mean, const float* __restrict__ invstd,
-                   double* sums, int pad, int N, int H, int W, int C, int cg_shift, int cpr) {
+                   double* sums, double count, int pad, int N, int H, int W, int C, int cg_shift, int cpr) {
     extern __shared__ __align__(128) uint8_t smem[];
     const int tid = threadIdx.x;
     const int ncg = C >> 3;
     const int c0 = (tid & (ncg - 1)) * 8;
     float2 sc[4], sh[4], nmu[4], s1[4], s2[4];
-    load_c8(scale, c0, 1.f, sc);
-    load_c8(shift, c0, 0.f, sh);
-    load_c8(mean, c0, 0.f, nmu);
-#pragma unroll
-    for (int i = 0; i < 4; ++i) nmu[i] = make_float2(-nmu[i].x, -nmu[i].y);
-#pragma unroll
-    for (int i = 0; i < 4; ++i) { s1[i] = make_float2(0.f, 0.f); s2[i] = make_float2(0.f, 0.f); }
+    bwd_consts(MODE, scale, shift, mean, invstd, sums, count, C, c0, sc, sh, nmu, s1, s2);
     const int units = N * H * cpr;
     // stage layout: [ext | dout chunk | ext | y chunk]; with a replicate-padded dout the chunk is loaded together with
     // the pixel before and after it, so the left / right border copies of the edge pixels come from shared memory
@@ -209,7 +230,7 @@ bn_bwd_none_pipe_k(Rows<const bf16> dout, Rows<const bf16> y, Rows<bf16> dy, con
     };
     auto body = [&](const Cursor& cu, const uint8_t* st) {
         const int n = cu.n, yy = cu.yy, ch = cu.ch;
-        bf16* orow = dy.row(n, yy);
+        bf16* orow = MODE == PASS1_SUMS ? nullptr : dy.row(n, yy);
         const bool rowb = pad && (yy == 0 || yy == H - 1);
         const uint8_t* sd = st + PIPE_EXT;
         const uint8_t* sy = st + 2 * PIPE_EXT + pipe::CHUNK_BYTES;
@@ -247,15 +268,19 @@ bn_bwd_none_pipe_k(Rows<const bf16> dout, Rows<const bf16> y, Rows<bf16> dy, con
                 const float2 z = fma2(yv[i], sc[i], sh[i]);
                 const float2 dz = make_float2(actg<ACT>(z.x, g[i].x), actg<ACT>(z.y, g[i].y));
                 const float2 yc = add2(yv[i], nmu[i]);
-                g[i] = dz;
-                s1[i] = add2(s1[i], dz);
-                s2[i] = fma2(dz, yc, s2[i]);
+                if (MODE == PASS2_GATHER) {
+                    g[i] = fma2(sc[i], dz, fma2(s2[i], yc, s1[i]));
+                } else {
+                    g[i] = dz;
+                    s1[i] = add2(s1[i], dz);
+                    s2[i] = fma2(dz, yc, s2[i]);
+                }
             }
-            P8<bf16>::st(orow + e, g);
+            if (MODE != PASS1_SUMS) P8<bf16>::st(orow + e, g);
         }
     };
     pipe_run<PIPE_BWD_STAGE, PIPE_BWD_STAGES>(smem, units, H, cpr, issue, body);
-    if (tid >= pipe::CONSUMERS) return;
+    if (tid >= pipe::CONSUMERS || MODE == PASS2_GATHER) return;
     // every unit of this CTA has been consumed: the ring is free, reuse it for the block reduction
     pipe::consumer_sync();
     float* red = reinterpret_cast<float*>(smem);               // [2][256 * 8]
@@ -407,24 +432,17 @@ bn_fwd_pool_pipe_k(Rows<const bf16> y, Rows<bf16> out, const float* __restrict__
 }
 
 // backward pass 1: the gradient of a pooled pixel goes to the first maximum of its window (row-major), zeros elsewhere
-template <int ACT>
+template <int ACT, int MODE>
 __global__ void __launch_bounds__(pipe::THREADS, 2)
 bn_bwd_pool_pipe_k(Rows<const bf16> dout, Rows<const bf16> y, Rows<bf16> dy, const float* __restrict__ scale,
                    const float* __restrict__ shift, const float* __restrict__ mean, const float* __restrict__ invstd,
-                   double* sums, int pad, int N, int OH, int OW, int C, int cg_shift, int cpr) {
+                   double* sums, double count, int pad, int N, int OH, int OW, int C, int cg_shift, int cpr) {
     extern __shared__ __align__(128) uint8_t smem[];
     const int tid = threadIdx.x;
     const int ncg = C >> 3;
     const int cg = tid & (ncg - 1), c0 = cg * 8;
     float2 sc[4], sh[4], nmu[4], s1[4], s2[4];
-    load_c8(scale, c0, 1.f, sc);
-    load_c8(shift, c0, 0.f, sh);
-    load_c8(mean, c0, 0.f, nmu);
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        nmu[i] = make_float2(-nmu[i].x, -nmu[i].y);
-        s1[i] = make_float2(0.f, 0.f); s2[i] = make_float2(0.f, 0.f);
-    }
+    bwd_consts(MODE, scale, shift, mean, invstd, sums, count, C, c0, sc, sh, nmu, s1, s2);
     const int units = N * OH * cpr;
     const int ext = pad ? C * 2 : 0;
     constexpr int DOFF = 2 * PIPE_POOL_YBYTES + PIPE_EXT;       // dout chunk inside the stage
@@ -470,7 +488,7 @@ bn_bwd_pool_pipe_k(Rows<const bf16> dout, Rows<const bf16> y, Rows<bf16> dy, con
                 if (q == 0 || ay > best[i].y) { best[i].y = ay; bi[2 * i + 1] = q; }
             }
         }
-        bf16* o0 = dy.row(cu.n, 2 * oy) + (2 * ox) * C + c0;
+        bf16* o0 = MODE == PASS1_SUMS ? nullptr : dy.row(cu.n, 2 * oy) + (2 * ox) * C + c0;
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
             float2 g[4], yq[4];
@@ -480,15 +498,20 @@ bn_bwd_pool_pipe_k(Rows<const bf16> dout, Rows<const bf16> y, Rows<bf16> dy, con
                 const float2 z = fma2(yq[i], sc[i], sh[i]);
                 const float2 dz = make_float2(bi[2 * i] == q ? actg<ACT>(z.x, t[i].x) : 0.f,
                                               bi[2 * i + 1] == q ? actg<ACT>(z.y, t[i].y) : 0.f);
-                g[i] = dz;
-                s1[i] = add2(s1[i], dz);
-                s2[i] = fma2(dz, add2(yq[i], nmu[i]), s2[i]);
+                const float2 yc = add2(yq[i], nmu[i]);
+                if (MODE == PASS2_GATHER) {
+                    g[i] = fma2(sc[i], dz, fma2(s2[i], yc, s1[i]));
+                } else {
+                    g[i] = dz;
+                    s1[i] = add2(s1[i], dz);
+                    s2[i] = fma2(dz, yc, s2[i]);
+                }
             }
-            P8<bf16>::st(o0 + (q >> 1) * dy.sy + (q & 1) * C, g);
+            if (MODE != PASS1_SUMS) P8<bf16>::st(o0 + (q >> 1) * dy.sy + (q & 1) * C, g);
         }
     };
     pipe_run<PIPE_BPOOL_STAGE, PIPE_BPOOL_STAGES>(smem, units, OH, cpr, issue, body);
-    if (tid >= pipe::CONSUMERS) return;
+    if (tid >= pipe::CONSUMERS || MODE == PASS2_GATHER) return;
     pipe::consumer_sync();
     float* red = reinterpret_cast<float*>(smem);
     float2 is[4];

@@ -1128,34 +1128,50 @@ extern "C" int kp_bn_act_bwd_reduce(kp_stream stream, const kp_view* dout, const
                 using TY = decltype(ty);
                 using TD = decltype(td);
                 if (pipe_enabled() && post == KP_POST_NONE && pipe_shape_ok(C, W) && pipe_view_ok(dout, C) &&
-                    pipe_view_ok(y, C) && dyv->ptr != nullptr && pipe_view_ok(dyv, C)) {
+                    pipe_view_ok(y, C) && (dyv->ptr == nullptr || pipe_view_ok(dyv, C))) {
                     const int cpr = (int)((long long)W * (C / 8) / pipe::IPC), sh = ilog2(C / 8);
                     const long long units = (long long)N * H * cpr;
                     constexpr int smem = pipe_smem_bytes<PIPE_BWD_STAGE, PIPE_BWD_STAGES>();
                     cudaStream_t st = (cudaStream_t)stream;
 #define KP_BWDP(ACTV)                                                                                                  \
     do {                                                                                                               \
-        int rc_ = pipe_attr(bn_bwd_none_pipe_k<ACTV>, smem);                                                           \
-        if (rc_) return rc_;                                                                                           \
-        bn_bwd_none_pipe_k<ACTV><<<pipe_grid(units), pipe::THREADS, smem, st>>>(                                       \
-            make_rows<const bf16>(dout), make_rows<const bf16>(y), make_rows<bf16>(dyv), scale, shift, mean, invstd,   \
-            sums, pad, N, H, W, C, sh, cpr);                                                                           \
+        if (dyv->ptr) {                                                                                                \
+            int rc_ = pipe_attr(bn_bwd_none_pipe_k<ACTV, PASS1_WRITE>, smem);                                          \
+            if (rc_) return rc_;                                                                                       \
+            bn_bwd_none_pipe_k<ACTV, PASS1_WRITE><<<pipe_grid(units), pipe::THREADS, smem, st>>>(                      \
+                make_rows<const bf16>(dout), make_rows<const bf16>(y), make_rows<bf16>(dyv), scale, shift, mean,       \
+                invstd, sums, 1.0, pad, N, H, W, C, sh, cpr);                                                          \
+        } else {                                                                                                       \
+            int rc_ = pipe_attr(bn_bwd_none_pipe_k<ACTV, PASS1_SUMS>, smem);                                           \
+            if (rc_) return rc_;                                                                                       \
+            bn_bwd_none_pipe_k<ACTV, PASS1_SUMS><<<pipe_grid(units), pipe::THREADS, smem, st>>>(                       \
+                make_rows<const bf16>(dout), make_rows<const bf16>(y), make_rows<bf16>(dyv), scale, shift, mean,       \
+                invstd, sums, 1.0, pad, N, H, W, C, sh, cpr);                                                          \
+        }                                                                                                              \
     } while (0)
                     KP_ACT_SWITCH(act, KP_BWDP);
 #undef KP_BWDP
                 } else if (pipe_enabled() && post == KP_POST_POOL && H % 2 == 0 && W % 2 == 0 && pipe_pool_shape_ok(C, OW) &&
-                           pipe_view_ok(dout, C) && pipe_view_ok(y, C) && dyv->ptr != nullptr && pipe_view_ok(dyv, C)) {
+                           pipe_view_ok(dout, C) && pipe_view_ok(y, C) && (dyv->ptr == nullptr || pipe_view_ok(dyv, C))) {
                     const int cpr = (int)((long long)OW * (C / 8) / PIPE_POOL_ITEMS), sh = ilog2(C / 8);
                     const long long units = (long long)N * OH * cpr;
                     constexpr int smem = pipe_smem_bytes<PIPE_BPOOL_STAGE, PIPE_BPOOL_STAGES>();
                     cudaStream_t st = (cudaStream_t)stream;
 #define KP_BWDPP(ACTV)                                                                                                 \
     do {                                                                                                               \
-        int rc_ = pipe_attr(bn_bwd_pool_pipe_k<ACTV>, smem);                                                           \
-        if (rc_) return rc_;                                                                                           \
-        bn_bwd_pool_pipe_k<ACTV><<<pipe_grid(units), pipe::THREADS, smem, st>>>(                                       \
-            make_rows<const bf16>(dout), make_rows<const bf16>(y), make_rows<bf16>(dyv), scale, shift, mean, invstd,   \
-            sums, pad, N, OH, OW, C, sh, cpr);                                                                         \
+        if (dyv->ptr) {                                                                                                \
+            int rc_ = pipe_attr(bn_bwd_pool_pipe_k<ACTV, PASS1_WRITE>, smem);                                          \
+            if (rc_) return rc_;                                                                                       \
+            bn_bwd_pool_pipe_k<ACTV, PASS1_WRITE><<<pipe_grid(units), pipe::THREADS, smem, st>>>(                      \
+                make_rows<const bf16>(dout), make_rows<const bf16>(y), make_rows<bf16>(dyv), scale, shift, mean,       \
+                invstd, sums, 1.0, pad, N, OH, OW, C, sh, cpr);                                                        \
+        } else {                                                                                                       \
+            int rc_ = pipe_attr(bn_bwd_pool_pipe_k<ACTV, PASS1_SUMS>, smem);                                           \
+            if (rc_) return rc_;                                                                                       \
+            bn_bwd_pool_pipe_k<ACTV, PASS1_SUMS><<<pipe_grid(units), pipe::THREADS, smem, st>>>(                       \
+                make_rows<const bf16>(dout), make_rows<const bf16>(y), make_rows<bf16>(dyv), scale, shift, mean,       \
+                invstd, sums, 1.0, pad, N, OH, OW, C, sh, cpr);                                                        \
+        }                                                                                                              \
     } while (0)
                     KP_ACT_SWITCH(act, KP_BWDPP);
 #undef KP_BWDPP
@@ -1225,6 +1241,43 @@ extern "C" int kp_bn_act_bwd_apply_gather(kp_stream stream, const kp_view* dout,
     const long long rows = post == KP_POST_POOL ? (long long)N * ((H + 1) / 2) : (long long)N * H;
     const int g = rows_grid(rows), sh = ilog2(C / 8);
     cudaStream_t st = (cudaStream_t)stream;
+    const bool views_ok = pipe_view_ok(dout, C) && pipe_view_ok(y, C) && pipe_view_ok(dy, C);
+    if (pipe_enabled() && views_ok && post == KP_POST_NONE && pipe_shape_ok(C, W)) {
+        const int cpr = (int)((long long)W * (C / 8) / pipe::IPC);
+        const long long units = (long long)N * H * cpr;
+        constexpr int smem = pipe_smem_bytes<PIPE_BWD_STAGE, PIPE_BWD_STAGES>();
+#define KP_GATHN(ACTV)                                                                                                 \
+    do {                                                                                                               \
+        int rc_ = pipe_attr(bn_bwd_none_pipe_k<ACTV, PASS2_GATHER>, smem);                                             \
+        if (rc_) return rc_;                                                                                           \
+        bn_bwd_none_pipe_k<ACTV, PASS2_GATHER><<<pipe_grid(units), pipe::THREADS, smem, st>>>(                         \
+            make_rows<const bf16>(dout), make_rows<const bf16>(y), make_rows<bf16>(dy), scale, shift, mean, invstd,    \
+            const_cast<double*>(sums), count, pad, N, H, W, C, sh, cpr);                                               \
+    } while (0)
+        KP_ACT_SWITCH(act, KP_GATHN);
+#undef KP_GATHN
+        if (dgamma || dbeta) bn_grad_finalize_k<<<(C + 127) / 128, 128, 0, st>>>(sums, C, dgamma, dbeta);
+        KP_LAUNCH_CHECK();
+        return KP_OK;
+    }
+    if (pipe_enabled() && views_ok && post == KP_POST_POOL && H % 2 == 0 && W % 2 == 0 && pipe_pool_shape_ok(C, OW)) {
+        const int cpr = (int)((long long)OW * (C / 8) / PIPE_POOL_ITEMS);
+        const long long units = (long long)N * OH * cpr;
+        constexpr int smem = pipe_smem_bytes<PIPE_BPOOL_STAGE, PIPE_BPOOL_STAGES>();
+#define KP_GATHP(ACTV)                                                                                                 \
+    do {                                                                                                               \
+        int rc_ = pipe_attr(bn_bwd_pool_pipe_k<ACTV, PASS2_GATHER>, smem);                                             \
+        if (rc_) return rc_;                                                                                           \
+        bn_bwd_pool_pipe_k<ACTV, PASS2_GATHER><<<pipe_grid(units), pipe::THREADS, smem, st>>>(                         \
+            make_rows<const bf16>(dout), make_rows<const bf16>(y), make_rows<bf16>(dy), scale, shift, mean, invstd,    \
+            const_cast<double*>(sums), count, pad, N, OH, OW, C, sh, cpr);                                             \
+    } while (0)
+        KP_ACT_SWITCH(act, KP_GATHP);
+#undef KP_GATHP
+        if (dgamma || dbeta) bn_grad_finalize_k<<<(C + 127) / 128, 128, 0, st>>>(sums, C, dgamma, dbeta);
+        KP_LAUNCH_CHECK();
+        return KP_OK;
+    }
     int rc = dispatch1(dout->dtype, [&](auto tg) -> int {
         return dispatch1(y->dtype, [&](auto ty) -> int {
             return dispatch1(dy->dtype, [&](auto td) -> int {

@@ -21,8 +21,21 @@ from . import lib as L
 import os
 
 BN_EPS = 1e-5
-REGATHER = os.environ.get('KP_BN_REGATHER', '0') != '0'     # measured slower than the dz round trip
+REGATHER = os.environ.get('KP_BN_REGATHER', '1') != '0'     # BN backward pass 2 recomputes dz instead of reading it back
 REGATHER_POSTS = tuple(os.environ.get('KP_BN_REGATHER_POSTS', 'none,pool').split(','))
+
+
+def regather_ok(s, h: int, w: int, dout: torch.Tensor, precision: str) -> bool:
+    """True when both BatchNorm backward passes of this layer run as bulk-async streaming kernels (kp_bn_pipe.cuh:
+    bf16, dense rows, whole 512-item chunks); only then is repeating the gather cheaper than the dz round trip."""
+    if not (REGATHER and precision == 'bf16' and s.post in REGATHER_POSTS and s.cout % 8 == 0):
+        return False
+    ncg = s.cout // 8
+    if ncg & (ncg - 1) or ncg > 64 or dout.dtype != torch.bfloat16 or dout.stride(3) != 1 or dout.stride(2) != s.cout:
+        return False
+    if s.post == 'none':
+        return (w * ncg) % 512 == 0
+    return h % 2 == 0 and w % 2 == 0 and ((w // 2) * ncg) % 256 == 0
 BN_MOMENTUM = 0.1
 
 
@@ -264,9 +277,7 @@ def unit_backward(specs: List[ConvSpec], params: List[LayerParams], grads: List[
             if c.mean is None:
                 raise NotImplementedError('backward through eval-mode BatchNorm is not supported')
             ltag = f'{tag}{i} {s.cin}->{s.cout}@{h}x{w} {s.post}'
-            ncg = s.cout // 8
-            regather = (REGATHER and precision == 'bf16' and s.post in REGATHER_POSTS and s.cout % 8 == 0 and ncg & (ncg - 1) == 0
-                        and ncg <= 256 and dout.stride(3) == 1 and dout.dtype == torch.bfloat16)
+            regather = regather_ok(s, h, w, dout, precision)
             L.call('kp_bn_act_bwd_reduce', st, L.view(dout), L.view(yv), None if regather else L.view(dy_int), L.ptr(c.scale),
                    L.ptr(c.shift), L.ptr(c.mean), L.ptr(c.invstd), L.ptr(sums), a, po, dout_pad, N, h, w, s.cout, tag=ltag)
             if regather:     # pass 2 repeats the (cheap) gather instead of reading dz back
