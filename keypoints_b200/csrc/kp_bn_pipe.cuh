@@ -530,3 +530,303 @@ bn_bwd_pool_pipe_k(Rows<const bf16> dout, Rows<const bf16> y, Rows<bf16> dy, con
         atomicAdd(&sums[C + ch], (double)b);
     }
 }
+
+// ------------------------------------------------------------------------------------------------
+// Bilinear x2 (align_corners=True) variants.  Every output row blends two input rows, so a CTA walks DOWN a strip
+// (image, band of input rows, 256-item column chunk): input rows stream through the ring once, each consumer thread owns
+// one (pixel, channel group) column of the strip and carries the horizontally interpolated rows it still needs in
+// registers - no re-reads, no shared-memory round trip for intermediates, no block barriers.
+// ------------------------------------------------------------------------------------------------
+constexpr int PIPE_UP_ITEMS = 256;
+constexpr int PIPE_UP_BAND = 16;                                            // input rows per strip
+constexpr int PIPE_FUP_STAGE = PIPE_UP_ITEMS * 16 + 2 * PIPE_EXT, PIPE_FUP_STAGES = 8;
+
+struct Strip {
+    int n, k0, k1, ch;
+    __device__ __forceinline__ void set(int t, int cpr, int nbands, int H) {
+        ch = t % cpr;
+        const int q = t / cpr;
+        const int band = q % nbands;
+        n = q / nbands;
+        k0 = band * PIPE_UP_BAND;
+        k1 = min(k0 + PIPE_UP_BAND, H);
+    }
+};
+
+// forward: out(2k+a, 2j+b) from the activated 3x3 neighbourhood of input pixel (k, j); fractions as PyTorch computes them
+template <int ACT>
+__global__ void __launch_bounds__(pipe::THREADS, 2)
+bn_fwd_up_pipe_k(Rows<const bf16> y, Rows<bf16> out, const float* __restrict__ scale, const float* __restrict__ shift,
+                 int pad, int N, int H, int W, int C, int cg_shift, int cpr, const BnFuse fuse) {
+    using namespace pipe;
+    extern __shared__ __align__(128) uint8_t smem[];
+    constexpr int STAGES = PIPE_FUP_STAGES, STAGE_BYTES = PIPE_FUP_STAGE;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint32_t bars = s32(smem + STAGES * STAGE_BYTES);
+    if (tid == 0) {
+        for (int s = 0; s < STAGES; ++s) { mbar_init(bars + 8 * s, 1); mbar_init(bars + 8 * (STAGES + s), CONSUMERS / 32); }
+        fence_init();
+    }
+    __syncthreads();
+    const int nbands = (H + PIPE_UP_BAND - 1) / PIPE_UP_BAND;
+    const int nstrips = N * nbands * cpr;
+    const int ext = C * 2;
+    if (warp == CONSUMERS / 32) {
+        if (lane == 0) {
+            int s = 0, ph = 0;
+            for (int t = blockIdx.x; t < nstrips; t += gridDim.x) {
+                Strip sp;
+                sp.set(t, cpr, nbands, H);
+                const int rs = max(sp.k0 - 1, 0), re = min(sp.k1, H - 1);
+                for (int r = rs; r <= re; ++r) {
+                    mbar_wait(bars + 8 * (STAGES + s), ph ^ 1);
+                    const uint32_t full = bars + 8 * s, stage = s32(smem + s * STAGE_BYTES);
+                    const uint8_t* src = reinterpret_cast<const uint8_t*>(y.row(sp.n, r) + sp.ch * (PIPE_UP_ITEMS * 8));
+                    const int lh = sp.ch == 0 ? 0 : ext;          // no left halo at the start of a row (it may lie before the buffer)
+                    mbar_expect_tx(full, PIPE_UP_ITEMS * 16 + ext + lh);
+                    bulk_g2s(stage + PIPE_EXT - lh, src - lh, PIPE_UP_ITEMS * 16 + ext + lh, full);
+                    if (++s == STAGES) { s = 0; ph ^= 1; }
+                }
+            }
+        }
+        return;
+    }
+    const int ncg = C >> 3;
+    const int cg = tid & (ncg - 1), c0 = cg * 8;
+    const int pl = tid >> cg_shift;
+    float2 sc[4], sh[4];
+    if (fuse.stats) {
+        float a[8], b[8];
+        fused_affine(fuse, C, c0, blockIdx.x == 0 && pl == 0, a, b);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { sc[i] = make_float2(a[2 * i], a[2 * i + 1]); sh[i] = make_float2(b[2 * i], b[2 * i + 1]); }
+    } else {
+        load_c8(scale, c0, 1.f, sc);
+        load_c8(shift, c0, 0.f, sh);
+    }
+    const int OH = 2 * H, OW = 2 * W;
+    const float ry = (float)(H - 1) / (float)(OH - 1), rx = (float)(W - 1) / (float)(OW - 1);
+    auto act8 = [&](const uint4& r, float2 (&o)[4]) {
+        P8<bf16>::up(r, o);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const float2 z = fma2(o[i], sc[i], sh[i]);
+            o[i] = make_float2(actv<ACT>(z.x), actv<ACT>(z.y));
+        }
+    };
+    auto lerp8 = [&](const float2 (&a)[4], const float2 (&b)[4], float l, float2 (&o)[4]) {
+        const float2 l2 = make_float2(l, l);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) o[i] = fma2(l2, sub2(b[i], a[i]), a[i]);
+    };
+    int s = 0, ph = 0;
+    for (int t = blockIdx.x; t < nstrips; t += gridDim.x) {
+        Strip sp;
+        sp.set(t, cpr, nbands, H);
+        const int j = sp.ch * (PIPE_UP_ITEMS >> cg_shift) + pl;              // input pixel column of this thread
+        const int offL = j == 0 ? 0 : -ext, offR = j == W - 1 ? 0 : ext;
+        const float lx0 = j > 0 ? fminf(fmaxf(rx * (float)(2 * j) - (float)(j - 1), 0.f), 1.f) : 0.f;
+        const float lx1 = fminf(fmaxf(rx * (float)(2 * j + 1) - (float)j, 0.f), 1.f);
+        bf16* obase = out.row(sp.n, 0) + (2 * j + pad) * C + c0;
+        // h[parity][8 channels] of the two previous input rows
+        float2 hA0[4], hA1[4], hB0[4], hB1[4];
+        auto emit = [&](int k, const float2 (&a0)[4], const float2 (&a1)[4], const float2 (&b0)[4], const float2 (&b1)[4],
+                        const float2 (&c0v)[4], const float2 (&c1v)[4]) {
+            const float ly0 = k > 0 ? fminf(fmaxf(ry * (float)(2 * k) - (float)(k - 1), 0.f), 1.f) : 0.f;
+            const float ly1 = fminf(fmaxf(ry * (float)(2 * k + 1) - (float)k, 0.f), 1.f);
+#pragma unroll
+            for (int a = 0; a < 2; ++a) {
+                float2 o0[4], o1[4];
+                if (a == 0) { lerp8(a0, b0, ly0, o0); lerp8(a1, b1, ly0, o1); }
+                else { lerp8(b0, c0v, ly1, o0); lerp8(b1, c1v, ly1, o1); }
+                const uint4 u0 = make_uint4(P8<bf16>::pk(o0[0]), P8<bf16>::pk(o0[1]), P8<bf16>::pk(o0[2]), P8<bf16>::pk(o0[3]));
+                const uint4 u1 = make_uint4(P8<bf16>::pk(o1[0]), P8<bf16>::pk(o1[1]), P8<bf16>::pk(o1[2]), P8<bf16>::pk(o1[3]));
+                const int oy = 2 * k + a;
+                bf16* p = obase + (long long)(oy + pad) * out.sy;
+                auto put = [&](bf16* q) {
+                    *reinterpret_cast<uint4*>(q) = u0;
+                    *reinterpret_cast<uint4*>(q + C) = u1;
+                    if (pad) {
+                        if (j == 0) *reinterpret_cast<uint4*>(q - C) = u0;
+                        if (j == W - 1) *reinterpret_cast<uint4*>(q + 2 * C) = u1;
+                    }
+                };
+                put(p);
+                if (pad) {
+                    if (oy == 0) put(p - out.sy);
+                    if (oy == OH - 1) put(p + out.sy);
+                }
+            }
+        };
+        const int rs = max(sp.k0 - 1, 0), re = min(sp.k1, H - 1);
+        for (int r = rs; r <= re; ++r) {
+            mbar_wait(bars + 8 * s, ph);
+            const uint8_t* st = smem + s * STAGE_BYTES + PIPE_EXT + tid * 16;
+            const uint4 rl = lds16(st + offL), rc = lds16(st), rr = lds16(st + offR);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bars + 8 * (STAGES + s));
+            if (++s == STAGES) { s = 0; ph ^= 1; }
+            float2 al[4], ac[4], ar[4], hC0[4], hC1[4];
+            act8(rl, al); act8(rc, ac); act8(rr, ar);
+            lerp8(al, ac, lx0, hC0);
+            lerp8(ac, ar, lx1, hC1);
+            if (r == rs) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) { hA0[i] = hC0[i]; hA1[i] = hC1[i]; hB0[i] = hC0[i]; hB1[i] = hC1[i]; }
+                if (!(H == 1)) continue;
+            }
+            // rows (r-2 | r-1 | r) are in (hA | hB | hC): emit the output pair of input row r-1 if this strip owns it
+            if (r - 1 >= sp.k0 && r - 1 < sp.k1 && r >= 1) emit(r - 1, hA0, hA1, hB0, hB1, hC0, hC1);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) { hA0[i] = hB0[i]; hA1[i] = hB1[i]; hB0[i] = hC0[i]; hB1[i] = hC1[i]; }
+            if (r == H - 1 && r >= sp.k0 && r < sp.k1) emit(r, hA0, hA1, hB0, hB1, hB0, hB1);     // last row: (H-2 | H-1 | H-1)
+        }
+    }
+}
+
+// backward pass 1 of the x2 bilinear layers (replicate-padded dout only).  Input pixel (k, j) receives from the 4x4 output
+// pixels (2k-1..2k+2, 2j-1..2j+2), i.e. PADDED rows 2k..2k+3 and PADDED columns 2j..2j+3 of dout; the border rows / columns
+// of the padding fold into the first / last output row / column, which only changes the tap weight (never the address).
+// A strip streams padded dout rows in pairs (2k+2, 2k+3) together with y row k; the horizontally gathered rows 2k, 2k+1
+// are carried in registers from the previous step.
+constexpr int PIPE_BUP_DROW = 2 * PIPE_UP_ITEMS * 16 + 2 * PIPE_EXT;        // one padded dout row span (+2 pixels)
+constexpr int PIPE_BUP_STAGE = 2 * PIPE_BUP_DROW + PIPE_UP_ITEMS * 16, PIPE_BUP_STAGES = 4;
+
+__device__ __forceinline__ float up_weight(int i, int O, float r, int n_in, int n_out) {
+    if (O < 0 || O >= n_out) return 0.f;
+    const float s = r * (float)O;
+    const int t = (int)s;
+    const float l = s - (float)t;
+    const int tb = min(t + 1, n_in - 1);
+    return (t == i ? 1.f - l : 0.f) + (tb == i ? l : 0.f);
+}
+
+template <int ACT>
+__global__ void __launch_bounds__(pipe::THREADS, 2)
+bn_bwd_up_pipe_k(Rows<const bf16> dout, Rows<const bf16> y, Rows<bf16> dy, const float* __restrict__ scale,
+                 const float* __restrict__ shift, const float* __restrict__ mean, const float* __restrict__ invstd,
+                 double* sums, int N, int H, int W, int C, int cg_shift, int cpr) {
+    using namespace pipe;
+    extern __shared__ __align__(128) uint8_t smem[];
+    constexpr int STAGES = PIPE_BUP_STAGES, STAGE_BYTES = PIPE_BUP_STAGE;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint32_t bars = s32(smem + STAGES * STAGE_BYTES);
+    if (tid == 0) {
+        for (int s = 0; s < STAGES; ++s) { mbar_init(bars + 8 * s, 1); mbar_init(bars + 8 * (STAGES + s), CONSUMERS / 32); }
+        fence_init();
+    }
+    __syncthreads();
+    const int nbands = (H + PIPE_UP_BAND - 1) / PIPE_UP_BAND;
+    const int nstrips = N * nbands * cpr;
+    const int ext = C * 2;                                        // bytes of one pixel
+    const int drow_bytes = 2 * PIPE_UP_ITEMS * 16 + 2 * ext;      // 2*np + 2 padded pixels
+    if (warp == CONSUMERS / 32) {
+        if (lane == 0) {
+            int s = 0, ph = 0;
+            for (int t = blockIdx.x; t < nstrips; t += gridDim.x) {
+                Strip sp;
+                sp.set(t, cpr, nbands, H);
+                // step k0-1 preloads padded rows 2*k0, 2*k0+1 (no y row); step k loads padded rows 2k+2, 2k+3 and y row k
+                for (int k = sp.k0 - 1; k < sp.k1; ++k) {
+                    mbar_wait(bars + 8 * (STAGES + s), ph ^ 1);
+                    const uint32_t full = bars + 8 * s, stage = s32(smem + s * STAGE_BYTES);
+                    const bool with_y = k >= sp.k0;
+                    mbar_expect_tx(full, 2 * drow_bytes + (with_y ? PIPE_UP_ITEMS * 16 : 0));
+                    const bf16* d0 = dout.row(sp.n, 2 * k + 2) + sp.ch * (2 * PIPE_UP_ITEMS * 8);
+                    bulk_g2s(stage, d0, drow_bytes, full);
+                    bulk_g2s(stage + PIPE_BUP_DROW, d0 + dout.sy, drow_bytes, full);
+                    if (with_y) bulk_g2s(stage + 2 * PIPE_BUP_DROW, y.row(sp.n, k) + sp.ch * (PIPE_UP_ITEMS * 8), PIPE_UP_ITEMS * 16, full);
+                    if (++s == STAGES) { s = 0; ph ^= 1; }
+                }
+            }
+        }
+        return;
+    }
+    const int ncg = C >> 3;
+    const int cg = tid & (ncg - 1), c0 = cg * 8;
+    const int pl = tid >> cg_shift;
+    float2 sc[4], sh[4], nmu[4], s1[4], s2[4];
+    bwd_consts(PASS1_WRITE, scale, shift, mean, invstd, sums, 1.0, C, c0, sc, sh, nmu, s1, s2);
+    const int OH = 2 * H, OW = 2 * W;
+    const float ry = (float)(H - 1) / (float)(OH - 1), rx = (float)(W - 1) / (float)(OW - 1);
+    const uint32_t doff = ((2 * pl) << cg_shift | cg) * 16;       // padded column 2j of this thread inside a dout row span
+    // sum_b wx[b] * dout[row][padded col 2j + b]
+    auto hgather = [&](const uint8_t* rowp, const float (&wx)[4], float2 (&o)[4]) {
+        uint4 r[4];
+#pragma unroll
+        for (int b = 0; b < 4; ++b) r[b] = lds16(rowp + doff + b * ext);
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+            float2 v[4];
+            P8<bf16>::up(r[b], v);
+            const float2 w2 = make_float2(wx[b], wx[b]);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) o[i] = b == 0 ? make_float2(w2.x * v[i].x, w2.y * v[i].y) : fma2(w2, v[i], o[i]);
+        }
+    };
+    int s = 0, ph = 0;
+    for (int t = blockIdx.x; t < nstrips; t += gridDim.x) {
+        Strip sp;
+        sp.set(t, cpr, nbands, H);
+        const int j = sp.ch * (PIPE_UP_ITEMS >> cg_shift) + pl;
+        float wx[4];
+#pragma unroll
+        for (int b = 0; b < 4; ++b) wx[b] = up_weight(j, 2 * j - 1 + b, rx, W, OW);
+        if (j == 0) wx[0] = wx[1];                               // left padding column folds into output column 0
+        if (j == W - 1) wx[3] = wx[2];                           // right padding column folds into output column OW-1
+        float2 hA[4], hB[4];
+        for (int k = sp.k0 - 1; k < sp.k1; ++k) {
+            mbar_wait(bars + 8 * s, ph);
+            const uint8_t* st = smem + s * STAGE_BYTES;
+            float2 hC[4], hD[4];
+            hgather(st, wx, hC);
+            hgather(st + PIPE_BUP_DROW, wx, hD);
+            uint4 ry4 = make_uint4(0, 0, 0, 0);
+            if (k >= sp.k0) ry4 = lds16(st + 2 * PIPE_BUP_DROW + tid * 16);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bars + 8 * (STAGES + s));
+            if (++s == STAGES) { s = 0; ph ^= 1; }
+            if (k >= sp.k0) {
+                float wy[4];
+#pragma unroll
+                for (int a = 0; a < 4; ++a) wy[a] = up_weight(k, 2 * k - 1 + a, ry, H, OH);
+                if (k == 0) wy[0] = wy[1];
+                if (k == H - 1) wy[3] = wy[2];
+                float2 g[4], yv[4];
+                P8<bf16>::up(ry4, yv);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    float2 acc = make_float2(wy[0] * hA[i].x, wy[0] * hA[i].y);
+                    acc = fma2(make_float2(wy[1], wy[1]), hB[i], acc);
+                    acc = fma2(make_float2(wy[2], wy[2]), hC[i], acc);
+                    acc = fma2(make_float2(wy[3], wy[3]), hD[i], acc);
+                    const float2 z = fma2(yv[i], sc[i], sh[i]);
+                    const float2 dz = make_float2(actg<ACT>(z.x, acc.x), actg<ACT>(z.y, acc.y));
+                    g[i] = dz;
+                    s1[i] = add2(s1[i], dz);
+                    s2[i] = fma2(dz, add2(yv[i], nmu[i]), s2[i]);
+                }
+                P8<bf16>::st(dy.row(sp.n, k) + j * C + c0, g);
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) { hA[i] = hC[i]; hB[i] = hD[i]; }
+        }
+    }
+    consumer_sync();
+    float* red = reinterpret_cast<float*>(smem);
+    float2 is[4];
+    load_c8(invstd, c0, 1.f, is);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        red[tid * 8 + 2 * i] = s1[i].x; red[tid * 8 + 2 * i + 1] = s1[i].y;
+        red[2048 + tid * 8 + 2 * i] = s2[i].x * is[i].x; red[2048 + tid * 8 + 2 * i + 1] = s2[i].y * is[i].y;
+    }
+    consumer_sync();
+    for (int ch = tid; ch < C; ch += CONSUMERS) {
+        const int g8 = ch >> 3, i = ch & 7;
+        float a = 0.f, b = 0.f;
+        for (int t = g8; t < CONSUMERS; t += ncg) { a += red[t * 8 + i]; b += red[2048 + t * 8 + i]; }
+        atomicAdd(&sums[ch], (double)a);
+        atomicAdd(&sums[C + ch], (double)b);
+    }
+}

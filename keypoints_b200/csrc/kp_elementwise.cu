@@ -941,6 +941,11 @@ static bool pipe_enabled() {
     return v == 1;
 }
 // dense bf16 NHWC rows the bulk-async kernels can stream: pixel stride == C, 512-item chunks
+static bool pipe_up_enabled() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("KP_BN_PIPE_UP"); v = (e && e[0] == '0') ? 0 : 1; }
+    return v == 1;
+}
 static bool pipe_view_ok(const kp_view* v, int C) { return v->dtype == KP_BF16 && v->sx == C && view_vec8_ok(v, C); }
 static bool pipe_shape_ok(int C, int W) {
     if (C % 8) return false;
@@ -1042,6 +1047,22 @@ static int bn_act_fwd_impl(kp_stream stream, const kp_view* y, const kp_view* ou
     } while (0)
                 KP_ACT_SWITCH(act, KP_FWDPP);
 #undef KP_FWDPP
+                if (fuse && fused_done) *fused_done = 1;
+            } else if (pipe_enabled() && post == KP_POST_UP && H >= 2 && W >= 2 && pipe_pool_shape_ok(C, W) &&
+                       pipe_view_ok(y, C) && pipe_view_ok(out, C) && pipe_up_enabled()) {
+                const int cpr = (int)((long long)W * (C / 8) / PIPE_UP_ITEMS), sh = ilog2(C / 8);
+                const long long strips = (long long)N * ((H + PIPE_UP_BAND - 1) / PIPE_UP_BAND) * cpr;
+                constexpr int smem = pipe_smem_bytes<PIPE_FUP_STAGE, PIPE_FUP_STAGES>();
+                cudaStream_t st = (cudaStream_t)stream;
+#define KP_FWDUP(ACTV)                                                                                                 \
+    do {                                                                                                               \
+        int rc_ = pipe_attr(bn_fwd_up_pipe_k<ACTV>, smem);                                                             \
+        if (rc_) return rc_;                                                                                           \
+        bn_fwd_up_pipe_k<ACTV><<<pipe_grid(strips), pipe::THREADS, smem, st>>>(                                        \
+            make_rows<const bf16>(y), make_rows<bf16>(out), scale, shift, pad, N, H, W, C, sh, cpr, fz);               \
+    } while (0)
+                KP_ACT_SWITCH(act, KP_FWDUP);
+#undef KP_FWDUP
                 if (fuse && fused_done) *fused_done = 1;
             } else if (vec && fast_ok(C, P * C) && std::is_same<TI, TO>::value && lean_enabled() &&
                 (post == KP_POST_NONE || post == KP_POST_POOL)) {
@@ -1175,6 +1196,23 @@ extern "C" int kp_bn_act_bwd_reduce(kp_stream stream, const kp_view* dout, const
     } while (0)
                     KP_ACT_SWITCH(act, KP_BWDPP);
 #undef KP_BWDPP
+                } else if (pipe_enabled() && pipe_up_enabled() && post == KP_POST_UP && pad == 1 && H >= 2 && W >= 2 &&
+                           pipe_pool_shape_ok(C, W) && pipe_view_ok(dout, C) && pipe_view_ok(y, C) && dyv->ptr != nullptr &&
+                           pipe_view_ok(dyv, C)) {
+                    const int cpr = (int)((long long)W * (C / 8) / PIPE_UP_ITEMS), sh = ilog2(C / 8);
+                    const long long strips = (long long)N * ((H + PIPE_UP_BAND - 1) / PIPE_UP_BAND) * cpr;
+                    constexpr int smem = pipe_smem_bytes<PIPE_BUP_STAGE, PIPE_BUP_STAGES>();
+                    cudaStream_t st = (cudaStream_t)stream;
+#define KP_BWDUP(ACTV)                                                                                                 \
+    do {                                                                                                               \
+        int rc_ = pipe_attr(bn_bwd_up_pipe_k<ACTV>, smem);                                                             \
+        if (rc_) return rc_;                                                                                           \
+        bn_bwd_up_pipe_k<ACTV><<<pipe_grid(strips), pipe::THREADS, smem, st>>>(                                        \
+            make_rows<const bf16>(dout), make_rows<const bf16>(y), make_rows<bf16>(dyv), scale, shift, mean, invstd,   \
+            sums, N, H, W, C, sh, cpr);                                                                                \
+    } while (0)
+                    KP_ACT_SWITCH(act, KP_BWDUP);
+#undef KP_BWDUP
                 } else if (vec && fast_ok(C, P * C) && std::is_same<TG, TY>::value && std::is_same<TY, TD>::value &&
                     lean_enabled() && (post == KP_POST_NONE || post == KP_POST_POOL)) {
                     const long long rows = post == KP_POST_POOL ? (long long)N * ((H + 1) / 2) : (long long)N * H;
