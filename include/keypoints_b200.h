@@ -181,6 +181,23 @@ int kp_transport_bwd(kp_stream stream, const kp_view* dout, int pad, const kp_vi
                      const kp_view* phi_t, const float* mask_s, const float* mask_t,
                      const kp_view* dphi_t, float* dmask_t, int N, int h, int w, int C);
 
+/* The other combine modes of TransporterNet.forward (models/transporter.py:41-50) and a mode-generic backward.
+ * mode: KP_COMBINE_MAX | KP_COMBINE_SUM ('sum_and_clamp') | KP_COMBINE_LOOP ('loop').
+ * aux: int32 [N][h][w] (max: arg-max keypoint of the target; sum: 1 where the unclamped target sum lies in [0,1]);
+ * coef: f32 [N][h][w][2], loop mode only: phi = phi_s*coef0 + phi_t*coef1.  In loop mode mask_s / mask_t receive the maps
+ * of the LAST keypoint (what the reference returns).  The backward writes dphi_t and dm_t (f32 [N][K][h][w], the
+ * gradient w.r.t. every rendered target map), to be reduced to d(keypoints) by kp_gaussian_bwd. */
+#define KP_COMBINE_MAX 0
+#define KP_COMBINE_SUM 1
+#define KP_COMBINE_LOOP 2
+int kp_transport_mode_fwd(kp_stream stream, int mode, const kp_view* phi_s, const kp_view* phi_t, const float* k_s,
+                          const float* k_t, const kp_view* out, int pad, float* mask_s, float* mask_t, int32_t* aux,
+                          float* coef, int N, int h, int w, int C, int K, float sigma, float eps);
+int kp_transport_mode_bwd(kp_stream stream, int mode, const kp_view* dout, int pad, const kp_view* phi_s,
+                          const kp_view* phi_t, const float* k_s, const float* k_t, const float* mask_s,
+                          const float* mask_t, const int32_t* aux, const float* coef, const kp_view* dphi_t,
+                          float* dm_t, int N, int h, int w, int C, int K, float sigma, float eps);
+
 /* l2_reconstruction_loss (transporter.py:56-60, keypoints.py:54-58) and its gradient:
  * loss[0] += sum (xhat-target)^2 * mask (double, caller zeroes; mean = /numel on the host side or
  * via kp_scale), dxhat = 2 (xhat-target) mask * gscale.  fp32 contiguous, mask nullable. */

@@ -214,6 +214,132 @@ transport_bwd_k(View<TG> dout, int pad, View<TP> phi_s, View<TP> phi_t, const fl
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// The non-default combine modes of TransporterNet.forward (models/transporter.py:41-50):
+//   KP_COMBINE_SUM : M = clamp(sum_k m_k, 0, 1) for source and target, then the same blend as 'max'
+//   KP_COMBINE_LOOP: phi <- phi (1 - m_s,k)(1 - m_t,k) + phi_t m_t,k for k = 0..K-1.  The recurrence is affine in phi with
+//                    per-pixel coefficients, phi_K = phi_s A + phi_t B (A_{k+1} = A_k c_k, B_{k+1} = B_k c_k + m_t,k,
+//                    c_k = (1 - m_s,k)(1 - m_t,k)), so it costs one pass over the keypoints per pixel, not per channel.
+// KP_COMBINE_MAX is accepted too (the fused trainer keeps using kp_transport_fwd / _bwd for it).
+// ------------------------------------------------------------------------------------------------
+template <int MODE, typename TP, typename TO>
+__global__ void __launch_bounds__(256)
+transport_mode_fwd_k(View<TP> phi_s, View<TP> phi_t, const float* __restrict__ k_s, const float* __restrict__ k_t,
+                     View<TO> out, int pad, float* mask_s, float* mask_t, int* aux, float* coef, int N, int h, int w, int C,
+                     int K, float two_s2, float eps) {
+    const int PH = h + 2 * pad, PW = w + 2 * pad;
+    const long long total = (long long)N * PH * PW * C;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+         idx += (long long)gridDim.x * blockDim.x) {
+        int c = (int)(idx % C);
+        long long p = idx / C;
+        int px = (int)(p % PW);
+        long long r = p / PW;
+        int py = (int)(r % PH);
+        int n = (int)(r / PH);
+        int i = min(max(py - pad, 0), h - 1), j = min(max(px - pad, 0), w - 1);
+        float yi = ruler(i, h), xj = ruler(j, w);
+        float ms = MODE == KP_COMBINE_MAX ? -INFINITY : 0.f, mt = ms, A = 1.f, B = 0.f;
+        int ax = 0;
+        for (int q = 0; q < K; ++q) {
+            const float* ks_ = k_s + ((long long)n * K + q) * 2;
+            const float* kt_ = k_t + ((long long)n * K + q) * 2;
+            float a = gauss(yi, xj, ks_[0], ks_[1], two_s2, eps);
+            float b = gauss(yi, xj, kt_[0], kt_[1], two_s2, eps);
+            if (MODE == KP_COMBINE_MAX) { ms = fmaxf(ms, a); if (b > mt) { mt = b; ax = q; } }
+            else if (MODE == KP_COMBINE_SUM) { ms += a; mt += b; }
+            else { const float cq = (1.f - a) * (1.f - b); A *= cq; B = fmaf(B, cq, b); ms = a; mt = b; }
+        }
+        float ps = to_f(*phi_s.at(n, i, j, c)), pt = to_f(*phi_t.at(n, i, j, c));
+        float o;
+        if (MODE == KP_COMBINE_LOOP) {
+            o = ps * A + pt * B;
+        } else {
+            if (MODE == KP_COMBINE_SUM) {
+                ax = (mt >= 0.f && mt <= 1.f) ? 1 : 0;          // clamp passes the gradient inside [0, 1] (inclusive, as torch)
+                ms = fminf(fmaxf(ms, 0.f), 1.f); mt = fminf(fmaxf(mt, 0.f), 1.f);
+            }
+            o = ps * (1.f - ms) * (1.f - mt) + pt * mt;
+        }
+        from_f(out.at(n, py, px, c), o);
+        if (c == 0 && py - pad == i && px - pad == j) {
+            long long e = ((long long)n * h + i) * w + j;
+            if (mask_s) mask_s[e] = ms;
+            if (mask_t) mask_t[e] = mt;
+            if (aux) aux[e] = ax;
+            if (coef) { coef[2 * e] = A; coef[2 * e + 1] = B; }
+        }
+    }
+}
+
+// one warp per pixel: dphi_t and the gradient w.r.t. every rendered target map m_t[n][k][i][j]
+template <int MODE, typename TG, typename TP, typename TD>
+__global__ void __launch_bounds__(256)
+transport_mode_bwd_k(View<TG> dout, int pad, View<TP> phi_s, View<TP> phi_t, const float* __restrict__ k_s,
+                     const float* __restrict__ k_t, const float* __restrict__ mask_s, const float* __restrict__ mask_t,
+                     const int* __restrict__ aux, const float* __restrict__ coef, View<TD> dphi_t, float* dm_t, int N, int h,
+                     int w, int C, int K, float two_s2, float eps) {
+    const int lane = threadIdx.x & 31;
+    const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+    const long long P = (long long)N * h * w, hw = (long long)h * w;
+    for (long long p = warp; p < P; p += nwarps) {
+        int j = (int)(p % w);
+        long long r = p / w;
+        int i = (int)(r % h);
+        int n = (int)(r / h);
+        const float ms = mask_s[p], mt = mask_t[p];
+        const float A = MODE == KP_COMBINE_LOOP ? coef[2 * p] : 0.f, B = MODE == KP_COMBINE_LOOP ? coef[2 * p + 1] : 0.f;
+        int ys[3], xs[3], ny = 0, nx = 0;
+        if (pad) {
+            ys[ny++] = i + 1; if (i == 0) ys[ny++] = 0; if (i == h - 1) ys[ny++] = h + 1;
+            xs[nx++] = j + 1; if (j == 0) xs[nx++] = 0; if (j == w - 1) xs[nx++] = w + 1;
+        } else { ys[ny++] = i; xs[nx++] = j; }
+        float acc = 0.f, accA = 0.f;
+        for (int c = lane; c < C; c += 32) {
+            float g = 0.f;
+            for (int a = 0; a < ny; ++a)
+                for (int b = 0; b < nx; ++b) g += to_f(*dout.at(n, ys[a], xs[b], c));
+            float ps = to_f(*phi_s.at(n, i, j, c)), pt = to_f(*phi_t.at(n, i, j, c));
+            if (MODE == KP_COMBINE_LOOP) {
+                from_f(dphi_t.at(n, i, j, c), g * B);
+                accA += g * ps;                                   // d/dA
+                acc += g * pt;                                    // d/dB
+            } else {
+                from_f(dphi_t.at(n, i, j, c), g * mt);
+                acc += g * (pt - ps * (1.f - ms));
+            }
+        }
+        acc = warp_sum(acc);
+        accA = warp_sum(accA);
+        float* dm = dm_t + (long long)n * K * hw + (long long)i * w + j;
+        if (MODE == KP_COMBINE_MAX) {
+            const int ax = aux[p];
+            for (int q = lane; q < K; q += 32) dm[q * hw] = q == ax ? acc : 0.f;
+        } else if (MODE == KP_COMBINE_SUM) {
+            const float v = aux[p] ? acc : 0.f;
+            for (int q = lane; q < K; q += 32) dm[q * hw] = v;
+        } else if (lane == 0) {
+            // reverse the recurrence: state before step q is recovered by dividing out c_q (c_q > 0: both maps are < 1)
+            float yi = ruler(i, h), xj = ruler(j, w);
+            float gA = accA, gB = acc, Aq = A, Bq = B;
+            for (int q = K - 1; q >= 0; --q) {
+                const float* ks_ = k_s + ((long long)n * K + q) * 2;
+                const float* kt_ = k_t + ((long long)n * K + q) * 2;
+                const float a = gauss(yi, xj, ks_[0], ks_[1], two_s2, eps);
+                const float b = gauss(yi, xj, kt_[0], kt_[1], two_s2, eps);
+                const float cq = (1.f - a) * (1.f - b);
+                Bq = (Bq - b) / cq;                               // B_q, A_q: the state entering step q
+                Aq = Aq / cq;
+                const float gc = gA * Aq + gB * Bq;
+                dm[q * hw] = gB - gc * (1.f - a);
+                gA *= cq;
+                gB *= cq;
+            }
+        }
+    }
+}
+
 __global__ void __launch_bounds__(256) l2_loss_k(const float* __restrict__ xhat, const float* __restrict__ target,
                                                  const float* __restrict__ mask, long long numel, float gscale,
                                                  double* loss_sum, float* dxhat) {
@@ -318,6 +444,62 @@ extern "C" int kp_transport_bwd(kp_stream stream, const kp_view* dout, int pad, 
                 transport_bwd_k<TG, TP, TD><<<grid, 256, 0, (cudaStream_t)stream>>>(
                     make_view<TG>(dout), pad, make_view<TP>(phi_s), make_view<TP>(phi_t), mask_s, mask_t,
                     make_view<TD>(dphi_t), dmask_t, N, h, w, C);
+                KP_LAUNCH_CHECK();
+                return KP_OK;
+            });
+        });
+    });
+}
+
+extern "C" int kp_transport_mode_fwd(kp_stream stream, int mode, const kp_view* phi_s, const kp_view* phi_t,
+                                     const float* k_s, const float* k_t, const kp_view* out, int pad, float* mask_s,
+                                     float* mask_t, int32_t* aux, float* coef, int N, int h, int w, int C, int K,
+                                     float sigma, float eps) {
+    KP_CHECK_ARG(phi_s && phi_t && out && phi_s->ptr && phi_t->ptr && out->ptr && k_s && k_t && N > 0 && h > 0 &&
+                     w > 0 && C > 0 && K > 0 && phi_s->dtype == phi_t->dtype && mode >= KP_COMBINE_MAX &&
+                     mode <= KP_COMBINE_LOOP && (mode != KP_COMBINE_LOOP || coef) && (mode == KP_COMBINE_LOOP || aux),
+                 "kp_transport_mode_fwd: bad arguments");
+    const float two_s2 = (float)(2.0 * (double)sigma * (double)sigma);
+    long long total = (long long)N * (h + 2 * pad) * (w + 2 * pad) * C;
+    int grid = grid_for(total, 256);
+    return dispatch1(phi_s->dtype, [&](auto tp) -> int {
+        return dispatch1(out->dtype, [&](auto to) -> int {
+            using TP = decltype(tp);
+            using TO = decltype(to);
+#define KP_TMF(M) transport_mode_fwd_k<M, TP, TO><<<grid, 256, 0, (cudaStream_t)stream>>>(make_view<TP>(phi_s), make_view<TP>(phi_t), k_s, k_t, make_view<TO>(out), pad, mask_s, mask_t, aux, coef, N, h, w, C, K, two_s2, eps)
+            if (mode == KP_COMBINE_MAX) KP_TMF(KP_COMBINE_MAX);
+            else if (mode == KP_COMBINE_SUM) KP_TMF(KP_COMBINE_SUM);
+            else KP_TMF(KP_COMBINE_LOOP);
+#undef KP_TMF
+            KP_LAUNCH_CHECK();
+            return KP_OK;
+        });
+    });
+}
+
+extern "C" int kp_transport_mode_bwd(kp_stream stream, int mode, const kp_view* dout, int pad, const kp_view* phi_s,
+                                     const kp_view* phi_t, const float* k_s, const float* k_t, const float* mask_s,
+                                     const float* mask_t, const int32_t* aux, const float* coef, const kp_view* dphi_t,
+                                     float* dm_t, int N, int h, int w, int C, int K, float sigma, float eps) {
+    KP_CHECK_ARG(dout && phi_s && phi_t && dphi_t && dout->ptr && phi_s->ptr && phi_t->ptr && dphi_t->ptr && mask_s &&
+                     mask_t && dm_t && k_s && k_t && N > 0 && h > 0 && w > 0 && C > 0 && K > 0 &&
+                     phi_s->dtype == phi_t->dtype && mode >= KP_COMBINE_MAX && mode <= KP_COMBINE_LOOP &&
+                     (mode != KP_COMBINE_LOOP || coef) && (mode == KP_COMBINE_LOOP || aux),
+                 "kp_transport_mode_bwd: bad arguments");
+    const float two_s2 = (float)(2.0 * (double)sigma * (double)sigma);
+    long long P = (long long)N * h * w;
+    int grid = grid_for(P * 32, 256);
+    return dispatch1(dout->dtype, [&](auto tg) -> int {
+        return dispatch1(phi_s->dtype, [&](auto tp) -> int {
+            return dispatch1(dphi_t->dtype, [&](auto td) -> int {
+                using TG = decltype(tg);
+                using TP = decltype(tp);
+                using TD = decltype(td);
+#define KP_TMB(M) transport_mode_bwd_k<M, TG, TP, TD><<<grid, 256, 0, (cudaStream_t)stream>>>(make_view<TG>(dout), pad, make_view<TP>(phi_s), make_view<TP>(phi_t), k_s, k_t, mask_s, mask_t, aux, coef, make_view<TD>(dphi_t), dm_t, N, h, w, C, K, two_s2, eps)
+                if (mode == KP_COMBINE_MAX) KP_TMB(KP_COMBINE_MAX);
+                else if (mode == KP_COMBINE_SUM) KP_TMB(KP_COMBINE_SUM);
+                else KP_TMB(KP_COMBINE_LOOP);
+#undef KP_TMB
                 KP_LAUNCH_CHECK();
                 return KP_OK;
             });

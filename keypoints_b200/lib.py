@@ -18,6 +18,7 @@ F32, BF16 = 0, 1
 ACT_NONE, ACT_LEAKY, ACT_RELU = 0, 1, 2
 POST_NONE, POST_POOL, POST_UP = 0, 1, 2
 ACTS = {None: ACT_NONE, 'none': ACT_NONE, 'leaky': ACT_LEAKY, 'relu': ACT_RELU}
+COMBINE = {'max': 0, 'sum_and_clamp': 1, 'loop': 2}
 POSTS = {None: POST_NONE, 'none': POST_NONE, 'pool': POST_POOL, 'up': POST_UP}
 
 
@@ -56,6 +57,8 @@ SIGNATURES = {
     'kp_gaussian_bwd': [_P, _VP, _I, _P, _P, _I, _I, _I, _I, _F, _F, _P],
     'kp_transport_fwd': [_P, _VP, _VP, _P, _P, _VP, _I, _P, _P, _P, _I, _I, _I, _I, _I, _F, _F],
     'kp_transport_bwd': [_P, _VP, _I, _VP, _VP, _P, _P, _VP, _P, _I, _I, _I, _I],
+    'kp_transport_mode_fwd': [_P, _I, _VP, _VP, _P, _P, _VP, _I, _P, _P, _P, _P, _I, _I, _I, _I, _I, _F, _F],
+    'kp_transport_mode_bwd': [_P, _I, _VP, _I, _VP, _VP, _P, _P, _P, _P, _P, _P, _VP, _P, _I, _I, _I, _I, _I, _F, _F],
     'kp_l2_loss': [_P, _P, _P, _P, _L, _F, _P, _P],
     'kp_tps_warp': [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I],
     'kp_rotate_warp': [_P, _P, _P, _P, _I, _I, _I, _I],

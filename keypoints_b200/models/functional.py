@@ -102,6 +102,46 @@ class _TransportMaxFn(torch.autograd.Function):
         return None, dphi_t, None, dk, None, None
 
 
+class _TransportModeFn(torch.autograd.Function):
+    """The 'sum_and_clamp' and 'loop' combine modes (models/transporter.py:41-50); 'max' is accepted as well."""
+
+    @staticmethod
+    def forward(ctx, phi_s, phi_t, k_s, k_t, mode, sigma, eps):
+        phi_s, phi_t, k_s, k_t = _planes(phi_s), _planes(phi_t), _planes(k_s), _planes(k_t)
+        n, c, h, w = phi_t.shape
+        K = k_t.shape[1]
+        dev = phi_t.device
+        out = torch.empty((n, c, h, w), dtype=torch.float32, device=dev)
+        mask_s = torch.empty((n, 1, h, w), dtype=torch.float32, device=dev)
+        mask_t = torch.empty((n, 1, h, w), dtype=torch.float32, device=dev)
+        aux = torch.zeros((n, h, w), dtype=torch.int32, device=dev)
+        coef = torch.empty((n, h, w, 2), dtype=torch.float32, device=dev)
+        L.call('kp_transport_mode_fwd', L.stream(), int(mode), L.nchw(phi_s), L.nchw(phi_t), L.ptr(k_s), L.ptr(k_t),
+               L.nchw(out), 0, L.ptr(mask_s), L.ptr(mask_t), L.ptr(aux), L.ptr(coef), n, h, w, c, K, float(sigma), float(eps))
+        ctx.save_for_backward(phi_s, phi_t, k_s, k_t, mask_s, mask_t, aux, coef)
+        ctx.cfg = (int(mode), float(sigma), float(eps))
+        ctx.mark_non_differentiable(mask_s)
+        return out, mask_s, mask_t
+
+    @staticmethod
+    def backward(ctx, dout, _dms, _dmt):
+        if ctx.needs_input_grad[0] or ctx.needs_input_grad[2]:
+            raise NotImplementedError('the source branch of the Transporter is a constant (reference runs it under no_grad)')
+        phi_s, phi_t, k_s, k_t, mask_s, mask_t, aux, coef = ctx.saved_tensors
+        mode, sigma, eps = ctx.cfg
+        n, c, h, w = phi_t.shape
+        K = k_t.shape[1]
+        dout = _planes(dout)
+        dphi_t = torch.empty_like(phi_t)
+        dm_t = torch.empty((n, K, h, w), dtype=torch.float32, device=phi_t.device)
+        L.call('kp_transport_mode_bwd', L.stream(), mode, L.nchw(dout), 0, L.nchw(phi_s), L.nchw(phi_t), L.ptr(k_s),
+               L.ptr(k_t), L.ptr(mask_s), L.ptr(mask_t), L.ptr(aux), L.ptr(coef), L.nchw(dphi_t), L.ptr(dm_t), n, h, w, c, K,
+               sigma, eps)
+        dk = torch.empty_like(k_t)
+        L.call('kp_gaussian_bwd', L.stream(), L.nchw(dm_t), 0, L.ptr(k_t), None, n, K, h, w, sigma, eps, L.ptr(dk))
+        return None, dphi_t, None, dk, None, None, None
+
+
 def spacial_softmax(heatmap, probs=False):
     """functional.py:27-34."""
     k, ph, pw = _SpatialSoftmaxFn.apply(heatmap)
@@ -122,6 +162,17 @@ def gaussian_like_function(kp, height, width, sigma=0.1, eps=1e-6):
 def transport_max(phi_s, phi_t, k_s, k_t, sigma=0.1, eps=1e-6):
     """Fused render + max-over-keypoints + transport; returns (phi, mask_s, mask_t)."""
     return _TransportMaxFn.apply(phi_s, phi_t, k_s, k_t, sigma, eps)
+
+
+def transport(phi_s, phi_t, k_s, k_t, mode='max', sigma=0.1, eps=1e-6):
+    """Render + combine + transport for any combine mode of TransporterNet.forward ('max' | 'sum_and_clamp' | 'loop',
+    models/transporter.py:41-60); returns (phi, mask_s, mask_t) exactly as the reference's forward leaves them."""
+    if mode == 'max':
+        return transport_max(phi_s, phi_t, k_s, k_t, sigma, eps)
+    if mode not in L.COMBINE:
+        raise NotImplementedError(f"combine mode {mode!r}: 'pretrained_network' needs a MaskMaker network that the "
+                                  "reference never builds in make() (models/transporter.py:112-128)")
+    return _TransportModeFn.apply(phi_s, phi_t, k_s, k_t, L.COMBINE[mode], sigma, eps)
 
 
 # -- small helpers kept for API completeness (not on the training path; plain tensor algebra) ------------

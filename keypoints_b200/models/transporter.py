@@ -28,15 +28,12 @@ class TransporterNet(knn.Container):
     def forward(self, xs, xt):
         """-> (x_t, phi, k_xt, m_xt, (p_h,p_w), heatmap_xt, mask_xs, mask_xt), transporter.py:34-64.
         The source frame is a constant (no_grad) but still updates the BatchNorm running statistics."""
-        if self.combine_method != 'max':
-            raise NotImplementedError(
-                f"combine_method={self.combine_method!r}: only 'max' (the default of make(), and the only mode the "
-                "reference's scripts can select, SURVEY.md 5) is implemented; see DESIGN.md 'out of scope'")
         with torch.no_grad():
             phi_xs, _, k_xs, _, _ = self.extract(xs)
         phi_xt, heatmap_xt, k_xt, p_xt, m_xt = self.extract(xt)
         sigma = getattr(self.key2map, 'sigma', 0.1)
-        phi, mask_xs, mask_xt = MF.transport_max(phi_xs, phi_xt, k_xs, k_xt, sigma=sigma)
+        # 'max' (default of make()), 'sum_and_clamp', 'loop' (:41-60); 'pretrained_network' raises (no MaskMaker in make())
+        phi, mask_xs, mask_xt = MF.transport(phi_xs, phi_xt, k_xs, k_xt, mode=self.combine_method, sigma=sigma)
         x_t = self.decoder(phi)
         return x_t, phi, k_xt, m_xt, p_xt, heatmap_xt, mask_xs, mask_xt
 

@@ -201,6 +201,18 @@ def keynet_ops(model_type: str, cin: int, z: int, K: int):
                 decoder=unit_ops(DECODER_CFG[model_type], z + K, cin, 'relu'))
 
 
+def autoencoder_ops(model_type: str, cin: int, z: int):
+    """Layer lists of the pre-training auto-encoder (autoencode.py:59-66): encoder AND decoder cores use LeakyReLU."""
+    return dict(encoder=unit_ops(ENCODER_CFG[model_type], cin, z, 'leaky'),
+                decoder=unit_ops(DECODER_CFG[model_type], z, cin, 'leaky'))
+
+
+def autoencoder_forward(x, sd, ops, training: bool = True):
+    """``AutoEncoder.forward`` (models/autoencoder.py:13-16).  Returns (z, x_hat)."""
+    z = unit_forward(x, sd, 'encoder.', ops['encoder'], training)
+    return z, unit_forward(z, sd, 'decoder.', ops['decoder'], training)
+
+
 def transporter_forward(xs, xt, sd, ops, mode: str = 'max', sigma: float = 0.1, training: bool = True):
     """``TransporterNet.forward`` (models/transporter.py:34-64).
 
@@ -356,9 +368,14 @@ def adam_step(p, g, m, v, step: int, lr=1e-4, b1=0.9, b2=0.999, eps=1e-8):
 class OracleTrainer:
     """Functional train step on a flat parameter dict: forward, L2 loss, autograd backward, Adam."""
 
-    def __init__(self, kind: str, model_type: str, cin: int, z: int, K: int, sd: Dict[str, torch.Tensor]):
+    def __init__(self, kind: str, model_type: str, cin: int, z: int, K: int, sd: Dict[str, torch.Tensor],
+                 mode: str = 'max'):
         self.kind = kind
-        self.ops = transporter_ops(model_type, cin, z, K) if kind == 'transporter' else keynet_ops(model_type, cin, z, K)
+        self.mode = mode
+        if kind == 'autoencoder':
+            self.ops = autoencoder_ops(model_type, cin, z)
+        else:
+            self.ops = transporter_ops(model_type, cin, z, K) if kind == 'transporter' else keynet_ops(model_type, cin, z, K)
         self.sd = sd
         self.keys = trainable_keys(sd)
         for k in self.keys:
@@ -369,7 +386,10 @@ class OracleTrainer:
 
     def forward(self, a, b):
         if self.kind == 'transporter':
-            return transporter_forward(a, b, self.sd, self.ops)
+            return transporter_forward(a, b, self.sd, self.ops, mode=self.mode)
+        if self.kind == 'autoencoder':          # autoencode.py:87-88: z, x_ = net(x); MSELoss(x_, x); (x_hat first here)
+            z, xh = autoencoder_forward(a, self.sd, self.ops)
+            return xh, z
         return keynet_forward(a, b, self.sd, self.ops)
 
     def step(self, a, b, mask=None, lr=1e-4):

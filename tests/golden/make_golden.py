@@ -26,6 +26,11 @@ warnings.filterwarnings('ignore')
 
 from keypoints.models import transporter as ref_transporter  # noqa: E402
 from keypoints.models import knn as ref_knn, vgg as ref_vgg, keynet as ref_keynet  # noqa: E402
+import keypoints.models as _ref_models  # noqa: E402
+# models/autoencoder.py:1 does `from keypoints.models import Container`, a name the package __init__ never exports (the
+# reference's autoencode.py cannot start either); supply it from knn, where the class lives, without touching the file
+_ref_models.Container = ref_knn.Container
+from keypoints.models import autoencoder as ref_autoencoder  # noqa: E402
 from keypoints.models import functional as RF  # noqa: E402
 import tps as ref_tps  # noqa: E402
 import data_augments as ref_aug  # noqa: E402
@@ -132,10 +137,61 @@ def build_ref_keynet(model_type, cin, z, K):
     return ref_keynet.KeyNet(enc, kp, ref_knn.GaussianLike(sigma=0.1), dec, init_weights=True)
 
 
-def model_fixture(name, kind, model_type, cin, z, K, n, h, w, seed, lo, hi, with_mask, adam=False):
+def build_ref_autoencoder(model_type, cin, z):
+    """autoencode.py:59-66."""
+    nn = torch.nn
+    kw = dict(nonlinearity=nn.LeakyReLU, nonlinearity_kwargs={'inplace': True})
+    enc = ref_knn.Unit(cin, z, ref_vgg.make_layers(ref_vgg.vgg_cfg[model_type], **kw))
+    dec = ref_knn.Unit(z, cin, ref_vgg.make_layers(ref_vgg.decoder_cfg[model_type], **kw))
+    return ref_autoencoder.AutoEncoder(enc, dec, init_weights=True)
+
+
+def autoencoder_fixture(name, model_type, cin, z, n, h, w, seed, lo, hi):
+    """One auto-encoder pre-training step (autoencode.py:84-96) + the checkpoint the reference writes, and what
+    TransporterNet.load_from_autoencoder (models/transporter.py:71-75) makes of it."""
+    import shutil
+    rng = np.random.default_rng(seed)
+    net = build_ref_autoencoder(model_type, cin, z)
+    ops = O.autoencoder_ops(model_type, cin, z)
+    sd = O.init_state_dict(ops, seed)
+    net.load_state_dict(sd, strict=True)
+    x = synth_images(rng, n, cin, h, w, lo, hi)
+    out = {'a': npy(x), 'meta': np.array([cin, z, 0, n, h, w, seed])}
+    optim = torch.optim.Adam(net.parameters(), lr=1e-4)
+    optim.zero_grad()
+    zz, xh = net(x)
+    loss = torch.nn.MSELoss()(xh, x)
+    loss.backward()
+    out['out/z'], out['out/x_hat'], out['loss'] = npy(zz), npy(xh), npy(loss)
+    for pname, p in net.named_parameters():
+        grad_summary(out, pname, p.grad)
+    new_sd = net.state_dict()
+    for key in new_sd:
+        if 'running_' in key or 'num_batches' in key:
+            out[f'stat/{key}'] = npy(new_sd[key])
+    optim.step()
+    for pname, p in net.named_parameters():
+        out[f'adam/{pname}'] = npy(p)
+    # checkpoint written by the reference itself (9 -> 6 .mdl files) and the transfer into a Transporter
+    ck = os.path.join(HERE, f'ckpt_{name}')
+    shutil.rmtree(ck, ignore_errors=True)
+    net.save(ck)
+    K = 3
+    tnet = ref_transporter.make(model_type, cin, z, K, transfer_load=ck)
+    for key, v in tnet.state_dict().items():
+        unit, block = key.split('.')[0], key.split('.')[1]
+        transferred = (unit == 'feature' and block != 'out_block') or (unit == 'keypoint' and block != 'out_block') or \
+                      (unit == 'decoder' and block != 'in_block')
+        if transferred:
+            out[f'transfer/{key}'] = npy(v)
+    np.savez_compressed(os.path.join(HERE, f'{name}.npz'), **out)
+    print(name, 'loss', float(loss), 'bytes', os.path.getsize(os.path.join(HERE, f'{name}.npz')))
+
+
+def model_fixture(name, kind, model_type, cin, z, K, n, h, w, seed, lo, hi, with_mask, adam=False, combine_mode='max'):
     rng = np.random.default_rng(seed)
     if kind == 'transporter':
-        net = ref_transporter.make(model_type, cin, z, K)
+        net = ref_transporter.make(model_type, cin, z, K, combine_mode=combine_mode)
         ops = O.transporter_ops(model_type, cin, z, K)
     else:
         net = build_ref_keynet(model_type, cin, z, K)
@@ -178,6 +234,11 @@ def model_fixture(name, kind, model_type, cin, z, K, n, h, w, seed, lo, hi, with
 
 
 if __name__ == '__main__':
+    only = sys.argv[1:]          # e.g. `make_golden.py modes` regenerates only the SURVEY 8f fixtures
+    if only:
+        known_answers = functional_fixture = tps_fixture = lambda: None
+        _mf = model_fixture
+        model_fixture = lambda name, *a, **k: _mf(name, *a, **k) if ('loop' in name or 'sum' in name) else None
     known_answers()
     functional_fixture()
     tps_fixture()
@@ -190,4 +251,11 @@ if __name__ == '__main__':
     # a pooled + upsampled small net (exercises 'M' right after in_block and 'U' chains)
     model_fixture('keynet_pong_mu', 'keynet', 'VGG_PONG', 1, 8, 3, 3, 24, 16, 104, -1.0, 1.0, with_mask=False,
                   adam=True)
+    # the non-default combine modes and the auto-encoder pre-training / transfer path
+    if not only or 'modes' in only:
+        model_fixture('transporter_pong_loop', 'transporter', 'VGG_PONG_LAYERNECK', 1, 16, 4, 2, 36, 28, 105, -1.0, 1.0,
+                      with_mask=False, combine_mode='loop')
+        model_fixture('transporter_pong_sum', 'transporter', 'VGG_PONG_LAYERNECK', 1, 16, 4, 2, 36, 28, 106, -1.0, 1.0,
+                      with_mask=False, combine_mode='sum_and_clamp')
+        autoencoder_fixture('autoencoder_pong', 'VGG_PONG', 1, 8, 3, 24, 16, 107, -1.0, 1.0)
     print('done')

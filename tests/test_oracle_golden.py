@@ -125,3 +125,73 @@ def test_model_step(golden, name, kind, model_type):
                 close(sd[key[5:]], g[key], 1.0, key, scale=2.001e-4)
             else:
                 close(sd[key[5:]], g[key], 0.02, key, scale=1e-4)      # within 2 % of one lr-sized step
+
+
+# ---- SURVEY 8f widening: non-default combine modes, auto-encoder pre-training, checkpoint transfer ----------------
+def _check_step(g, sd, loss, outs, names, tol=2e-5):
+    for nm, r in zip(names, outs):
+        if nm == 'p':
+            close(r[0], g['out/p_h'], tol, 'p_h'); close(r[1], g['out/p_w'], tol, 'p_w')
+        else:
+            close(r, g[f'out/{nm}'], tol, nm)
+    close(loss, g['loss'], tol, 'loss')
+    for key in g:
+        if key.startswith('grad/'):
+            sib = bn_sibling(key, g)
+            close(sd[key[5:]].grad, g[key], 2e-4, key, scale=None if sib is None else np.abs(g[sib]).max())
+        elif key.startswith('stat/'):
+            close(sd[key[5:]], g[key], tol, key)
+
+
+@pytest.mark.parametrize('name,mode', [('transporter_pong_loop', 'loop'), ('transporter_pong_sum', 'sum_and_clamp')])
+def test_transporter_combine_modes(golden, name, mode):
+    """models/transporter.py:41-50 ('loop', 'sum_and_clamp') against the reference's own forward/backward."""
+    g = golden(name)
+    cin, z, K, n, h, w, seed = (int(v) for v in g['meta'])
+    sd = O.init_state_dict(O.transporter_ops('VGG_PONG_LAYERNECK', cin, z, K), seed)
+    tr = O.OracleTrainer('transporter', 'VGG_PONG_LAYERNECK', cin, z, K, sd, mode=mode)
+    loss, out = tr.step(torch.from_numpy(g['a']), torch.from_numpy(g['b']))
+    _check_step(g, sd, loss, out, ['x_hat', 'phi', 'k', 'm', 'p', 'heat', 'mask_s', 'mask_t'])
+
+
+def test_autoencoder_step(golden):
+    """autoencode.py:84-96 (MSE of the reconstruction against the input) against the reference."""
+    g = golden('autoencoder_pong')
+    cin, z, _, n, h, w, seed = (int(v) for v in g['meta'])
+    sd = O.init_state_dict(O.autoencoder_ops('VGG_PONG', cin, z), seed)
+    tr = O.OracleTrainer('autoencoder', 'VGG_PONG', cin, z, 0, sd)
+    x = torch.from_numpy(g['a'])
+    loss, out = tr.step(x, x)
+    _check_step(g, sd, loss, out, ['x_hat', 'z'])
+
+
+def test_reference_checkpoint_interop(golden, tmp_path):
+    """The .mdl files written by the reference's AutoEncoder.save (tests/golden/ckpt_autoencoder_pong, made by
+    make_golden.py) load into keypoints_b200's modules, transfer into a Transporter exactly as
+    models/transporter.py:71-75 does, and a save/load round trip through our modules preserves them."""
+    import os
+    from conftest import GOLDEN
+    from keypoints_b200.models import autoencoder, transporter
+    g = golden('autoencoder_pong')
+    cin, z, _, n, h, w, seed = (int(v) for v in g['meta'])
+    ck = os.path.join(GOLDEN, 'ckpt_autoencoder_pong')
+    net = autoencoder.make('VGG_PONG', cin, z, load=ck)
+    sd = net.state_dict()
+    for key in g:
+        if key.startswith('adam/'):                       # the checkpoint was written after the Adam step
+            close(sd[key[5:]], g[key], 1e-7, key)
+    t = transporter.make('VGG_PONG', cin, z, 3, transfer_load=ck)
+    tsd = t.state_dict()
+    moved = [k for k in g if k.startswith('transfer/')]
+    assert len(moved) > 20
+    for key in moved:
+        close(tsd[key[9:]].float(), g[key], 1e-7, key)
+    net.save(str(tmp_path / 'ours'))
+    ref_files = sorted(os.path.relpath(os.path.join(d, f), ck) for d, _, fs in os.walk(ck) for f in fs)
+    our_files = sorted(os.path.relpath(os.path.join(d, f), tmp_path / 'ours') for d, _, fs in os.walk(tmp_path / 'ours') for f in fs)
+    assert ref_files == our_files
+    for f in ref_files:
+        a, b = torch.load(os.path.join(ck, f)), torch.load(str(tmp_path / 'ours' / f))
+        assert list(a.keys()) == list(b.keys())
+        for k in a:
+            assert torch.equal(a[k], b[k]), (f, k)
