@@ -272,9 +272,17 @@ def main():
         tc_fl = sum(agg[k][2] for k in ('kp_conv_tc', 'kp_conv_wgrad_tc') if k in agg)
         tc_n = sum(agg[k][0] for k in ('kp_conv_tc', 'kp_conv_wgrad_tc') if k in agg)
         ach = tc_fl / (tc_ms / 1e3) / 1e12 if tc_ms > 0 else 0.0
+        traffic, traffic_note = None, None
+        tpath = os.path.join(ROOT, 'profiles', 'r1_tc_traffic.json')
+        if args.workload == 'keynet_F_128_K10' and B == 64 and os.path.exists(tpath):
+            tj = json.load(open(tpath))
+            traffic = tj['bytes_per_launch']
+            traffic_note = (f"dram read+write bytes per launch, mean over the {tj['launches']} tcgen05 launches of one step "
+                            f"(ncu, profiles/r1_tc_traffic.md); algorithmic minimum 219.3 MB/pair x 64 / {tj['launches']} = "
+                            f"{219.3e6 * 64 / tj['launches'] / 1e6:.0f} MB per launch (SURVEY 8d)")
         roof = {'bound': 'tensor', 'kernel': 'conv_tc_k + wgrad_tc_k (tcgen05 implicit-GEMM convs)', 'achieved': ach,
                 'peak': pk['tf_sustained'], 'peak_source': pk['source'] + ' bf16_tflops_sustained', 'unit': 'TFLOP/s',
-                'frac': ach / pk['tf_sustained'], 'traffic': None, 'launches_per_step': tc_n,
+                'frac': ach / pk['tf_sustained'], 'traffic': traffic, 'traffic_note': traffic_note, 'launches_per_step': tc_n,
                 'share_of_step': tc_ms / total_ms if total_ms else None,
                 'step_frac_of_roofline': (value / world) * GFLOP_PER_PAIR[args.workload] / 1e3 / pk['tf_sustained'],
                 'per_call_ms': {k: round(v[1], 4) for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1])}}

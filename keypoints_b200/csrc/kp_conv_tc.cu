@@ -642,6 +642,247 @@ conv_tc_pair_k(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// 3x3 variant with A-halo reuse.  The three horizontal taps of one kernel row read activation rows that differ by ONE
+// flat pixel, so a single TMA box of 128 + 2 (padded to 136) pixel rows serves all three: the MMA of tap tx simply starts tx
+// rows (tx * 128 B) into the tile.  That is legal because the 128-byte swizzle is a function of the absolute shared-memory
+// address bits (chunk ^= (addr >> 7) & 7) for TMA and UMMA alike - measured on B200 with scripts/exp_umma_shift.cu: every
+// row shift 0..7 is exact with the descriptor's base-offset field left at 0 (and wrong if it is set).  Activation traffic
+// from L2 into shared memory drops 3x (the weight tiles are unchanged), which is what bounds the 64- and 128-channel
+// layers at 128x128.  Two rings: AS slots of 18 KB for the activation tiles (one per kernel row and 64-channel chunk),
+// BS slots for the per-tap weight half-tiles.
+// ------------------------------------------------------------------------------------------------
+constexpr int A3_ROWS = 136;
+constexpr int A3_BYTES = A3_ROWS * 128;        // 17408 bytes landed by TMA
+constexpr int A3_SLOT = 18432;                 // slot pitch (multiple of 1024)
+
+template <int BN, int AS, int BS>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(320, 1)
+conv_tc_pair3_k(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmO, const ConvTcParams p) {
+    constexpr int B_BYTES = (BN / 2) * 128;                    // this CTA's half of the weight tile
+    constexpr int RING_BYTES = AS * A3_SLOT + BS * B_BYTES;
+    constexpr int NBAR = 2 * AS + 2 * BS + 4;                  // a_full, a_empty, b_full, b_empty, tfull[2], tempty[2]
+    constexpr int AFULL = 0, AEMPTY = AS, BFULL = 2 * AS, BEMPTY = 2 * AS + BS, TFULL = 2 * AS + 2 * BS, TEMPTY = TFULL + 2;
+    constexpr int EPI_FLOATS = 8 * 32 * 17 + 4 * 2 * BN;   // per-warp 32x16 transpose tiles, per-lane-group running column sums
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* gen_base = smem_raw + (base - smem_u32(smem_raw));
+    const uint32_t slab = base + RING_BYTES;                 // 2 x SLAB_BYTES, 1024-byte aligned
+    uint8_t* slab_gen = gen_base + RING_BYTES;
+    float* epi = reinterpret_cast<float*>(gen_base + RING_BYTES + 2 * SLAB_BYTES);
+    const uint32_t bars = base + RING_BYTES + 2 * SLAB_BYTES + EPI_FLOATS * 4;   // full[S], empty[S], tfull[2], tempty[2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gen_base + RING_BYTES + 2 * SLAB_BYTES + EPI_FLOATS * 4 + 8 * NBAR);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const bool leader = rank == 0;
+    const int kchunks = p.Cin / 64;
+    const int num_kb = p.taps * kchunks;
+    const int num_m = (int)((p.Q + 255) / 256);                 // pair tiles of 256 pixels
+    const int total = num_m * (p.Cout / BN);
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmA);
+        tma_prefetch_desc(&tmB);
+        tma_prefetch_desc(&tmO);
+        for (int i = 0; i < 2 * AS + 2 * BS + 2; ++i) mbar_init(bars + 8 * i, 1);
+        for (int b = 0; b < 2; ++b) mbar_init(bars + 8 * (TEMPTY + b), 2);   // tmem empty: one arrive from each CTA's epilogue
+        fence_barrier_init();
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(2 * BN) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    if (threadIdx.x >= 64) {
+        float* wsum0 = epi + 8 * 32 * 17;
+        for (int i = threadIdx.x - 64; i < 4 * 2 * BN; i += 256) wsum0[i] = 0.f;
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();                                         // both CTAs' barriers are initialised before any remote signal
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const int nclusters = gridDim.x >> 1, cid = blockIdx.x >> 1;
+
+    if (warp == 0) {
+        if (elect_one()) {
+            int ia = 0, ib = 0;
+            for (int t = cid; t < total; t += nclusters) {
+                const int n_t = t / num_m, m_t = t - n_t * num_m;
+                const long long q0 = (long long)m_t * 256 + rank * 128;
+                const int n0 = n_t * BN + rank * (BN / 2);
+                for (int ty = 0; ty < 3; ++ty)
+                    for (int kc = 0; kc < kchunks; ++kc) {
+                        const int sa_i = ia % AS, pa = (ia / AS) & 1;
+                        ++ia;
+                        mbar_wait(bars + 8 * (AEMPTY + sa_i), pa ^ 1);
+                        const uint32_t afull = bars + 8 * (AFULL + sa_i);
+                        if (leader) mbar_expect_tx(afull, 2 * A3_BYTES);
+                        tma_load_2d_pair(base + sa_i * A3_SLOT, &tmA, kc * 64, (int)(q0 + p.shift[3 * ty]), afull);
+                        for (int tx = 0; tx < 3; ++tx) {
+                            const int sb_i = ib % BS, pb = (ib / BS) & 1;
+                            ++ib;
+                            mbar_wait(bars + 8 * (BEMPTY + sb_i), pb ^ 1);
+                            const uint32_t bfull = bars + 8 * (BFULL + sb_i);
+                            if (leader) mbar_expect_tx(bfull, 2 * B_BYTES);
+                            tma_load_2d_pair(base + AS * A3_SLOT + sb_i * B_BYTES, &tmB, kc * 64, (3 * ty + tx) * p.Cout + n0, bfull);
+                        }
+                    }
+            }
+        }
+    } else if (warp == 1) {
+        if (leader && elect_one()) {
+            constexpr uint32_t idesc = make_idesc_m256(BN);
+            int ia = 0, ib = 0, lt = 0;
+            for (int t = cid; t < total; t += nclusters, ++lt) {
+                const int buf = lt & 1;
+                mbar_wait(bars + 8 * (TEMPTY + buf), ((lt >> 1) & 1) ^ 1);
+                tc_fence_after();
+                const uint32_t dcol = tmem_base + buf * BN;
+                uint32_t first = 1;
+                for (int ty = 0; ty < 3; ++ty)
+                    for (int kc = 0; kc < kchunks; ++kc) {
+                        const int sa_i = ia % AS, pa = (ia / AS) & 1;
+                        ++ia;
+                        mbar_wait(bars + 8 * (AFULL + sa_i), pa);
+                        const uint32_t sa = base + sa_i * A3_SLOT;
+                        for (int tx = 0; tx < 3; ++tx) {
+                            const int sb_i = ib % BS, pb = (ib / BS) & 1;
+                            ++ib;
+                            mbar_wait(bars + 8 * (BFULL + sb_i), pb);
+                            tc_fence_after();
+                            const uint64_t ad = make_desc(sa + tx * 128, 16, 1024);
+                            const uint64_t bd = make_desc(base + AS * A3_SLOT + sb_i * B_BYTES, 16, 1024);
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) umma_bf16_pair(dcol, ad + 2 * k, bd + 2 * k, idesc, (first && k == 0) ? 0u : 1u);
+                            first = 0;
+                            umma_commit_pair(bars + 8 * (BEMPTY + sb_i));
+                        }
+                        umma_commit_pair(bars + 8 * (AEMPTY + sa_i));
+                    }
+                umma_commit_pair(bars + 8 * (TFULL + buf));
+            }
+        }
+    } else {
+        const int wq = warp & 3;
+        const int row = wq * 32 + lane;
+        const int et = threadIdx.x - 64;                       // 0..255: 8 epilogue warps, 2 per TMEM lane group
+        const int half = (warp - 2) >> 2;                      // which interleaved set of 32-column chunks
+        float* tile = epi + (warp - 2) * (32 * 17);
+        float* wsum_all = epi + 8 * 32 * 17;                   // [4 lane groups][2*BN] running column sums of this CTA
+        float* wsum = wsum_all + wq * (2 * BN);
+        int lt = 0, cur_n = -1, slabs = 0;
+        auto flush = [&](int n_tile) {                         // all 128 epilogue threads
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            for (int ch = et; ch < BN; ch += 256) {
+                float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+                for (int w = 0; w < 4; ++w) {
+                    s1 += wsum_all[w * 2 * BN + ch];
+                    s2 += wsum_all[w * 2 * BN + BN + ch];
+                    wsum_all[w * 2 * BN + ch] = 0.f;
+                    wsum_all[w * 2 * BN + BN + ch] = 0.f;
+                }
+                atomicAdd(&p.stats[n_tile * BN + ch], (double)s1);
+                atomicAdd(&p.stats[p.Cout + n_tile * BN + ch], (double)s2);
+            }
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+        };
+        for (int t = cid; t < total; t += nclusters, ++lt) {
+            const int n_t = t / num_m, m_t = t - n_t * num_m;
+            const int n0 = n_t * BN;
+            const int buf = lt & 1;
+            if (p.stats && cur_n >= 0 && cur_n != n_t) flush(cur_n);
+            cur_n = n_t;
+            const long long q_tile = (long long)m_t * 256 + rank * 128;
+            const long long q = q_tile + row;
+            bool valid = q < p.Q;
+            if (valid && p.stats) {
+                int x = (int)(q % p.PW);
+                int y = (int)((q / p.PW) % p.PH);
+                valid = x < p.VW && y < p.VH;
+            }
+            mbar_wait(bars + 8 * (TFULL + buf), (lt >> 1) & 1);
+            tc_fence_after();
+#pragma unroll 1
+            for (int c = half; c < BN / 32; c += 2) {
+                uint32_t r[32];
+                tmem_ld32(tmem_base + ((uint32_t)(wq * 32) << 16) + buf * BN + c * 32, r);
+                float v[32];
+                if (p.bias && ((reinterpret_cast<uintptr_t>(p.bias) & 15) == 0)) {
+                    const float4* bp = reinterpret_cast<const float4*>(p.bias + n0 + c * 32);
+#pragma unroll
+                    for (int g = 0; g < 8; ++g) {
+                        const float4 bv = bp[g];
+                        v[4 * g] = __uint_as_float(r[4 * g]) + bv.x; v[4 * g + 1] = __uint_as_float(r[4 * g + 1]) + bv.y;
+                        v[4 * g + 2] = __uint_as_float(r[4 * g + 2]) + bv.z; v[4 * g + 3] = __uint_as_float(r[4 * g + 3]) + bv.w;
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) + (p.bias ? p.bias[n0 + c * 32 + j] : 0.f);
+                }
+                {   // stage this warp's 32 rows x 32 columns into the 128-row x 64-column slab (128-byte swizzle: the
+                    // 16-byte chunk j of row r lives at chunk j ^ (r & 7)), then ONE TMA store writes the slab
+                    const int sb = slabs & 1;
+                    if (et == 0) bulk_wait_read<1>();          // the store that last read this buffer is done with it
+                    asm volatile("bar.sync 1, 256;" ::: "memory");
+                    uint8_t* drow = slab_gen + sb * SLAB_BYTES + row * 128;
+#pragma unroll
+                    for (int g = 0; g < 4; ++g) {
+                        uint4 u;
+                        __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) h[e] = __floats2bfloat162_rn(v[g * 8 + 2 * e], v[g * 8 + 2 * e + 1]);
+                        *reinterpret_cast<uint4*>(drow + (((half * 4 + g) ^ (row & 7)) << 4)) = u;
+                    }
+                    fence_async_smem();
+                    asm volatile("bar.sync 1, 256;" ::: "memory");
+                    if (et == 0) tma_store_2d(&tmO, slab + sb * SLAB_BYTES, n0 + (c >> 1) * 64, (int)q_tile);
+                    ++slabs;
+                }
+                if (p.stats) {
+                    // column sums over the warp's 32 rows, 16 columns at a time through a 32x17 shared tile: lane l sums
+                    // column (l & 15) over rows [16 (l >> 4), +16), the two row halves are combined with one shuffle
+#pragma unroll
+                    for (int hc = 0; hc < 2; ++hc) {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) tile[lane * 17 + j] = valid ? v[hc * 16 + j] : 0.f;
+                        __syncwarp();
+                        float s1 = 0.f, s2 = 0.f;
+                        const int col = lane & 15, r0 = (lane >> 4) * 16;
+#pragma unroll
+                        for (int rr = 0; rr < 16; ++rr) {
+                            float tv = tile[(r0 + rr) * 17 + col];
+                            s1 += tv;
+                            s2 = fmaf(tv, tv, s2);
+                        }
+                        s1 += __shfl_xor_sync(0xffffffffu, s1, 16);
+                        s2 += __shfl_xor_sync(0xffffffffu, s2, 16);
+                        if (lane < 16) {
+                            wsum[c * 32 + hc * 16 + col] += s1;
+                            wsum[BN + c * 32 + hc * 16 + col] += s2;
+                        }
+                        __syncwarp();
+                    }
+                }
+            }
+            // every epilogue thread has drained its TMEM rows: release the accumulator buffer to the MMA warp
+            tc_fence_before();
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            if (et == 0) mbar_arrive_leader(bars + 8 * (TEMPTY + buf));
+        }
+        if (p.stats && cur_n >= 0) flush(cur_n);
+        if (et == 0) bulk_wait_all();                          // every TMA store has completed before the CTA exits
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();                                         // no remote signal may target a CTA that has exited
+    if (warp == 1) {
+        __syncwarp();
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(2 * BN) : "memory");
+    }
+}
+
 template <int BN, int STAGES>
 __global__ void __launch_bounds__(192, 1)
 wgrad_tc_persist_k(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const WgradTcParams p,
@@ -1006,6 +1247,25 @@ static int launch_conv_pair(cudaStream_t st, const CUtensorMap& a, const CUtenso
     return KP_OK;
 }
 
+template <int BN, int AS, int BS>
+static int launch_conv_pair3(cudaStream_t st, const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& o, const ConvTcParams& p) {
+    constexpr int smem = AS * A3_SLOT + BS * (BN / 2) * 128 + 2 * SLAB_BYTES + (8 * 32 * 17 + 4 * 2 * BN) * 4 +
+                         8 * (2 * AS + 2 * BS + 4) + 16 + 1024;
+    static_assert(smem <= 227 * 1024, "shared memory budget");
+    static bool attr_done = false;
+    if (!attr_done) {
+        KP_CUDA(cudaFuncSetAttribute(conv_tc_pair3_k<BN, AS, BS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        attr_done = true;
+    }
+    long long total = ((p.Q + 255) / 256) * (p.Cout / BN);
+    int clusters = kp_sm_count() / 2;
+    if (clusters > total) clusters = (int)total;
+    if (clusters < 1) clusters = 1;
+    conv_tc_pair3_k<BN, AS, BS><<<2 * clusters, 320, smem, st>>>(a, b, o, p);
+    KP_LAUNCH_CHECK();
+    return KP_OK;
+}
+
 template <int BN, int STAGES>
 static int launch_wgrad_pair(cudaStream_t st, const CUtensorMap& a, const CUtensorMap& b, const WgradTcParams& p, int taps) {
     constexpr int smem = STAGES * (2 * 8192 + (BN / 128) * 8192) + 8 * (2 * STAGES + 4) + 16 + 1024;
@@ -1069,6 +1329,18 @@ extern "C" int kp_conv_tc(kp_stream stream, const void* in_bf16, int64_t Q, int 
         CUtensorMap tbh;                                       // each CTA of the pair loads half of the weight tile
         rc = make_map(&tbh, wt_bf16, (long long)taps * Cout, Cin, BN / 2);
         if (rc) return rc;
+        static int halo_on = -1;
+        if (halo_on < 0) { const char* e = getenv("KP_TC_HALO"); halo_on = (e && e[0] == '0') ? 0 : 1; }
+        bool regular = taps == 9;                              // shift[3 ty + tx] = shift[3 ty] + tx
+        for (int t = 0; regular && t < 9; ++t) regular = shifts[t] == shifts[3 * (t / 3)] + (t % 3);
+        if (halo_on && regular) {
+            CUtensorMap ta3;                                   // 128 + 2 pixel rows (padded to 136) per kernel row
+            rc = make_map(&ta3, in_bf16, Q, Cin, A3_ROWS);
+            if (rc) return rc;
+            if (BN == 256) return launch_conv_pair3<256, 3, 6>(st, ta3, tbh, to, p);
+            if (BN == 128) return launch_conv_pair3<128, 4, 8>(st, ta3, tbh, to, p);
+            return launch_conv_pair3<64, 4, 9>(st, ta3, tbh, to, p);
+        }
         if (BN == 256) return launch_conv_pair<256, 5>(st, ta, tbh, to, p);
         if (BN == 128) return launch_conv_pair<128, 7>(st, ta, tbh, to, p);
         return launch_conv_pair<64, 8>(st, ta, tbh, to, p);

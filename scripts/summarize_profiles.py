@@ -57,18 +57,18 @@ def launches():
 
 def reports():
     lines = [f'# ncu --set full summaries ({TAG})\n',
-             'Captured with `ncu --set full --clock-control none --import-source on -k regex:<kernel> ... python bench.py --steps 1 '
-             '--warmup 3 --no-graph ...` on one B200; values per launch.\n']
-    for f in sorted(os.listdir(os.path.join(ROOT, 'gpurun_out'))):
-        if not f.endswith('.ncu-rep') or not f.startswith('prof_'):
+             'Captured by `scripts/profile_round.sh` (`ncu --set full --clock-control none -k regex:<kernel> ... python bench.py '
+             '--steps 1 --warmup 3 --no-graph ...`) on one B200; values per launch.  The raw pages are exported on the GPU box '
+             '(`ncu -i <rep> --page raw --csv`) because gpurun returns at most 64 MiB.\n']
+    gdir = os.path.join(ROOT, 'gpurun_out')
+    for f in sorted(os.listdir(gdir)):
+        if not (f.startswith('prof_') and f.endswith('.raw.csv')):
             continue
-        out = subprocess.run(['ncu', '-i', os.path.join(ROOT, 'gpurun_out', f), '--page', 'raw', '--csv'], capture_output=True,
-                             text=True).stdout
-        rows = list(csv.reader(out.splitlines()))
+        rows = list(csv.reader(open(os.path.join(gdir, f))))
         if len(rows) < 3:
             continue
         hdr, units = rows[0], rows[1]
-        lines.append(f'\n## {f}\n')
+        lines.append(f'\n## {f[:-8]}\n')
         for r in rows[2:]:
             name = r[hdr.index('Kernel Name')][:110]
             lines.append(f'\n`{name}`\n\n| metric | value |\n|---|---|\n')
@@ -80,24 +80,63 @@ def reports():
         fh.writelines(lines)
 
 
+def traffic():
+    """DRAM bytes of every tcgen05 conv launch of one step -> profiles/<tag>_tc_traffic.json (bench.py roofline.traffic)."""
+    import json
+    path = os.path.join(ROOT, 'gpurun_out', 'tc_traffic.csv')
+    if not os.path.exists(path):
+        return
+    rows = list(csv.reader(open(path)))
+    hi = next(i for i, r in enumerate(rows) if r and r[0] == 'ID')
+    hdr = rows[hi]
+    ki, mi, vi, ui, ii = (hdr.index(k) for k in ('Kernel Name', 'Metric Name', 'Metric Value', 'Metric Unit', 'ID'))
+    per = collections.OrderedDict()
+    for r in rows[hi + 1:]:
+        if len(r) <= vi:
+            continue
+        d = per.setdefault(r[ii], {'kernel': r[ki].split('(')[0].replace('void ', '').replace('<unnamed>::', '')})
+        v = float(r[vi].replace(',', ''))
+        u = r[ui]
+        scale = {'byte': 1, 'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9, 'ns': 1e-6, 'us': 1e-3, 'ms': 1.0}.get(u, 1)
+        d[r[mi]] = v * scale
+    launches = list(per.values())
+    tot_r = sum(l.get('dram__bytes_read.sum', 0) for l in launches)
+    tot_w = sum(l.get('dram__bytes_write.sum', 0) for l in launches)
+    tot_t = sum(l.get('gpu__time_duration.sum', 0) for l in launches)
+    out = {'launches': len(launches), 'dram_bytes_read': tot_r, 'dram_bytes_write': tot_w, 'time_ms_under_ncu': tot_t,
+           'bytes_per_launch': (tot_r + tot_w) / max(len(launches), 1),
+           'how': 'ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum -k regex:conv_tc|wgrad_tc over the 69 tcgen05 launches '
+                  'of one eager step (scripts/profile_round.sh), KeyNet F 128x128 K=10 batch 64'}
+    json.dump(out, open(os.path.join(OUT, f'{TAG}_tc_traffic.json'), 'w'), indent=1)
+    with open(os.path.join(OUT, f'{TAG}_tc_traffic.md'), 'w') as fh:
+        fh.write(f'# DRAM traffic of the tcgen05 conv launches of one step ({TAG})\n\n{out["how"]}\n\n')
+        fh.write(f'{len(launches)} launches: read {tot_r / 1e9:.3f} GB, written {tot_w / 1e9:.3f} GB, {tot_t:.3f} ms under ncu\n\n')
+        fh.write('| kernel | ms | read MB | write MB |\n|---|---:|---:|---:|\n')
+        for l in launches:
+            fh.write(f"| `{l['kernel'][:60]}` | {l.get('gpu__time_duration.sum', 0):.4f} | {l.get('dram__bytes_read.sum', 0) / 1e6:.1f} | "
+                     f"{l.get('dram__bytes_write.sum', 0) / 1e6:.1f} |\n")
+
+
 def sass():
     so = os.path.join(ROOT, 'keypoints_b200', 'lib', 'libkeypoints_b200.so')
     txt = subprocess.run(['cuobjdump', '-sass', so], capture_output=True, text=True).stdout
     c = collections.Counter()
     import re
-    for m in re.finditer(r'\b(UTCHMMA[.A-Z0-9]*|UTMALDG[.A-Z0-9_]*|UTMAPF[.A-Z0-9_]*|UTCBAR[.A-Z0-9_]*|LDTM[.A-Z0-9_]*|HMMA[.A-Z0-9_]*|REDG[.A-Z0-9_]*|SYNCS[.A-Z0-9_]*)', txt):
+    for m in re.finditer(r'\b(UTCHMMA[.A-Z0-9]*|UTMALDG[.A-Z0-9_]*|UTMAPF[.A-Z0-9_]*|UTCBAR[.A-Z0-9_]*|LDTM[.A-Z0-9_]*|HMMA[.A-Z0-9_]*|REDG[.A-Z0-9_]*|SYNCS[.A-Z0-9_]*|UBLKCP[.A-Z0-9_]*|FFMA2[.A-Z0-9_]*|UTMASTG[.A-Z0-9_]*)', txt):
         c[m.group(1)] += 1
     with open(os.path.join(OUT, f'{TAG}_sass_evidence.md'), 'w') as fh:
         fh.write(f'# SASS mnemonics in libkeypoints_b200.so ({TAG})\n\n`cuobjdump -sass keypoints_b200/lib/libkeypoints_b200.so`\n\n| mnemonic | count |\n|---|---:|\n')
         for k, v in sorted(c.items()):
             fh.write(f'| {k} | {v} |\n')
         fh.write('\nUTCHMMA = tcgen05.mma (`.2CTA` = cta_group::2), UTMALDG = cp.async.bulk.tensor (TMA), LDTM = tcgen05.ld, '
-                 'UTCBAR = tcgen05.commit; no HMMA (legacy mma.sync) anywhere.\n')
+                 'UTCBAR = tcgen05.commit, UTMASTG = TMA store (conv epilogue), UBLKCP = cp.async.bulk (BatchNorm streaming kernels), '
+                 'FFMA2 = packed fp32x2 math; HMMA (mma.sync) only in the first-layer Cin<=3 kernels (kp_conv_thin_mma.cu).\n')
 
 
 if __name__ == '__main__':
     os.makedirs(OUT, exist_ok=True)
     launches()
     reports()
+    traffic()
     sass()
     print(os.listdir(OUT))
