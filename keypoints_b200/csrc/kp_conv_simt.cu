@@ -531,6 +531,13 @@ extern "C" int kp_conv_simt(kp_stream stream, const kp_view* in, const float* wk
     dim3 grid((unsigned)((M + BM - 1) / BM), (unsigned)((Cout + BN - 1) / BN), 1);
     const int KKt = ks * ks * Cin;
     const bool out2 = out->sc == 1 && (((uintptr_t)out->ptr) % 8) == 0 && out->sx % 2 == 0 && out->sy % 2 == 0 && out->sn % 2 == 0;
+    if (thin_mma_enabled() && ks == 1 && !stats && OH == IH && OW == IW && M < (1LL << 31)) {
+        // 1x1 head: forward (wide -> <= 4) or its data gradient (<= 4 -> wide); wk is [Cin][Cout] in both cases
+        if (kp_head1x1_ok(in, out, Cin, Cout))
+            return kp_head1x1_fprop((cudaStream_t)stream, in, wk, bias, out, N, OH, OW, Cin, Cout);
+        if (!bias && out->dtype == KP_BF16 && in->dtype == KP_BF16 && kp_head1x1_ok(out, in, Cout, Cin))
+            return kp_head1x1_dgrad((cudaStream_t)stream, in, wk, out, N, OH, OW, Cout, Cin);
+    }
     if (thin_mma_enabled() && out->dtype == KP_BF16 && kp_thin_mma_fprop_ok(in, out, OH, OW, IH, IW, Cin, Cout, ks, off))
         return kp_thin_mma_fprop((cudaStream_t)stream, in, wk, bias, out, stats, N, OH, OW, Cin, Cout);
     if (thin_fast_enabled() && KKt <= THIN_MAX && Cout % 64 == 0 && out2) {      // thin-K: first conv / dgrad of a thin head
@@ -587,6 +594,8 @@ extern "C" int kp_conv_wgrad_simt(kp_stream stream, const kp_view* x, const kp_v
     auto pair_ok = [](const kp_view* v) {
         return v->sc == 1 && (((uintptr_t)v->ptr) % 8) == 0 && v->sx % 2 == 0 && v->sy % 2 == 0 && v->sn % 2 == 0;
     };
+    if (thin_mma_enabled() && ks == 1 && P < (1LL << 31) && dy->dtype == KP_BF16 && kp_head1x1_ok(x, dy, Cin, Cout))
+        return kp_head1x1_wgrad((cudaStream_t)stream, x, dy, dw_oihw, N, H, W, Cin, Cout);
     if (thin_mma_enabled() && dy->dtype == KP_BF16 && kp_thin_mma_wgrad_ok(x, dy, W, Cin, Cout, ks))
         return kp_thin_mma_wgrad((cudaStream_t)stream, x, dy, dw_oihw, N, H, W, Cin, Cout);
     if (thin_fast_enabled() && KK <= THIN_MAX && Cout % 64 == 0 && pair_ok(dy)) {

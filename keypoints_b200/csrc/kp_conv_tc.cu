@@ -1309,7 +1309,16 @@ extern "C" int kp_conv_tc(kp_stream stream, const void* in_bf16, int64_t Q, int 
                      Cin % 64 == 0 && Cout % 64 == 0 && Cin > 0 && Cout > 0,
                  "kp_conv_tc: unsupported shape Q=%lld Cin=%d Cout=%d taps=%d", (long long)Q, Cin, Cout, taps);
     KP_CHECK_ARG(!stats || (PH > 0 && PW > 0), "kp_conv_tc: stats need PH/PW");
-    const int BN = (Cout % 256 == 0) ? 256 : (Cout % 128 == 0 ? 128 : 64);
+    int BN = (Cout % 256 == 0) ? 256 : (Cout % 128 == 0 ? 128 : 64);
+    if (BN == 256) {
+        // wave quantisation: with few pixel tiles (16x16 layers) 256-wide tiles leave the last round of the persistent
+        // CTA pairs mostly idle; 128-wide tiles fill the rounds better
+        const long long mt = (Q + 255) / 256, workers = kp_sm_count() / 2;
+        auto eff = [&](long long tiles) { return (double)tiles / (double)(((tiles + workers - 1) / workers) * workers); };
+        static int q_on = -1;
+        if (q_on < 0) { const char* e = getenv("KP_TC_QUANT"); q_on = (e && e[0] == '0') ? 0 : 1; }
+        if (q_on && eff(mt * (Cout / 256)) < 0.8 && eff(mt * (Cout / 128)) > eff(mt * (Cout / 256)) + 0.08) BN = 128;
+    }
     CUtensorMap ta, tb;
     int rc = make_map(&ta, in_bf16, Q, Cin, 128);
     if (rc) return rc;

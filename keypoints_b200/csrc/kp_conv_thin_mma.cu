@@ -77,9 +77,9 @@ thin_mma_fprop_k(View<bf16> in, const float* __restrict__ wk /*[KK][Cout]*/, con
     const int tiles_per_row = OW >> 4;
     const long long ntiles = (long long)N * OH * tiles_per_row;
     for (long long tile = (long long)blockIdx.x * THIN_WARPS + warp; tile < ntiles; tile += (long long)gridDim.x * THIN_WARPS) {
-        const int xt = (int)(tile % tiles_per_row);
-        const long long r = tile / tiles_per_row;
-        const int y = (int)(r % OH), n = (int)(r / OH);
+        const unsigned tu = (unsigned)tile, r = tu / (unsigned)tiles_per_row;      // 32-bit divisions (tiles < 2^31)
+        const int xt = (int)(tu - r * (unsigned)tiles_per_row);
+        const int n = (int)(r / (unsigned)OH), y = (int)(r - (unsigned)n * (unsigned)OH);
         const int x0 = xt << 4;
         const bf16* pa = in.at(n, y, x0 + g, 0);
         const bf16* pb = pa + 8 * in.sx;
@@ -165,9 +165,9 @@ thin_mma_wgrad_k(View<bf16> in, View<bf16> dy, float* __restrict__ dw, int N, in
     const int tiles_per_row = OW >> 4;
     const long long ntiles = (long long)N * OH * tiles_per_row;
     for (long long tile = (long long)blockIdx.x * THIN_WARPS + warp; tile < ntiles; tile += (long long)gridDim.x * THIN_WARPS) {
-        const int xt = (int)(tile % tiles_per_row);
-        const long long r = tile / tiles_per_row;
-        const int y = (int)(r % OH), n = (int)(r / OH);
+        const unsigned tu = (unsigned)tile, r = tu / (unsigned)tiles_per_row;      // 32-bit divisions (tiles < 2^31)
+        const int xt = (int)(tu - r * (unsigned)tiles_per_row);
+        const int n = (int)(r / (unsigned)OH), y = (int)(r - (unsigned)n * (unsigned)OH);
         const int x0 = xt << 4;
         const bf16* px = in.at(n, y, x0 + 2 * q, 0);
         // gradient rows of the 4 pixels this thread contracts over: channel pairs (2g, 2g+1) of each 16-channel group
@@ -264,6 +264,194 @@ int kp_thin_mma_wgrad(cudaStream_t st, const kp_view* x, const kp_view* dy, floa
     if (blocks > cap) blocks = cap;
     dim3 grid((unsigned)blocks, (unsigned)(Cout / 64), 1);
     thin_mma_wgrad_k<<<grid, THIN_WARPS * 32, 0, st>>>(make_view<bf16>(x), make_view<bf16>(dy), dw, N, H, W, Cin, Cout);
+    KP_LAUNCH_CHECK();
+    return KP_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// 1x1 output head with <= 4 outputs (decoder out_block 64 -> 3 at full resolution): three streaming kernels that move
+// 128 bytes per pixel with 16-byte accesses (8 wide channels per thread).
+//   fprop : y[pix][co]  = b[co] + sum_ci x[pix][ci] w[ci][co]
+//   dgrad : dx[pix][ci] = sum_co dy[pix][co] w[co][ci]
+//   wgrad : dw[co][ci] += sum_pix dy[pix][co] x[pix][ci]
+// ------------------------------------------------------------------------------------------------
+namespace {
+
+__device__ __forceinline__ void unpack8(const uint4& r, float (&f)[8]) {
+    const uint32_t u[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { f[2 * i] = __uint_as_float(u[i] << 16); f[2 * i + 1] = __uint_as_float(u[i] & 0xffff0000u); }
+}
+
+struct PixIdx { int n, y, x; };
+__device__ __forceinline__ PixIdx pix_of(long long p, int H, int W) {      // p < 2^31 (checked by kp_head1x1_ok): 32-bit divisions
+    PixIdx r;
+    const unsigned pu = (unsigned)p;
+    const unsigned q = pu / (unsigned)W;
+    r.x = (int)(pu - q * (unsigned)W);
+    r.n = (int)(q / (unsigned)H);
+    r.y = (int)(q - (unsigned)r.n * (unsigned)H);
+    return r;
+}
+
+// groups of G = Cw / 8 lanes share a pixel; wk: fp32 [Cw][CT]
+template <int CT, typename TO>
+__global__ void __launch_bounds__(256)
+head1x1_fprop_k(View<bf16> in, const float* __restrict__ wk, const float* __restrict__ bias, View<TO> out, int N, int H, int W,
+                int Cw, int g_shift) {
+    const int G = 1 << g_shift;
+    const int gl = threadIdx.x & (G - 1);
+    float w[8][CT];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int c = 0; c < CT; ++c) w[i][c] = wk[(gl * 8 + i) * CT + c];
+    const long long P = (long long)N * H * W;
+    const long long stride = ((long long)gridDim.x * blockDim.x) >> g_shift;
+    // every lane of a warp runs the same number of iterations (the shuffles below are warp-wide)
+    const long long first = ((long long)blockIdx.x * blockDim.x + (threadIdx.x & ~31)) >> g_shift;
+    for (long long pb = first; pb < P; pb += stride) {
+        const long long pr = pb + ((threadIdx.x & 31) >> g_shift);
+        const bool valid = pr < P;
+        const long long p = valid ? pr : P - 1;
+        const PixIdx q = pix_of(p, H, W);
+        float f[8], acc[CT];
+        unpack8(*reinterpret_cast<const uint4*>(in.at(q.n, q.y, q.x, gl * 8)), f);
+#pragma unroll
+        for (int c = 0; c < CT; ++c) {
+            float a = 0.f;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) a = fmaf(f[i], w[i][c], a);
+            for (int o = 1; o < G; o <<= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+            acc[c] = a;
+        }
+        if (gl == 0 && valid) {
+#pragma unroll
+            for (int c = 0; c < CT; ++c) from_f(out.at(q.n, q.y, q.x, c), acc[c] + (bias ? bias[c] : 0.f));
+        }
+    }
+}
+
+// wd: fp32 [CT][Cw]
+template <int CT>
+__global__ void __launch_bounds__(256)
+head1x1_dgrad_k(View<bf16> dy, const float* __restrict__ wd, View<bf16> dx, int N, int H, int W, int Cw, int g_shift) {
+    const int G = 1 << g_shift;
+    const int gl = threadIdx.x & (G - 1);
+    float w[CT][8];
+#pragma unroll
+    for (int c = 0; c < CT; ++c)
+#pragma unroll
+        for (int i = 0; i < 8; ++i) w[c][i] = wd[c * Cw + gl * 8 + i];
+    const long long P = (long long)N * H * W;
+    const long long stride = ((long long)gridDim.x * blockDim.x) >> g_shift;
+    for (long long p = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> g_shift; p < P; p += stride) {
+        const PixIdx q = pix_of(p, H, W);
+        float g[CT];
+#pragma unroll
+        for (int c = 0; c < CT; ++c) g[c] = to_f(*dy.at(q.n, q.y, q.x, c));
+        float o[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            float a = 0.f;
+#pragma unroll
+            for (int c = 0; c < CT; ++c) a = fmaf(g[c], w[c][i], a);
+            o[i] = a;
+        }
+        uint4 u;
+        u.x = pack_bf16(o[0], o[1]); u.y = pack_bf16(o[2], o[3]); u.z = pack_bf16(o[4], o[5]); u.w = pack_bf16(o[6], o[7]);
+        *reinterpret_cast<uint4*>(dx.at(q.n, q.y, q.x, gl * 8)) = u;
+    }
+}
+
+template <int CT>
+__global__ void __launch_bounds__(256)
+head1x1_wgrad_k(View<bf16> x, View<bf16> dy, float* __restrict__ dw, int N, int H, int W, int Cw, int g_shift) {
+    __shared__ float red[CT * 512];
+    const int G = 1 << g_shift;
+    const int gl = threadIdx.x & (G - 1);
+    float acc[CT][8];
+#pragma unroll
+    for (int c = 0; c < CT; ++c)
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[c][i] = 0.f;
+    const long long P = (long long)N * H * W;
+    const long long stride = ((long long)gridDim.x * blockDim.x) >> g_shift;
+    for (long long p = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> g_shift; p < P; p += stride) {
+        const PixIdx q = pix_of(p, H, W);
+        float f[8], g[CT];
+        unpack8(*reinterpret_cast<const uint4*>(x.at(q.n, q.y, q.x, gl * 8)), f);
+#pragma unroll
+        for (int c = 0; c < CT; ++c) g[c] = to_f(*dy.at(q.n, q.y, q.x, c));
+#pragma unroll
+        for (int c = 0; c < CT; ++c)
+#pragma unroll
+            for (int i = 0; i < 8; ++i) acc[c][i] = fmaf(g[c], f[i], acc[c][i]);
+    }
+    for (int i = threadIdx.x; i < CT * Cw; i += blockDim.x) red[i] = 0.f;
+    __syncthreads();
+#pragma unroll
+    for (int c = 0; c < CT; ++c)
+#pragma unroll
+        for (int i = 0; i < 8; ++i) atomicAdd(&red[c * Cw + gl * 8 + i], acc[c][i]);
+    __syncthreads();
+    for (int i = threadIdx.x; i < CT * Cw; i += blockDim.x) atomicAdd(&dw[i], red[i]);      // dw OIHW [co][ci] for a 1x1 conv
+}
+
+static int head_grid(long long P, int g_shift) {
+    long long threads = P << g_shift;
+    long long blocks = (threads + 255) / 256;
+    const long long cap = (long long)kp_sm_count() * 8;
+    return (int)(blocks < cap ? (blocks < 1 ? 1 : blocks) : cap);
+}
+static int head_shift(int Cw) { int s = 0; while ((8 << s) < Cw) ++s; return s; }
+static bool wide_ok(const kp_view* v, int Cw) {      // bf16, 16-byte aligned 8-channel chunks, 64 <= Cw <= 256 a power of two
+    return v->dtype == KP_BF16 && v->sc == 1 && Cw >= 64 && Cw <= 256 && (Cw & (Cw - 1)) == 0 && (((uintptr_t)v->ptr) % 16) == 0 &&
+           v->sx % 8 == 0 && v->sy % 8 == 0 && v->sn % 8 == 0;
+}
+
+}  // namespace
+
+bool kp_head1x1_ok(const kp_view* wide, const kp_view* thin, int Cw, int Ct) {      // callers pass images of < 2^31 pixels
+    return Ct >= 1 && Ct <= 4 && wide_ok(wide, Cw) && (thin->dtype == KP_BF16 || thin->dtype == KP_F32);
+}
+
+#define KP_HEAD_CT(CTV, CALL) \
+    do { if ((CTV) == 1) { CALL(1); } else if ((CTV) == 2) { CALL(2); } else if ((CTV) == 3) { CALL(3); } else { CALL(4); } } while (0)
+
+int kp_head1x1_fprop(cudaStream_t st, const kp_view* in, const float* wk, const float* bias, const kp_view* out, int N, int H,
+                     int W, int Cw, int Ct) {
+    const int sh = head_shift(Cw), grid = head_grid((long long)N * H * W, sh);
+    if (out->dtype == KP_BF16) {
+#define KP_C(CT) head1x1_fprop_k<CT, bf16><<<grid, 256, 0, st>>>(make_view<bf16>(in), wk, bias, make_view<bf16>(out), N, H, W, Cw, sh)
+        KP_HEAD_CT(Ct, KP_C);
+#undef KP_C
+    } else {
+#define KP_C(CT) head1x1_fprop_k<CT, float><<<grid, 256, 0, st>>>(make_view<bf16>(in), wk, bias, make_view<float>(out), N, H, W, Cw, sh)
+        KP_HEAD_CT(Ct, KP_C);
+#undef KP_C
+    }
+    KP_LAUNCH_CHECK();
+    return KP_OK;
+}
+
+int kp_head1x1_dgrad(cudaStream_t st, const kp_view* dy, const float* wd, const kp_view* dx, int N, int H, int W, int Cw, int Ct) {
+    const int sh = head_shift(Cw), grid = head_grid((long long)N * H * W, sh);
+#define KP_C(CT) head1x1_dgrad_k<CT><<<grid, 256, 0, st>>>(make_view<bf16>(dy), wd, make_view<bf16>(dx), N, H, W, Cw, sh)
+    KP_HEAD_CT(Ct, KP_C);
+#undef KP_C
+    KP_LAUNCH_CHECK();
+    return KP_OK;
+}
+
+int kp_head1x1_wgrad(cudaStream_t st, const kp_view* x, const kp_view* dy, float* dw, int N, int H, int W, int Cw, int Ct) {
+    const int sh = head_shift(Cw);
+    long long blocks = ((((long long)N * H * W) << sh) + 255) / 256;
+    const long long cap = (long long)kp_sm_count() * 4;
+    if (blocks > cap) blocks = cap;
+#define KP_C(CT) head1x1_wgrad_k<CT><<<(int)blocks, 256, 0, st>>>(make_view<bf16>(x), make_view<bf16>(dy), dw, N, H, W, Cw, sh)
+    KP_HEAD_CT(Ct, KP_C);
+#undef KP_C
     KP_LAUNCH_CHECK();
     return KP_OK;
 }

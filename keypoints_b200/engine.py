@@ -213,7 +213,8 @@ def unit_forward(specs: List[ConvSpec], params: List[LayerParams], x_pad: torch.
         else:
             src = cur if s.k == 3 else cur[:, 1:, 1:, :]
             L.call('kp_conv_simt', st, L.view(src), L.ptr(pk['simt_f']), L.ptr(p.b), L.view(y[:, :h, :w, :]),
-                   L.ptr(stats), N, h, w, PH if s.k == 3 else h, PW if s.k == 3 else w, s.cin, s.cout, s.k, 0)
+                   L.ptr(stats), N, h, w, PH if s.k == 3 else h, PW if s.k == 3 else w, s.cin, s.cout, s.k, 0,
+                   tag=f'{tag}{i} {s.cin}->{s.cout}@{h}x{w} k{s.k}')
         c = LayerCtx(x=cur, y=y, h=h, w=w, tc=tc, pack=pk)
         oh, ow = post_dims(s.post, h, w)
         if last:
@@ -306,15 +307,17 @@ def unit_backward(specs: List[ConvSpec], params: List[LayerParams], grads: List[
                        L.ptr(dx), cinp, None, PH, PW, PH, PW, flops=2.0 * N * h * w * s.cin * s.cout * s.k * s.k, tag=f'{tag}{i} {s.cin}->{s.cout}@{h}x{w} k{s.k}')
         else:
             src = c.x if s.k == 3 else c.x[:, 1:, 1:, :]
-            L.call('kp_conv_wgrad_simt', st, L.view(src), L.view(dy_int), L.ptr(g.dw), N, h, w, s.cin, s.cout, s.k)
+            L.call('kp_conv_wgrad_simt', st, L.view(src), L.view(dy_int), L.ptr(g.dw), N, h, w, s.cin, s.cout, s.k,
+                   tag=f'{tag}{i} {s.cin}->{s.cout}@{h}x{w} k{s.k}')
             if want_dx:
                 dx = alloc(f'{tag}.dx{i}', (N, PH, PW, cinp), T, dev, zero=s.k == 1)
                 if s.k == 3:
                     L.call('kp_conv_simt', st, L.view(dy_int), L.ptr(c.pack['simt_d']), None, L.view(dx[..., :s.cin]),
-                           None, N, PH, PW, h, w, s.cout, s.cin, 3, -2)
+                           None, N, PH, PW, h, w, s.cout, s.cin, 3, -2, tag=f'{tag}{i} dgrad {s.cin}->{s.cout}@{h}x{w} k{s.k}')
                 else:
                     L.call('kp_conv_simt', st, L.view(dy_int), L.ptr(c.pack['simt_d']), None,
-                           L.view(dx[:, 1:h + 1, 1:w + 1, :s.cin]), None, N, h, w, h, w, s.cout, s.cin, 1, 0)
+                           L.view(dx[:, 1:h + 1, 1:w + 1, :s.cin]), None, N, h, w, h, w, s.cout, s.cin, 1, 0,
+                           tag=f'{tag}{i} dgrad {s.cin}->{s.cout}@{h}x{w} k{s.k}')
         if want_dx and i > 0:
             dout, dout_pad = dx[..., :specs[i - 1].cout], 1
     return dx if need_dx else None
