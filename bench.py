@@ -158,6 +158,9 @@ def main():
     ap.add_argument('--no-kernel-timing', action='store_true')
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
+    if os.environ.get('KP_FAULT_S'):          # debugging aid: dump every thread's stack and exit if the run hangs
+        import faulthandler
+        faulthandler.dump_traceback_later(int(os.environ['KP_FAULT_S']), exit=True)
     if args.impl == 'reference':
         return run_reference(args)
 
@@ -246,16 +249,17 @@ def main():
     pk = peaks()
     if rank == 0 and not args.no_kernel_timing and args.precision == 'bf16':
         tr2 = tr
-        was, was2 = tr2.use_graph, tr2.two_streams
+        was, was2, was_world = tr2.use_graph, tr2.two_streams, tr2.world
         tr2.use_graph = False
         tr2.two_streams = False                    # time every kernel alone on one stream
+        tr2.world = 1                              # rank 0 only: no collective in this leg (the other ranks are not in it)
         one_step()
         torch.cuda.synchronize()
         L.timing = []
         one_step()
         torch.cuda.synchronize()
         rec, L.timing = L.timing, None
-        tr2.use_graph, tr2.two_streams = was, was2
+        tr2.use_graph, tr2.two_streams, tr2.world = was, was2, was_world
         agg = {}
         calls = []
         for name, fl, a, b, tg in rec:
