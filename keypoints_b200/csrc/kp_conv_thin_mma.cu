@@ -144,23 +144,24 @@ thin_mma_fprop_k(View<bf16> in, const float* __restrict__ wk /*[KK][Cout]*/, con
     }
 }
 
-// dw[co][ci][t] += sum_pix P[pix][kk] dY[pix][co];  grid = (blocks over 16-pixel tiles, Cout / 64)
-__global__ void __launch_bounds__(THIN_WARPS * 32, 2)
+// dw[co][ci][t] += sum_pix P[pix][kk] dY[pix][co];  grid = (blocks over 16-pixel tiles, Cout / 32).
+// 32 output channels per warp keep the accumulators at 32 registers, so 3 blocks (24 warps) per SM hide the gather latency
+__global__ void __launch_bounds__(THIN_WARPS * 32, 3)
 thin_mma_wgrad_k(View<bf16> in, View<bf16> dy, float* __restrict__ dw, int N, int OH, int OW, int Cin, int Cout) {
-    __shared__ float red[32 * 64];
+    __shared__ float red[32 * 32];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int g = lane >> 2, q = lane & 3;
     const int KK = 9 * Cin;
-    const int cb = blockIdx.y * 64;
+    const int cb = blockIdx.y * 32;
     // A = P^T: rows kk in {g, g+8} + 16 mt, columns = pixels {2q, 2q+1, 2q+8, 2q+9}
     int off[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) off[i] = patch_off(g + 8 * i, KK, Cin, in.sy, in.sx, in.sc);
-    float c[2][8][4];
+    float c[2][4][4];
 #pragma unroll
     for (int m = 0; m < 2; ++m)
 #pragma unroll
-        for (int j = 0; j < 8; ++j) { c[m][j][0] = c[m][j][1] = c[m][j][2] = c[m][j][3] = 0.f; }
+        for (int j = 0; j < 4; ++j) { c[m][j][0] = c[m][j][1] = c[m][j][2] = c[m][j][3] = 0.f; }
 
     const int tiles_per_row = OW >> 4;
     const long long ntiles = (long long)N * OH * tiles_per_row;
@@ -172,12 +173,12 @@ thin_mma_wgrad_k(View<bf16> in, View<bf16> dy, float* __restrict__ dw, int N, in
         const bf16* px = in.at(n, y, x0 + 2 * q, 0);
         // gradient rows of the 4 pixels this thread contracts over: channel pairs (2g, 2g+1) of each 16-channel group
         const bf16* pd = dy.at(n, y, x0 + 2 * q, cb + 2 * g);
-        uint32_t u[4][4];                                       // [pixel 2q, 2q+1, 2q+8, 2q+9][group]
+        uint32_t u[4][2];                                       // [pixel 2q, 2q+1, 2q+8, 2q+9][group]
 #pragma unroll
         for (int pp = 0; pp < 4; ++pp) {
             const bf16* row = pd + ((pp & 1) + 8 * (pp >> 1)) * dy.sx;
 #pragma unroll
-            for (int jj = 0; jj < 4; ++jj) u[pp][jj] = __ldg(reinterpret_cast<const uint32_t*>(row + 16 * jj));
+            for (int jj = 0; jj < 2; ++jj) u[pp][jj] = __ldg(reinterpret_cast<const uint32_t*>(row + 16 * jj));
         }
         uint32_t a[2][4];
 #pragma unroll
@@ -191,7 +192,7 @@ thin_mma_wgrad_k(View<bf16> in, View<bf16> dy, float* __restrict__ dw, int N, in
             a[i >> 1][2 + (i & 1)] = v8 | (v9 << 16);           // k = 2q+8, 2q+9
         }
 #pragma unroll
-        for (int jj = 0; jj < 4; ++jj) {
+        for (int jj = 0; jj < 2; ++jj) {
             const uint32_t e0 = __byte_perm(u[0][jj], u[1][jj], 0x5410), o0 = __byte_perm(u[0][jj], u[1][jj], 0x7632);
             const uint32_t e1 = __byte_perm(u[2][jj], u[3][jj], 0x5410), o1 = __byte_perm(u[2][jj], u[3][jj], 0x7632);
 #pragma unroll
@@ -202,22 +203,22 @@ thin_mma_wgrad_k(View<bf16> in, View<bf16> dy, float* __restrict__ dw, int N, in
         }
     }
     // block reduction in shared memory, then one atomic per weight
-    for (int i = threadIdx.x; i < 32 * 64; i += blockDim.x) red[i] = 0.f;
+    for (int i = threadIdx.x; i < 32 * 32; i += blockDim.x) red[i] = 0.f;
     __syncthreads();
 #pragma unroll
     for (int m = 0; m < 2; ++m)
 #pragma unroll
-        for (int j = 0; j < 8; ++j)
+        for (int j = 0; j < 4; ++j)
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
                 const int kk = 16 * m + g + 8 * (e >> 1);
                 const int col = 2 * q + (e & 1);
                 const int co = 16 * (j >> 1) + 2 * col + (j & 1);
-                atomicAdd(&red[kk * 64 + co], c[m][j][e]);
+                atomicAdd(&red[kk * 32 + co], c[m][j][e]);
             }
     __syncthreads();
-    for (int i = threadIdx.x; i < KK * 64; i += blockDim.x) {
-        const int kk = i >> 6, co = cb + (i & 63);
+    for (int i = threadIdx.x; i < KK * 32; i += blockDim.x) {
+        const int kk = i >> 5, co = cb + (i & 31);
         const int t = kk / Cin, ci = kk - t * Cin;
         atomicAdd(&dw[((long long)co * Cin + ci) * 9 + t], red[i]);
     }
@@ -260,9 +261,9 @@ int kp_thin_mma_wgrad(cudaStream_t st, const kp_view* x, const kp_view* dy, floa
                       int Cout) {
     const long long tiles = (long long)N * H * (W / 16);
     long long blocks = (tiles + THIN_WARPS - 1) / THIN_WARPS;
-    const long long cap = (long long)kp_sm_count() * 2;
-    if (blocks > cap) blocks = cap;
-    dim3 grid((unsigned)blocks, (unsigned)(Cout / 64), 1);
+    const long long cap = ((long long)kp_sm_count() * 3) / (Cout / 32);
+    if (blocks > cap) blocks = cap > 0 ? cap : 1;
+    dim3 grid((unsigned)blocks, (unsigned)(Cout / 32), 1);
     thin_mma_wgrad_k<<<grid, THIN_WARPS * 32, 0, st>>>(make_view<bf16>(x), make_view<bf16>(dy), dw, N, H, W, Cin, Cout);
     KP_LAUNCH_CHECK();
     return KP_OK;

@@ -9,6 +9,7 @@ local BatchNorm statistics; the only exchange is a sum all-reduce of the flat fp
 from __future__ import annotations
 
 import math
+import os
 from typing import Optional
 
 import torch
@@ -68,7 +69,7 @@ class Trainer:
         self._flatten()
         self.misc = CachedAlloc('misc')
         self.side = torch.cuda.Stream(device=self.device)     # encoder branch runs beside the keypoint branch
-        self.two_streams = True
+        self.two_streams = os.environ.get('KP_TWO_STREAMS', '1') != '0'
         self.graph = None
         self.graph_key = None
         self.steps_done = 0
