@@ -10,7 +10,7 @@ import types
 
 import keypoints_b200
 from keypoints_b200 import data_augments, tps
-from keypoints_b200.models import functional, keynet, knn, transporter, vgg
+from keypoints_b200.models import autoencoder, functional, keynet, knn, transporter, vgg
 
 
 def _amp_shim():
@@ -35,7 +35,9 @@ def _amp_shim():
 def install(precision=None, shim_apex=True):
     pkg, models = types.ModuleType('keypoints'), types.ModuleType('keypoints.models')
     pkg.__path__, models.__path__ = [], []
-    for name, mod in dict(knn=knn, vgg=vgg, keynet=keynet, transporter=transporter, functional=functional).items():
+    models.Container = knn.Container        # models/autoencoder.py:1 imports it from the package (the reference's __init__ forgot it)
+    for name, mod in dict(knn=knn, vgg=vgg, keynet=keynet, transporter=transporter, functional=functional,
+                          autoencoder=autoencoder).items():
         setattr(models, name, mod)
         sys.modules[f'keypoints.models.{name}'] = mod
     pkg.models = models
