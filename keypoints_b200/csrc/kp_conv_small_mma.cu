@@ -1,0 +1,255 @@
+// 3x3 convolutions with 16 or 32 input AND output channels (the VGG_PONG* nets of the reference, vgg.py:48-70) in bf16
+// mode.  A 64-channel tcgen05 k-block / 128-row UMMA tile would be 50-94 % padding at these widths, and the fp32 SIMT
+// kernels reach ~6 TFLOP/s, so these layers run on warp-level mma.sync.m16n8k16 instead: A fragments are gathered
+// straight from the NHWC buffer with 4-byte loads (16 consecutive pixels of one image row per MMA tile, masked at the
+// row end), the weights sit in shared memory pre-arranged in B-fragment order, fp32 accumulation.
+//   conv  : out[pix][co] = b[co] + sum_{t,ci} in[pix + tap t][ci] w[t*CIN + ci][co]   (fprop, and dgrad with the flipped /
+//           transposed weights the caller packs; CHECK = bounds-checked taps for dgrad's zero halo)
+//   wgrad : dw[co][ci][t] += sum_pix in[pix + tap t][ci] dy[pix][co]; one warp per tap, the dy fragments are built from
+//           4-byte loads with byte permutes (both operands have pixels as the slow axis; output columns relabelled)
+#include "kp_common.cuh"
+
+namespace {
+
+__device__ __forceinline__ void mma16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile(
+        "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+        : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t pk2(float lo, float hi) {
+    __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
+    return *reinterpret_cast<uint32_t*>(&h);
+}
+__device__ __forceinline__ uint32_t ld32(const bf16* p) { return *reinterpret_cast<const uint32_t*>(p); }
+__device__ __forceinline__ uint32_t ld16(const bf16* p) { return (uint32_t)*reinterpret_cast<const unsigned short*>(p); }
+
+constexpr int SM_WARPS = 8;
+
+// tile = 16 consecutive x of one output row; tiles_per_row = ceil(OW / 16)
+template <int CIN, int COUT, bool CHECK>
+__global__ void __launch_bounds__(SM_WARPS * 32, 2)
+small_mma_conv_k(View<bf16> in, const float* __restrict__ wk, const float* __restrict__ bias, View<bf16> out, double* stats,
+                 int N, int OH, int OW, int IH, int IW, int off) {
+    constexpr int KH = CIN / 16, KS = 9 * KH, NT = COUT / 8;
+    __shared__ uint2 wf[KS][NT][32];
+    __shared__ float red[SM_WARPS][2][COUT];
+    __shared__ float sbias[COUT];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int g = lane >> 2, q = lane & 3;
+    for (int i = threadIdx.x; i < KS * NT * 32; i += blockDim.x) {
+        const int ln = i & 31, nt = (i >> 5) % NT, ks = (i >> 5) / NT;
+        const int co = nt * 8 + (ln >> 2), k0 = ks * 16 + 2 * (ln & 3);
+        uint2 v;
+        v.x = pk2(wk[(k0)*COUT + co], wk[(k0 + 1) * COUT + co]);
+        v.y = pk2(wk[(k0 + 8) * COUT + co], wk[(k0 + 9) * COUT + co]);
+        wf[ks][nt][ln] = v;
+    }
+    if (threadIdx.x < COUT) sbias[threadIdx.x] = bias ? bias[threadIdx.x] : 0.f;
+    __syncthreads();
+    float s1[NT][2], s2[NT][2];
+#pragma unroll
+    for (int j = 0; j < NT; ++j) { s1[j][0] = s1[j][1] = s2[j][0] = s2[j][1] = 0.f; }
+    const unsigned tpr = (unsigned)(OW + 15) >> 4;
+    const unsigned ntiles = (unsigned)N * (unsigned)OH * tpr;
+    for (unsigned tile = blockIdx.x * SM_WARPS + warp; tile < ntiles; tile += gridDim.x * SM_WARPS) {
+        const unsigned r = tile / tpr;
+        const int x0 = (int)(tile - r * tpr) << 4;
+        const int n = (int)(r / (unsigned)OH), y = (int)(r - (unsigned)n * (unsigned)OH);
+        const int xa = x0 + g, xb = xa + 8;
+        const bool va = xa < OW, vb = xb < OW;
+        const bf16* pa = in.at(n, y + off, xa + off, 2 * q);
+        const bf16* pb = pa + 8 * in.sx;
+        float c[NT][4];
+#pragma unroll
+        for (int j = 0; j < NT; ++j) {
+            const float b0 = sbias[8 * j + 2 * q], b1 = sbias[8 * j + 2 * q + 1];
+            c[j][0] = b0; c[j][1] = b1; c[j][2] = b0; c[j][3] = b1;
+        }
+#pragma unroll
+        for (int t = 0; t < 9; ++t) {
+            const int ty = t / 3, tx = t % 3;
+            bool oa = va, ob = vb;
+            if (CHECK) {
+                const int iy = y + ty + off;
+                const bool oky = iy >= 0 && iy < IH;
+                oa = oa && oky && (xa + tx + off) >= 0 && (xa + tx + off) < IW;
+                ob = ob && oky && (xb + tx + off) >= 0 && (xb + tx + off) < IW;
+            }
+            const long long toff = ty * in.sy + tx * in.sx;
+#pragma unroll
+            for (int h = 0; h < KH; ++h) {
+                uint32_t a[4];
+                a[0] = oa ? ld32(pa + toff + 16 * h) : 0u;
+                a[1] = ob ? ld32(pb + toff + 16 * h) : 0u;
+                a[2] = oa ? ld32(pa + toff + 16 * h + 8) : 0u;
+                a[3] = ob ? ld32(pb + toff + 16 * h + 8) : 0u;
+#pragma unroll
+                for (int j = 0; j < NT; ++j) {
+                    const uint2 w = wf[t * KH + h][j][lane];
+                    mma16816(c[j], a, w.x, w.y);
+                }
+            }
+        }
+        bf16* oa_p = out.at(n, y, xa, 2 * q);
+        bf16* ob_p = oa_p + 8 * out.sx;
+#pragma unroll
+        for (int j = 0; j < NT; ++j) {
+            if (va) {
+                *reinterpret_cast<uint32_t*>(oa_p + 8 * j) = pk2(c[j][0], c[j][1]);
+                s1[j][0] += c[j][0]; s1[j][1] += c[j][1];
+                s2[j][0] = fmaf(c[j][0], c[j][0], s2[j][0]); s2[j][1] = fmaf(c[j][1], c[j][1], s2[j][1]);
+            }
+            if (vb) {
+                *reinterpret_cast<uint32_t*>(ob_p + 8 * j) = pk2(c[j][2], c[j][3]);
+                s1[j][0] += c[j][2]; s1[j][1] += c[j][3];
+                s2[j][0] = fmaf(c[j][2], c[j][2], s2[j][0]); s2[j][1] = fmaf(c[j][3], c[j][3], s2[j][1]);
+            }
+        }
+    }
+    if (stats) {
+#pragma unroll
+        for (int j = 0; j < NT; ++j)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                float a = s1[j][e], b = s2[j][e];
+#pragma unroll
+                for (int o = 4; o < 32; o <<= 1) { a += __shfl_xor_sync(0xffffffffu, a, o); b += __shfl_xor_sync(0xffffffffu, b, o); }
+                if (g == 0) { red[warp][0][8 * j + 2 * q + e] = a; red[warp][1][8 * j + 2 * q + e] = b; }
+            }
+        __syncthreads();
+        if (threadIdx.x < 2 * COUT) {
+            const int w = threadIdx.x / COUT, ch = threadIdx.x % COUT;
+            float a = 0.f;
+            for (int k = 0; k < SM_WARPS; ++k) a += red[k][w][ch];
+            atomicAdd(&stats[w * COUT + ch], (double)a);
+        }
+    }
+}
+
+// block = 9 warps, warp t accumulates tap t: D[ci (M)][co (N)] over the block's pixel tiles
+template <int CIN, int COUT>
+__global__ void __launch_bounds__(288, 2)
+small_mma_wgrad_k(View<bf16> x, View<bf16> dy, float* __restrict__ dw, int N, int H, int W) {
+    constexpr int MT = CIN / 16, NJ = COUT / 16;
+    const int lane = threadIdx.x & 31, t = threadIdx.x >> 5;
+    const int g = lane >> 2, q = lane & 3;
+    const int ty = t / 3, tx = t % 3;
+    float c[MT][2 * NJ][4];
+#pragma unroll
+    for (int m = 0; m < MT; ++m)
+#pragma unroll
+        for (int j = 0; j < 2 * NJ; ++j) { c[m][j][0] = c[m][j][1] = c[m][j][2] = c[m][j][3] = 0.f; }
+    const unsigned tpr = (unsigned)(W + 15) >> 4;
+    const unsigned ntiles = (unsigned)N * (unsigned)H * tpr;
+    for (unsigned tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const unsigned r = tile / tpr;
+        const int x0 = (int)(tile - r * tpr) << 4;
+        const int n = (int)(r / (unsigned)H), y = (int)(r - (unsigned)n * (unsigned)H);
+        // the 4 pixels this thread contracts over: x0 + {2q, 2q+1, 2q+8, 2q+9}
+        const int xp = x0 + 2 * q;
+        bool v[4];
+        v[0] = xp < W; v[1] = xp + 1 < W; v[2] = xp + 8 < W; v[3] = xp + 9 < W;
+        const bf16* pd = dy.at(n, y, xp, 2 * g);
+        const bf16* px = x.at(n, y + ty, xp + tx, g);
+        uint32_t u[4][NJ];
+#pragma unroll
+        for (int pp = 0; pp < 4; ++pp) {
+            const bf16* row = pd + ((pp & 1) + 8 * (pp >> 1)) * dy.sx;
+#pragma unroll
+            for (int jj = 0; jj < NJ; ++jj) u[pp][jj] = v[pp] ? ld32(row + 16 * jj) : 0u;
+        }
+        uint32_t a[MT][4];
+#pragma unroll
+        for (int m = 0; m < MT; ++m) {
+#pragma unroll
+            for (int hf = 0; hf < 2; ++hf) {                     // ci = 16 m + g + 8 hf
+                const bf16* p0 = px + 16 * m + 8 * hf;
+                const uint32_t v0 = v[0] ? ld16(p0) : 0u, v1 = v[1] ? ld16(p0 + x.sx) : 0u;
+                const uint32_t v8 = v[2] ? ld16(p0 + 8 * x.sx) : 0u, v9 = v[3] ? ld16(p0 + 9 * x.sx) : 0u;
+                a[m][hf] = v0 | (v1 << 16);
+                a[m][2 + hf] = v8 | (v9 << 16);
+            }
+        }
+#pragma unroll
+        for (int jj = 0; jj < NJ; ++jj) {
+            const uint32_t e0 = __byte_perm(u[0][jj], u[1][jj], 0x5410), o0 = __byte_perm(u[0][jj], u[1][jj], 0x7632);
+            const uint32_t e1 = __byte_perm(u[2][jj], u[3][jj], 0x5410), o1 = __byte_perm(u[2][jj], u[3][jj], 0x7632);
+#pragma unroll
+            for (int m = 0; m < MT; ++m) {
+                mma16816(c[m][2 * jj], a[m], e0, e1);
+                mma16816(c[m][2 * jj + 1], a[m], o0, o1);
+            }
+        }
+    }
+#pragma unroll
+    for (int m = 0; m < MT; ++m)
+#pragma unroll
+        for (int j = 0; j < 2 * NJ; ++j)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int ci = 16 * m + g + 8 * (e >> 1);
+                const int col = 2 * q + (e & 1);
+                const int co = 16 * (j >> 1) + 2 * col + (j & 1);
+                atomicAdd(&dw[((long long)co * CIN + ci) * 9 + t], c[m][j][e]);
+            }
+}
+
+static bool small_view_ok(const kp_view* v, int C) {
+    return v->dtype == KP_BF16 && v->sc == 1 && (((uintptr_t)v->ptr) % 4) == 0 && v->sx % 2 == 0 && v->sy % 2 == 0 &&
+           v->sn % 2 == 0 && v->sx >= C;
+}
+
+}  // namespace
+
+bool kp_small_mma_conv_ok(const kp_view* in, const kp_view* out, int N, int OH, int OW, int Cin, int Cout, int ks) {
+    return ks == 3 && (Cin == 16 || Cin == 32) && (Cout == 16 || Cout == 32) && small_view_ok(in, Cin) && small_view_ok(out, Cout) &&
+           (long long)N * OH * ((OW + 15) / 16) < (1LL << 31);
+}
+
+int kp_small_mma_conv(cudaStream_t st, const kp_view* in, const float* wk, const float* bias, const kp_view* out,
+                      double* stats, int N, int OH, int OW, int IH, int IW, int Cin, int Cout, int off) {
+    const long long tiles = (long long)N * OH * ((OW + 15) / 16);
+    long long blocks = (tiles + SM_WARPS - 1) / SM_WARPS;
+    const long long cap = (long long)kp_sm_count() * 4;
+    if (blocks > cap) blocks = cap;
+    const bool check = !(off >= 0 && OH + off + 2 <= IH && OW + off + 2 <= IW);
+    const dim3 grid((unsigned)blocks);
+#define KP_SM(CI, CO)                                                                                                       \
+    do {                                                                                                                    \
+        if (check)                                                                                                          \
+            small_mma_conv_k<CI, CO, true><<<grid, SM_WARPS * 32, 0, st>>>(make_view<bf16>(in), wk, bias, make_view<bf16>(out), \
+                                                                          stats, N, OH, OW, IH, IW, off);                   \
+        else                                                                                                                \
+            small_mma_conv_k<CI, CO, false><<<grid, SM_WARPS * 32, 0, st>>>(make_view<bf16>(in), wk, bias,                  \
+                                                                           make_view<bf16>(out), stats, N, OH, OW, IH, IW, off); \
+    } while (0)
+    if (Cin == 16 && Cout == 16) KP_SM(16, 16);
+    else if (Cin == 16 && Cout == 32) KP_SM(16, 32);
+    else if (Cin == 32 && Cout == 16) KP_SM(32, 16);
+    else KP_SM(32, 32);
+#undef KP_SM
+    KP_LAUNCH_CHECK();
+    return KP_OK;
+}
+
+bool kp_small_mma_wgrad_ok(const kp_view* x, const kp_view* dy, int N, int H, int W, int Cin, int Cout, int ks) {
+    return ks == 3 && (Cin == 16 || Cin == 32) && (Cout == 16 || Cout == 32) && small_view_ok(x, Cin) && small_view_ok(dy, Cout) &&
+           (long long)N * H * ((W + 15) / 16) < (1LL << 31);
+}
+
+int kp_small_mma_wgrad(cudaStream_t st, const kp_view* x, const kp_view* dy, float* dw, int N, int H, int W, int Cin, int Cout) {
+    const long long tiles = (long long)N * H * ((W + 15) / 16);
+    long long blocks = tiles;
+    const long long cap = (long long)kp_sm_count() * 2;
+    if (blocks > cap) blocks = cap;
+    const dim3 grid((unsigned)blocks);
+#define KP_SW(CI, CO) small_mma_wgrad_k<CI, CO><<<grid, 288, 0, st>>>(make_view<bf16>(x), make_view<bf16>(dy), dw, N, H, W)
+    if (Cin == 16 && Cout == 16) KP_SW(16, 16);
+    else if (Cin == 16 && Cout == 32) KP_SW(16, 32);
+    else if (Cin == 32 && Cout == 16) KP_SW(32, 16);
+    else KP_SW(32, 32);
+#undef KP_SW
+    KP_LAUNCH_CHECK();
+    return KP_OK;
+}

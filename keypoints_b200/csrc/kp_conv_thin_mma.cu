@@ -406,8 +406,8 @@ static int head_grid(long long P, int g_shift) {
     return (int)(blocks < cap ? (blocks < 1 ? 1 : blocks) : cap);
 }
 static int head_shift(int Cw) { int s = 0; while ((8 << s) < Cw) ++s; return s; }
-static bool wide_ok(const kp_view* v, int Cw) {      // bf16, 16-byte aligned 8-channel chunks, 64 <= Cw <= 256 a power of two
-    return v->dtype == KP_BF16 && v->sc == 1 && Cw >= 64 && Cw <= 256 && (Cw & (Cw - 1)) == 0 && (((uintptr_t)v->ptr) % 16) == 0 &&
+static bool wide_ok(const kp_view* v, int Cw) {      // bf16, 16-byte aligned 8-channel chunks, 16 <= Cw <= 256 a power of two
+    return v->dtype == KP_BF16 && v->sc == 1 && Cw >= 16 && Cw <= 256 && (Cw & (Cw - 1)) == 0 && (((uintptr_t)v->ptr) % 16) == 0 &&
            v->sx % 8 == 0 && v->sy % 8 == 0 && v->sn % 8 == 0;
 }
 

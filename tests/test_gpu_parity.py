@@ -291,6 +291,43 @@ def test_tensor_core_conv_vs_fp32(dev, cin, cout, k, n, h, w):
     close(dx, xr.grad, 2e-2, 'dgrad')
 
 
+@pytest.mark.parametrize('cin,cout,n,h,w', [(16, 32, 2, 20, 20), (32, 32, 3, 84, 84), (32, 16, 2, 9, 33), (16, 16, 2, 16, 48)])
+def test_small_channel_mma_conv_vs_fp32(dev, cin, cout, n, h, w):
+    """The 16/32-channel 3x3 layers of the VGG_PONG* nets in bf16 mode (mma.sync kernels, kp_conv_small_mma.cu): fprop,
+    dgrad (bounds-checked taps) and wgrad against an fp32 reference fed the same bf16-rounded operands; odd widths
+    exercise the masked row tails."""
+    from keypoints_b200 import engine
+    from keypoints_b200.engine import ConvSpec, LayerParams, LayerGrads
+    torch.manual_seed(cin * 100 + cout + w)
+    spec = ConvSpec(k=3, cin=cin, cout=cout, bn=True, act='none')
+    x = torch.randn(n, cin, h, w).bfloat16().float()
+    wt = (torch.randn(cout, cin, 3, 3) / (cin * 9) ** 0.5).bfloat16().float()
+    bias = torch.randn(cout) * 0.1
+    p = LayerParams(w=wt.to(dev), b=bias.to(dev), gamma=torch.ones(cout, device=dev), beta=torch.zeros(cout, device=dev),
+                    rmean=torch.zeros(cout, device=dev), rvar=torch.ones(cout, device=dev),
+                    nbt=torch.zeros((), dtype=torch.long, device=dev))
+    assert not engine.uses_tc(spec, cin, 'bf16')
+    xp = engine.to_padded(x.to(dev), 'bf16')
+    out = torch.empty(n, h, w, cout, device=dev)
+    ctxs = engine.unit_forward([spec], [p], xp, h, w, 'bf16', out, 0)
+    y = ctxs[0].y[:, :h, :w, :].float().permute(0, 3, 1, 2)
+    ref_y = _conv_ref(x, wt, bias)
+    close(y, ref_y, 1e-2, 'fprop (bf16 store)')
+    ref_bn = torch.nn.functional.batch_norm(ref_y, None, None, training=True)
+    close(out.permute(0, 3, 1, 2), ref_bn, 1e-2, 'bn(fprop): statistics from the fp32 accumulators')
+    dout = torch.randn(n, cout, h, w).bfloat16().float()
+    xr = x.clone().requires_grad_(True)
+    wr = wt.clone().requires_grad_(True)
+    ref = torch.nn.functional.batch_norm(_conv_ref(xr, wr, bias), None, None, training=True)
+    ref.backward(dout)
+    g = LayerGrads(dw=torch.zeros(cout, cin, 3, 3, device=dev), db=torch.zeros(cout, device=dev),
+                   dgamma=torch.zeros(cout, device=dev), dbeta=torch.zeros(cout, device=dev))
+    dxp = engine.unit_backward([spec], [p], [g], ctxs, dout.to(dev).permute(0, 2, 3, 1), 0, 'bf16', True)
+    dx = engine.fold_to_nchw(dxp, cin, h, w)
+    close(g.dw, wr.grad, 2e-2, 'wgrad')
+    close(dx, xr.grad, 2e-2, 'dgrad')
+
+
 def test_adjoint_identity_full_size(dev):
     """Size-independent property at the BASELINE layer sizes: <conv(x,w), dy> == <w, wgrad(x,dy)> == <x, dgrad(dy,w)>
     for the tensor-core kernels (bf16 operands, fp32 accumulation), 128x128x64->128 at batch 8."""
