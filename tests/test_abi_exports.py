@@ -37,8 +37,8 @@ def test_sass_is_blackwell_native(built):
     """The tensor-core kernels must be tcgen05 / TMA code, not a legacy mma.sync path."""
     sass = subprocess.run(['cuobjdump', '-sass', built.LIB_PATH], capture_output=True, text=True).stdout
     assert 'UTCHMMA' in sass and 'UTMALDG' in sass and 'LDTM' in sass
-    # per kernel: warp-level HMMA only in the first-layer (Cin <= 3, K = 27) kernels, where a tcgen05 k-block would be
-    # > 95 % zero padding (kp_conv_thin_mma.cu); the conv / wgrad families are tcgen05 + TMA, the BatchNorm streaming
+    # per kernel: warp-level HMMA only in the first-layer (Cin <= 3, K = 27) kernels and the 16/32-channel Pong layers, where
+    # a tcgen05 k-block / tile would be 50-95 % zero padding (kp_conv_thin_mma.cu, kp_conv_small_mma.cu); the conv / wgrad families are tcgen05 + TMA, the BatchNorm streaming
     # kernels use the bulk-copy engine (UBLKCP) with mbarrier transaction counts (SYNCS)
     funcs = {}
     name = None
@@ -51,8 +51,8 @@ def test_sass_is_blackwell_native(built):
     body = {k: '\n'.join(v) for k, v in funcs.items()}
     for k, text in body.items():
         if 'HMMA' in text.replace('UTCHMMA', ''):
-            assert 'thin_mma' in k, f'legacy mma.sync code in {k}'
-    conv = [k for k in body if 'conv_tc_pair_k' in k or 'wgrad_tc_pair_k' in k]
+            assert 'thin_mma' in k or 'small_mma' in k, f'legacy mma.sync code in {k}'
+    conv = [k for k in body if 'conv_tc_pair' in k or 'wgrad_tc_pair_k' in k]
     assert conv and all('UTCHMMA' in body[k] and 'UTMALDG' in body[k] for k in conv)
     pipe = [k for k in body if '_pipe_k' in k]
     assert len(pipe) >= 10 and all('UBLKCP' in body[k] and 'SYNCS' in body[k] for k in pipe)
