@@ -47,6 +47,9 @@ CASES = [
     (128, 256, 16, 'up', 'leaky', 2),
     (128, 512, 16, 'up', 'relu', 2),
     (128, 64, 48, 'up', 'relu', 2),          # 3 row bands of 16
+    (128, 64, (24, 32), 'up', 'leaky', 2),   # bands of 16 + 8 rows, H != W
+    (128, 64, (20, 64), 'pool', 'relu', 2),  # H != W
+    (128, 128, (10, 32), 'none', 'relu', 3),
     # not pipe-eligible (row length): register-staged kernels
     (128, 64, 24, 'none', 'leaky', 2),
     (128, 64, 24, 'pool', 'relu', 2),
@@ -58,8 +61,8 @@ CASES = [
 def test_bn_act_post_kernels_vs_torch(dev, cin, cout, h, post, act, n):
     from keypoints_b200 import engine
     from keypoints_b200.engine import ConvSpec, LayerGrads, LayerParams
+    h, w = h if isinstance(h, tuple) else (h, h)
     torch.manual_seed(h * 1000 + cout)
-    w = h
     spec = ConvSpec(k=3, cin=cin, cout=cout, bn=True, act=act, post=post)
     x = torch.randn(n, cin, h, w, device=dev)
     p = LayerParams(w=torch.randn(cout, cin, 3, 3, device=dev) / (3 * cin ** 0.5), b=torch.randn(cout, device=dev) * 0.1,
