@@ -91,6 +91,12 @@ int kp_conv_tc(kp_stream stream, const void* in_bf16, int64_t Q, int Cin, const 
 int kp_conv_wgrad_tc(kp_stream stream, const void* x_bf16, const void* dy_bf16, int64_t Q, int Cin,
                      int CinP, int Cout, int taps, const int32_t* shifts, float* stg,
                      float* dw_oihw);
+/* Image-aware form of the same gradient: x = replicate-padded input [N][H+2][W+2][CinP], dy = interior-aligned
+ * gradient [N][H+2][W+2][Cout]; the contraction runs over the N*H*W valid pixels only (4-D TMA boxes of bx x by = 64
+ * pixels), so no MMA work is spent on the pad / zero-border pixels the flat form multiplies (3 % of the pixels at
+ * 128x128, 27 % at 16x16).  W must be a power of two >= 16 (W < 64: H % (64 / W) == 0); ks in {1, 3}. */
+int kp_conv_wgrad_tc_img(kp_stream stream, const void* x_bf16, const void* dy_bf16, int N, int H, int W,
+                         int Cin, int CinP, int Cout, int ks, float* stg, float* dw_oihw);
 
 /* Repack OIHW fp32 master weights for the kernels above (any output may be NULL):
  *  simt_f   f32  [t][ci][co]            simt_d  f32  [t'][co][ci]   (t' = taps flipped)

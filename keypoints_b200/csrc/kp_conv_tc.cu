@@ -55,6 +55,12 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* tm,
         ::"r"(dst), "l"((uint64_t)tm), "r"(c0), "r"(c1), "r"(bar)
         : "memory");
 }
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* tm, int c0, int c1, int c2, int c3, uint32_t bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
+        ::"r"(dst), "l"((uint64_t)tm), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(bar)
+        : "memory");
+}
 __device__ __forceinline__ void tma_prefetch_l2_2d(const CUtensorMap* tm, int c0, int c1) {
     asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"((uint64_t)tm), "r"(c0), "r"(c1) : "memory");
 }
@@ -153,6 +159,12 @@ struct WgradTcParams {
     int shiftA[9], shiftB[9];
     int Mtot, Ntot;         // staging is [taps][Mtot][Ntot] fp32
     float* stg;
+    // image mode: the contraction runs over the VALID pixels only.  A k-block is a bx x by patch (bx * by = 64) of one image,
+    // fetched with 4-D tensor maps (channel, x, y, image) of the padded buffers; tap t reads operand A at (+ax, +ay) and
+    // operand B at (+bx_o, +by_o) from the patch origin.  The flat mode also multiplies the zero / pad border pixels
+    // (3 % of the MMA work at 128x128, 27 % at 16x16).
+    int img, bx, by, bpr, bpi;
+    int ax[9], ay[9], bxo[9], byo[9];
 };
 
 // ================================================================================================
@@ -401,6 +413,12 @@ __device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap
     asm volatile(
         "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
         ::"r"(dst), "l"((uint64_t)tm), "r"(c0), "r"(c1), "r"(bar & PEER_MASK)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_4d_pair(uint32_t dst, const CUtensorMap* tm, int c0, int c1, int c2, int c3, uint32_t bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
+        ::"r"(dst), "l"((uint64_t)tm), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(bar & PEER_MASK)
         : "memory");
 }
 __device__ __forceinline__ void umma_commit_pair(uint32_t bar) {
@@ -947,6 +965,17 @@ wgrad_tc_persist_k(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                     mbar_expect_tx(full, STAGE_BYTES);
                     const long long q = qbeg + (long long)kb * 64;
                     const uint32_t sa = base + s * STAGE_BYTES;
+                    if (p.img) {
+                        const int P = (int)(q >> 6), n = P / p.bpi, rem = P - n * p.bpi, yb = rem / p.bpr, xb = rem - yb * p.bpr;
+                        const int x0 = xb * p.bx, y0 = yb * p.by;
+#pragma unroll
+                        for (int b = 0; b < 2; ++b)
+                            tma_load_4d(sa + b * BOX_BYTES, &tmA, m0 + b * 64, x0 + p.ax[tap], y0 + p.ay[tap], n, full);
+#pragma unroll
+                        for (int b = 0; b < BN / 64; ++b)
+                            tma_load_4d(sa + A_BYTES + b * BOX_BYTES, &tmB, n0 + b * 64, x0 + p.bxo[tap], y0 + p.byo[tap], n, full);
+                        continue;
+                    }
 #pragma unroll
                     for (int b = 0; b < 2; ++b)
                         tma_load_2d(sa + b * BOX_BYTES, &tmA, m0 + b * 64, (int)(q + p.shiftA[tap]), full);
@@ -1091,6 +1120,17 @@ wgrad_tc_pair_k(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                     if (leader) mbar_expect_tx(full, 2 * STAGE_BYTES);
                     const long long q = qbeg + (long long)kb * 64;
                     const uint32_t sa = base + s * STAGE_BYTES;
+                    if (p.img) {
+                        const int P = (int)(q >> 6), n = P / p.bpi, rem = P - n * p.bpi, yb = rem / p.bpr, xb = rem - yb * p.bpr;
+                        const int x0 = xb * p.bx, y0 = yb * p.by;
+#pragma unroll
+                        for (int b = 0; b < 2; ++b)
+                            tma_load_4d_pair(sa + b * BOX_BYTES, &tmA, m0 + b * 64, x0 + p.ax[tap], y0 + p.ay[tap], n, full);
+#pragma unroll
+                        for (int b = 0; b < BN / 128; ++b)
+                            tma_load_4d_pair(sa + A_BYTES + b * BOX_BYTES, &tmB, n0 + b * 64, x0 + p.bxo[tap], y0 + p.byo[tap], n, full);
+                        continue;
+                    }
 #pragma unroll
                     for (int b = 0; b < 2; ++b)
                         tma_load_2d_pair(sa + b * BOX_BYTES, &tmA, m0 + b * 64, (int)(q + p.shiftA[tap]), full);
@@ -1208,6 +1248,21 @@ static int make_map(CUtensorMap* tm, const void* ptr, long long rows, long long 
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { kp_set_error("cuTensorMapEncodeTiled failed: %d (rows=%lld cols=%lld box=%d)", (int)r, rows, cols, box_rows); return KP_ERR_CUDA; }
+    return KP_OK;
+}
+
+// 4-D bf16 tensor [N][PH][PW][C] (C contiguous), box = 64 channels x bx x by x 1 image, 128-byte swizzle
+static int make_map4(CUtensorMap* tm, const void* ptr, int N, int PH, int PW, int C, int bx, int by) {
+    EncodeTiledFn enc = get_encode();
+    if (!enc) { kp_set_error("cuTensorMapEncodeTiled entry point not available"); return KP_ERR_CUDA; }
+    cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)PW, (cuuint64_t)PH, (cuuint64_t)N};
+    cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)PW * C * 2, (cuuint64_t)PH * PW * C * 2};
+    cuuint32_t box[4] = {64, (cuuint32_t)bx, (cuuint32_t)by, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { kp_set_error("cuTensorMapEncodeTiled(4d) failed: %d (N=%d PH=%d PW=%d C=%d box=%dx%d)", (int)r, N, PH, PW, C, bx, by); return KP_ERR_CUDA; }
     return KP_OK;
 }
 
@@ -1386,9 +1441,10 @@ static void choose_split(int tiles, int workers, long long blocks64, long long* 
 // dw_oihw[co][ci][t] += sum_q dy[q][co] * x[q + shifts[t]][ci];  x: bf16 [Q][CinP] (CinP >= Cin, extra
 // channels ignored), dy: bf16 [Q][Cout] with zero rows wherever the product must not count.
 // stg: fp32 workspace of taps*Cout*CinP floats (zeroed here).
-extern "C" int kp_conv_wgrad_tc(kp_stream stream, const void* x_bf16, const void* dy_bf16, int64_t Q, int Cin, int CinP,
-                                int Cout, int taps, const int32_t* shifts, float* stg, float* dw_oihw) {
-    KP_CHECK_ARG(x_bf16 && dy_bf16 && stg && dw_oihw && shifts && Q > 0 && Q < (1LL << 31) - 4096 && taps >= 1 &&
+// img != nullptr: image mode {N, H, W} (contraction over the valid pixels through 4-D tensor maps)
+static int wgrad_tc_impl(kp_stream stream, const void* x_bf16, const void* dy_bf16, int64_t Q, int Cin, int CinP,
+                         int Cout, int taps, const int32_t* shifts, float* stg, float* dw_oihw, const int* img) {
+    KP_CHECK_ARG(x_bf16 && dy_bf16 && stg && dw_oihw && (shifts || img) && (img || (Q > 0 && Q < (1LL << 31) - 4096)) && taps >= 1 &&
                      taps <= 9 && CinP % 64 == 0 && Cout % 64 == 0 && Cin <= CinP && (Cout % 128 == 0 || CinP % 128 == 0),
                  "kp_conv_wgrad_tc: unsupported shape Q=%lld Cin=%d/%d Cout=%d taps=%d", (long long)Q, Cin, CinP, Cout, taps);
     cudaStream_t st = (cudaStream_t)stream;
@@ -1396,14 +1452,36 @@ extern "C" int kp_conv_wgrad_tc(kp_stream stream, const void* x_bf16, const void
     const int Mtot = m_is_cout ? Cout : CinP, Ntot = m_is_cout ? CinP : Cout;
     const int BN = (Ntot % 256 == 0) ? 256 : (Ntot % 128 == 0 ? 128 : 64);
     CUtensorMap ta, tb;
-    int rc = make_map(&ta, m_is_cout ? dy_bf16 : x_bf16, Q, Mtot, 64);
-    if (rc) return rc;
-    rc = make_map(&tb, m_is_cout ? x_bf16 : dy_bf16, Q, Ntot, 64);
-    if (rc) return rc;
+    int rc;
     WgradTcParams p;
-    p.Q = Q; p.Mtot = Mtot; p.Ntot = Ntot; p.stg = stg;
+    p.Mtot = Mtot; p.Ntot = Ntot; p.stg = stg; p.img = 0;
+    p.bx = p.by = p.bpr = p.bpi = 0;
+    for (int i = 0; i < 9; ++i) { p.ax[i] = p.ay[i] = p.bxo[i] = p.byo[i] = 0; }
+    if (img) {
+        const int N = img[0], H = img[1], W = img[2], PH = H + 2, PW = W + 2;
+        p.img = 1;
+        p.bx = W < 64 ? W : 64; p.by = 64 / p.bx;
+        p.bpr = W / p.bx; p.bpi = p.bpr * (H / p.by);
+        Q = (int64_t)N * p.bpi * 64;                       // = N * H * W valid pixels
+        const int ks = taps == 9 ? 3 : 1;
+        for (int t = 0; t < taps; ++t) {
+            const int xo = ks == 3 ? t % 3 : 1, yo = ks == 3 ? t / 3 : 1;     // x window of output pixel (y, x) starts at (y, x)
+            p.ax[t] = m_is_cout ? 1 : xo; p.ay[t] = m_is_cout ? 1 : yo;      // dy is interior-aligned: (+1, +1)
+            p.bxo[t] = m_is_cout ? xo : 1; p.byo[t] = m_is_cout ? yo : 1;
+        }
+        rc = make_map4(&ta, m_is_cout ? dy_bf16 : x_bf16, N, PH, PW, Mtot, p.bx, p.by);
+        if (rc) return rc;
+        rc = make_map4(&tb, m_is_cout ? x_bf16 : dy_bf16, N, PH, PW, Ntot, p.bx, p.by);
+        if (rc) return rc;
+    } else {
+        rc = make_map(&ta, m_is_cout ? dy_bf16 : x_bf16, Q, Mtot, 64);
+        if (rc) return rc;
+        rc = make_map(&tb, m_is_cout ? x_bf16 : dy_bf16, Q, Ntot, 64);
+        if (rc) return rc;
+    }
+    p.Q = Q;
     for (int i = 0; i < 9; ++i) {
-        int s = i < taps ? shifts[i] : 0;
+        int s = (i < taps && shifts) ? shifts[i] : 0;
         p.shiftA[i] = m_is_cout ? 0 : s;
         p.shiftB[i] = m_is_cout ? s : 0;
     }
@@ -1429,4 +1507,20 @@ extern "C" int kp_conv_wgrad_tc(kp_stream stream, const void* x_bf16, const void
     wgrad_finalize_k<<<blocks, 256, 0, st>>>(stg, dw_oihw, taps, Cout, Cin, CinP, m_is_cout ? 1 : 0);
     KP_LAUNCH_CHECK();
     return KP_OK;
+}
+
+extern "C" int kp_conv_wgrad_tc(kp_stream stream, const void* x_bf16, const void* dy_bf16, int64_t Q, int Cin, int CinP,
+                                int Cout, int taps, const int32_t* shifts, float* stg, float* dw_oihw) {
+    return wgrad_tc_impl(stream, x_bf16, dy_bf16, Q, Cin, CinP, Cout, taps, shifts, stg, dw_oihw, nullptr);
+}
+
+// Image-aware form: x = replicate-padded input [N][H+2][W+2][CinP], dy = interior-aligned gradient [N][H+2][W+2][Cout];
+// only the N*H*W valid pixels are contracted.  Needs W a power of two >= 16 (W <= 64: 64 % W == 0 and H % (64 / W) == 0).
+extern "C" int kp_conv_wgrad_tc_img(kp_stream stream, const void* x_bf16, const void* dy_bf16, int N, int H, int W, int Cin,
+                                    int CinP, int Cout, int ks, float* stg, float* dw_oihw) {
+    KP_CHECK_ARG(N > 0 && H > 0 && W >= 16 && (W & (W - 1)) == 0 && (ks == 1 || ks == 3) &&
+                     (W >= 64 || H % (64 / W) == 0) && (long long)N * H * W < (1LL << 31),
+                 "kp_conv_wgrad_tc_img: unsupported image %dx%dx%d k%d", N, H, W, ks);
+    const int img[3] = {N, H, W};
+    return wgrad_tc_impl(stream, x_bf16, dy_bf16, 0, Cin, CinP, Cout, ks * ks, nullptr, stg, dw_oihw, img);
 }

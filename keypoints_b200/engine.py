@@ -37,6 +37,7 @@ def regather_ok(s, h: int, w: int, dout: torch.Tensor, precision: str) -> bool:
         return (w * ncg) % 512 == 0
     return h % 2 == 0 and w % 2 == 0 and ((w // 2) * ncg) % 256 == 0
 BN_MOMENTUM = 0.1
+WGRAD_IMG = os.environ.get('KP_WGRAD_IMG', '1') != '0'
 
 
 @dataclass
@@ -299,8 +300,16 @@ def unit_backward(specs: List[ConvSpec], params: List[LayerParams], grads: List[
             sh = bshifts(s.k, PW)
             stg = alloc(f'{tag}.stg', (max(sp.k * sp.k * sp.cout * cx.x.shape[3] for sp, cx in zip(specs, ctxs) if cx.tc),),
                         torch.float32, dev)
-            L.call('kp_conv_wgrad_tc', st, L.ptr(c.x), L.ptr(dyp), Q, s.cin, cinp, s.cout, len(sh), L.shifts_array(sh),
-                   L.ptr(stg), L.ptr(g.dw), flops=2.0 * N * h * w * s.cin * s.cout * s.k * s.k, tag=f'{tag}{i} {s.cin}->{s.cout}@{h}x{w} k{s.k}')
+            # measured (gpurun_out/calls_s10/s11): the 4-D loads cost more per k-block than the flat 2-D ones, so the image form
+            # wins where the flat form wastes many pixels (W <= 32: 13-27 %) or the tiles are wide (>= 256 channels both sides)
+            if (WGRAD_IMG and w >= 16 and w & (w - 1) == 0 and (w >= 64 or h % (64 // w) == 0)
+                    and (w <= 32 or min(cinp, s.cout) >= 256)):
+                # contraction over the valid pixels only (no MMA work on the pad / zero border)
+                L.call('kp_conv_wgrad_tc_img', st, L.ptr(c.x), L.ptr(dyp), N, h, w, s.cin, cinp, s.cout, s.k, L.ptr(stg),
+                       L.ptr(g.dw), flops=2.0 * N * h * w * s.cin * s.cout * s.k * s.k, tag=f'{tag}{i} {s.cin}->{s.cout}@{h}x{w} k{s.k}')
+            else:
+                L.call('kp_conv_wgrad_tc', st, L.ptr(c.x), L.ptr(dyp), Q, s.cin, cinp, s.cout, len(sh), L.shifts_array(sh),
+                       L.ptr(stg), L.ptr(g.dw), flops=2.0 * N * h * w * s.cin * s.cout * s.k * s.k, tag=f'{tag}{i} {s.cin}->{s.cout}@{h}x{w} k{s.k}')
             if want_dx:
                 dx = alloc(f'{tag}.dx{i}', (N, PH, PW, cinp), T, dev)
                 L.call('kp_conv_tc', st, L.ptr(dyp), Q, s.cout, L.ptr(c.pack['tc_d']), len(sh), L.shifts_array(sh), None,
