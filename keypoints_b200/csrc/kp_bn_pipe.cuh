@@ -400,25 +400,26 @@ bn_fwd_pool_pipe_k(Rows<const bf16> y, Rows<bf16> out, const float* __restrict__
     auto body = [&](const Cursor& cu, const uint8_t* st) {
         const uint4 r00 = pipe::lds16(st + yoff), r01 = pipe::lds16(st + yoff + ncg * 16);
         const uint4 r10 = pipe::lds16(st + PIPE_POOL_YBYTES + yoff), r11 = pipe::lds16(st + PIPE_POOL_YBYTES + yoff + ncg * 16);
+        // the activation is monotone: max over the window of act(z) = act(max z)
         float2 v[4], a[4];
-        auto act8 = [&](const uint4& r, float2 (&o)[4]) {
+        auto z8 = [&](const uint4& r, float2 (&o)[4]) {
             P8<bf16>::up(r, o);
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const float2 z = fma2(o[i], sc[i], sh[i]);
-                o[i] = make_float2(actv<ACT>(z.x), actv<ACT>(z.y));
-            }
+            for (int i = 0; i < 4; ++i) o[i] = fma2(o[i], sc[i], sh[i]);
         };
-        act8(r00, v);
-        act8(r01, a);
+        z8(r00, v);
+        z8(r01, a);
 #pragma unroll
         for (int i = 0; i < 4; ++i) v[i] = make_float2(fmaxf(v[i].x, a[i].x), fmaxf(v[i].y, a[i].y));
-        act8(r10, a);
+        z8(r10, a);
 #pragma unroll
         for (int i = 0; i < 4; ++i) v[i] = make_float2(fmaxf(v[i].x, a[i].x), fmaxf(v[i].y, a[i].y));
-        act8(r11, a);
+        z8(r11, a);
 #pragma unroll
-        for (int i = 0; i < 4; ++i) v[i] = make_float2(fmaxf(v[i].x, a[i].x), fmaxf(v[i].y, a[i].y));
+        for (int i = 0; i < 4; ++i) {
+            v[i] = make_float2(fmaxf(v[i].x, a[i].x), fmaxf(v[i].y, a[i].y));
+            v[i] = make_float2(actv<ACT>(v[i].x), actv<ACT>(v[i].y));
+        }
         const int ox = cu.ch * (PIPE_POOL_ITEMS >> cg_shift) + pl;
         bf16* dst = out.row(cu.n, cu.yy) + (ox + pad) * C + c0;
         const uint4 o = make_uint4(P8<bf16>::pk(v[0]), P8<bf16>::pk(v[1]), P8<bf16>::pk(v[2]), P8<bf16>::pk(v[3]));
@@ -474,7 +475,9 @@ bn_bwd_pool_pipe_k(Rows<const bf16> dout, Rows<const bf16> y, Rows<bf16> dy, con
                 for (int i = 0; i < 4; ++i) t[i] = add2(t[i], e[i]);
             }
         }
-        float2 best[4];
+        // arg-max of the window per channel.  The activation is monotone, so the first maximum of z is the first maximum of
+        // act(z) wherever the routed gradient is non-zero (ties of a ReLU at 0 route a zero gradient either way).
+        float2 zb[4], yb[4];
         int bi[8];
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
@@ -483,31 +486,42 @@ bn_bwd_pool_pipe_k(Rows<const bf16> dout, Rows<const bf16> y, Rows<bf16> dy, con
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
                 const float2 z = fma2(yq[i], sc[i], sh[i]);
-                const float ax = actv<ACT>(z.x), ay = actv<ACT>(z.y);
-                if (q == 0 || ax > best[i].x) { best[i].x = ax; bi[2 * i] = q; }
-                if (q == 0 || ay > best[i].y) { best[i].y = ay; bi[2 * i + 1] = q; }
+                if (q == 0 || z.x > zb[i].x) { zb[i].x = z.x; yb[i].x = yq[i].x; bi[2 * i] = q; }
+                if (q == 0 || z.y > zb[i].y) { zb[i].y = z.y; yb[i].y = yq[i].y; bi[2 * i + 1] = q; }
             }
         }
-        bf16* o0 = MODE == PASS1_SUMS ? nullptr : dy.row(cu.n, 2 * oy) + (2 * ox) * C + c0;
+        float2 dzw[4];                                              // gradient at the winner; every other window pixel gets 0
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            float2 g[4], yq[4];
-            P8<bf16>::up(ry[q], yq);
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const float2 z = fma2(yq[i], sc[i], sh[i]);
-                const float2 dz = make_float2(bi[2 * i] == q ? actg<ACT>(z.x, t[i].x) : 0.f,
-                                              bi[2 * i + 1] == q ? actg<ACT>(z.y, t[i].y) : 0.f);
-                const float2 yc = add2(yq[i], nmu[i]);
-                if (MODE == PASS2_GATHER) {
-                    g[i] = fma2(sc[i], dz, fma2(s2[i], yc, s1[i]));
-                } else {
-                    g[i] = dz;
-                    s1[i] = add2(s1[i], dz);
-                    s2[i] = fma2(dz, yc, s2[i]);
-                }
+        for (int i = 0; i < 4; ++i) {
+            dzw[i] = make_float2(actg<ACT>(zb[i].x, t[i].x), actg<ACT>(zb[i].y, t[i].y));
+            if (MODE == PASS2_GATHER) {
+                dzw[i] = make_float2(sc[i].x * dzw[i].x, sc[i].y * dzw[i].y);
+            } else {
+                s1[i] = add2(s1[i], dzw[i]);
+                s2[i] = fma2(dzw[i], add2(yb[i], nmu[i]), s2[i]);
             }
-            if (MODE != PASS1_SUMS) P8<bf16>::st(o0 + (q >> 1) * dy.sy + (q & 1) * C, g);
+        }
+        if (MODE != PASS1_SUMS) {
+            bf16* o0 = dy.row(cu.n, 2 * oy) + (2 * ox) * C + c0;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                float2 g[4];
+                if (MODE == PASS2_GATHER) {                          // dy = sc*dz + s2*(y - mu) + s1
+                    float2 yq[4];
+                    P8<bf16>::up(ry[q], yq);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        g[i] = fma2(s2[i], add2(yq[i], nmu[i]), s1[i]);
+                        g[i].x += bi[2 * i] == q ? dzw[i].x : 0.f;
+                        g[i].y += bi[2 * i + 1] == q ? dzw[i].y : 0.f;
+                    }
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+                        g[i] = make_float2(bi[2 * i] == q ? dzw[i].x : 0.f, bi[2 * i + 1] == q ? dzw[i].y : 0.f);
+                }
+                P8<bf16>::st(o0 + (q >> 1) * dy.sy + (q & 1) * C, g);
+            }
         }
     };
     pipe_run<PIPE_BPOOL_STAGE, PIPE_BPOOL_STAGES>(smem, units, OH, cpr, issue, body);
