@@ -96,10 +96,18 @@ bn_act_fwd_k(View<TI> y, View<TO> out, const float* __restrict__ scale, const fl
     const float ry = (OH > 1) ? (float)(H - 1) / (float)(OH - 1) : 0.f;
     const float rx = (OW > 1) ? (float)(W - 1) / (float)(OW - 1) : 0.f;
     for (long long p = (long long)blockIdx.x * blockDim.y + threadIdx.y; p < P; p += (long long)gridDim.x * blockDim.y) {
-        int px = (int)(p % PW);
-        long long r = p / PW;
-        int py = (int)(r % PH);
-        int n = (int)(r / PH);
+        int px, py, n;
+        if (P < (1LL << 31)) {                         // 32-bit divisions
+            const unsigned u = (unsigned)p, r = u / (unsigned)PW;
+            px = (int)(u - r * (unsigned)PW);
+            n = (int)(r / (unsigned)PH);
+            py = (int)(r - (unsigned)n * (unsigned)PH);
+        } else {
+            px = (int)(p % PW);
+            long long r = p / PW;
+            py = (int)(r % PH);
+            n = (int)(r / PH);
+        }
         int oy = min(max(py - pad, 0), OH - 1), ox = min(max(px - pad, 0), OW - 1);
         float v[V];
         if (post == KP_POST_NONE) {
@@ -250,10 +258,18 @@ bn_act_bwd_reduce_k(View<TG> dout, View<TY> y, View<TD> dy, const float* __restr
     if (active) {
         for (long long p = (long long)blockIdx.x * blockDim.y + threadIdx.y; p < P;
              p += (long long)gridDim.x * blockDim.y) {
-            int xx = (int)(p % W);
-            long long r = p / W;
-            int yy = (int)(r % H);
-            int n = (int)(r / H);
+            int xx, yy, n;
+            if (P < (1LL << 31)) {                     // 32-bit divisions
+                const unsigned u = (unsigned)p, r = u / (unsigned)W;
+                xx = (int)(u - r * (unsigned)W);
+                n = (int)(r / (unsigned)H);
+                yy = (int)(r - (unsigned)n * (unsigned)H);
+            } else {
+                xx = (int)(p % W);
+                long long r = p / W;
+                yy = (int)(r % H);
+                n = (int)(r / H);
+            }
             float g[V], yv[V];
             compute_dz<TG, TY, V>(dout, y, sc, sh, act, post, pad, n, yy, xx, c0, H, W, OH, OW, ry, rx, g, yv);
 #pragma unroll

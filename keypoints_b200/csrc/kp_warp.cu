@@ -33,10 +33,18 @@ __global__ void __launch_bounds__(256) tps_warp_k(const float* __restrict__ x, f
     const int rows = reduced ? T + 2 : T + 3;
     for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
          idx += (long long)gridDim.x * blockDim.x) {
-        int j = (int)(idx % W);
-        long long r = idx / W;
-        int i = (int)(r % H);
-        int n = (int)(r / H);
+        int i, j, n;
+        if (total < (1LL << 31)) {                    // 32-bit divisions (the 64-bit ones cost more than the whole TPS evaluation)
+            const unsigned u = (unsigned)idx, r = u / (unsigned)W;
+            j = (int)(u - r * (unsigned)W);
+            n = (int)(r / (unsigned)H);
+            i = (int)(r - (unsigned)n * (unsigned)H);
+        } else {
+            j = (int)(idx % W);
+            long long r = idx / W;
+            i = (int)(r % H);
+            n = (int)(r / H);
+        }
         const float* th = theta + (long long)n * rows * 2;
         const float* ct = ctrl + (long long)n * T * 2;
         float px = W > 1 ? (float)j / (float)(W - 1) : 0.f;
@@ -69,10 +77,18 @@ __global__ void __launch_bounds__(256) rotate_warp_k(const float* __restrict__ x
     const long long total = (long long)N * H * W;
     for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
          idx += (long long)gridDim.x * blockDim.x) {
-        int j = (int)(idx % W);
-        long long r = idx / W;
-        int i = (int)(r % H);
-        int n = (int)(r / H);
+        int i, j, n;
+        if (total < (1LL << 31)) {                    // 32-bit divisions (the 64-bit ones cost more than the whole TPS evaluation)
+            const unsigned u = (unsigned)idx, r = u / (unsigned)W;
+            j = (int)(u - r * (unsigned)W);
+            n = (int)(r / (unsigned)H);
+            i = (int)(r - (unsigned)n * (unsigned)H);
+        } else {
+            j = (int)(idx % W);
+            long long r = idx / W;
+            i = (int)(r % H);
+            n = (int)(r / H);
+        }
         float c = cosf(rot[n]), s = sinf(rot[n]);
         float bx = (2.f * j + 1.f) / W - 1.f;          // F.affine_grid base grid, align_corners=False
         float by = (2.f * i + 1.f) / H - 1.f;
