@@ -151,7 +151,7 @@ def main():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--workload', default='keynet_F_128_K10', choices=sorted(WORKLOADS))
     ap.add_argument('--batch', type=int, default=64, help='per-GPU batch (weak scaling)')
-    ap.add_argument('--cpu-batch', type=int, default=4, help='batch of the bounded CPU sample')
+    ap.add_argument('--cpu-batch', type=int, default=16, help='batch of the bounded CPU sample')
     ap.add_argument('--precision', default='bf16', choices=['bf16', 'fp32'])
     ap.add_argument('--no-graph', action='store_true')
     ap.add_argument('--no-cpu-baseline', action='store_true')
