@@ -178,17 +178,23 @@ class Trainer:
 
         def perturb(src, dst, tmp, prm):
             theta, ctrl, rot = prm
-            L.call('kp_tps_warp', st, L.ptr(src), L.ptr(tmp), L.ptr(theta), L.ptr(ctrl), n, c, H, W, T, 0)
-            L.call('kp_rotate_warp', st, L.ptr(tmp), L.ptr(dst), L.ptr(rot), n, c, H, W)
+            s_ = L.stream()
+            L.call('kp_tps_warp', s_, L.ptr(src), L.ptr(tmp), L.ptr(theta), L.ptr(ctrl), n, c, H, W, T, 0)
+            L.call('kp_rotate_warp', s_, L.ptr(tmp), L.ptr(dst), L.ptr(rot), n, c, H, W)
 
         mk = lambda name: self.misc(name, (n, c, H, W), torch.float32, dev)
         tmp, x1, x2, m1, m2, ones = mk('aug.tmp'), mk('aug.x1'), mk('aug.x2'), mk('aug.m1'), mk('aug.m2'), mk('aug.ones')
-        ones.fill_(1.0)
+        tmp_m = mk('aug.tmp_m')
         p1, p2 = draw(), draw()
+        # the loss mask P2(P1(1)) is independent of the image chain P2(P1(x)): the small latency-bound warp kernels of the
+        # two chains run side by side
+        with self._fork():
+            ones.fill_(1.0)
+            perturb(ones, m1, tmp_m, p1)
+            perturb(m1, m2, tmp_m, p2)
         perturb(x, x1, tmp, p1)
-        perturb(ones, m1, tmp, p1)
         perturb(x1, x2, tmp, p2)
-        perturb(m1, m2, tmp, p2)
+        self._join()
         return x1, x2, m2
 
     # ------------------------------------------------------------------------------------------
