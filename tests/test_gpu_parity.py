@@ -513,6 +513,46 @@ def test_full_size_properties_keynet_f_128(dev):
     assert float(d.max()) <= 6.5e-4, float(d.max())            # never further apart than the 3 lr-sized steps (+-)
 
 
+def test_full_size_bf16_path_tracks_fp32_path(dev):
+    """Every fast kernel of the throughput mode at once (A-halo tcgen05 convs, image-mode wgrad, bulk-async BatchNorm
+    passes with regather, mma.sync thin layers) against the fp32 parity-mode kernels on the BASELINE layer sizes:
+    KeyNet F, 128x128x3, K=10, identical weights and inputs, one step.  bf16 activations through 24 BatchNorm layers
+    cannot match fp32 element-wise (the reference's own autocast run deviates by 2.4e-1), so the check is on
+    the loss and on the direction of the weight gradient per Unit."""
+    from keypoints_b200.models import keynet
+    from keypoints_b200.trainer import Trainer
+    torch.manual_seed(3)
+    n, H = 8, 128
+    x = torch.rand(n, 3, H, H, device=dev)
+    xb = x.flip(0).contiguous()
+    out = {}
+    for prec in ('fp32', 'bf16'):
+        torch.manual_seed(5)
+        net = keynet.build('F', 3, 64, 10)
+        tr = Trainer(net, precision=prec, use_graph=False)
+        tr.step(x, xb)
+        k_t, xhat = tr.outputs()
+        out[prec] = (tr.loss(), k_t.clone(), xhat.clone(), tr.flat_g.clone(), {u: s.span for u, s in tr.units.items()})
+    l32, k32, x32, g32, spans = out['fp32']
+    l16, k16, x16, g16, _ = out['bf16']
+    print(f'loss fp32 {l32:.5f} bf16 {l16:.5f};  k max-abs diff {float((k32 - k16).abs().max()):.3e};  '
+          f'x_hat rel diff {float((x32 - x16).abs().max() / x32.abs().max()):.3e}')
+    assert abs(l16 - l32) <= 0.05 * abs(l32)
+    assert float((k32 - k16).abs().max()) < 0.1
+    for unit, (a, b) in spans.items():
+        u, v = g32[a:b].double(), g16[a:b].double()
+        cos = float((u * v).sum() / (u.norm() * v.norm()))
+        ratio = float(v.norm() / u.norm())
+        print(f'  grad[{unit}]: cosine {cos:.4f}  norm ratio {ratio:.3f}')
+        # The keypoint branch is ill-conditioned at initialisation in ANY reduced precision: the heat-maps are almost flat,
+        # so the keypoints sit within +-0.03 of the centre and a 0.02 shift from bf16 rounding of the heat-map changes which
+        # way the decoder wants them moved.  Measured: cosine 0.53 with the current kernels, 0.30 with the round-start
+        # kernels (KP_BN_PIPE=0 KP_TC_HALO=0 KP_THIN_MMA=0 ...), and unchanged when d(maps) is recomputed in fp32 — it is
+        # the forward operating point, not a backward kernel.  It is held to agreement in sign and size only.
+        lo = {'keypoint': 0.15, 'encoder': 0.75}.get(unit, 0.9)      # measured 0.53 / 0.84 / 0.93 (decoder)
+        assert cos > lo and 0.7 < ratio < 1.4, (unit, cos, ratio)
+
+
 def test_batchnorm_output_is_normalised_full_width(dev):
     """Train-mode BatchNorm through the tensor-core path at a BASELINE layer shape (256 -> 256 @ 64x64, batch 8): the
     normalised activations have per-channel mean ~0 and variance ~1 (statistics come from the conv epilogue)."""
