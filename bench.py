@@ -125,6 +125,16 @@ def cpu_reference_rate(wl, batch, steps, warmup, threads=None):
     return batch / per, torch.get_num_threads(), per
 
 
+def workload_config(args, world, graph=None):
+    """The `config` object of the JSON line (identical for both arms)."""
+    kind, mt, cin, z, K, H, W, aug = WORKLOADS[args.workload]
+    cfg = {'workload': args.workload, 'per_gpu_batch': args.batch, 'global_batch': args.batch * world, 'image': [cin, H, W],
+           'keypoints': K, 'augment': 'TpsAndRotate(4,0.05,0.1) on device' if aug else 'none', 'parallelism': f'dp{world}'}
+    if graph is not None:
+        cfg['cuda_graph'] = graph
+    return cfg
+
+
 def run_reference(args):
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
@@ -136,7 +146,8 @@ def run_reference(args):
     line = {'metric': 'training images/sec', 'value': rate, 'unit': 'pairs/s', 'impl': 'reference', 'n_gpus': args.gpus,
             'steps': steps, 'warmup': 1, 'ms_per_step': per * 1e3, 'higher_is_better': True, 'scaling': 'weak',
             'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-            'config': {'workload': wl, 'per_gpu_batch': args.batch, 'sample_batch': batch},
+            'config': dict(workload_config(args, max(args.gpus, 1)), sample_batch=batch,
+                           augment='TpsAndRotate(4,0.05,0.1) on the host' if WORKLOADS[wl][7] else 'none'),
             'cpu_baseline': {'value': rate, 'unit': 'pairs/s', 'cores': cores, 'kind': 'port',
                              'sample': f'{steps} full train steps of {wl} at batch {batch} (fp32, torch CPU ops)'},
             'e2e': {'value': rate, 'unit': 'pairs/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
@@ -308,11 +319,9 @@ def main():
         line = {'metric': 'training images/sec', 'value': value, 'unit': 'pairs/s', 'n_gpus': world, 'steps': args.steps,
                 'warmup': args.warmup, 'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak',
                 'vs_baseline': None, 'dtype': args.precision, 'data': 'synthetic',
-                'config': {'workload': args.workload, 'per_gpu_batch': B, 'global_batch': B * world, 'image': [cin, H, W],
-                           'keypoints': K, 'augment': 'TpsAndRotate(4,0.05,0.1) on device' if aug else 'none',
-                           'parallelism': f'dp{world}', 'cuda_graph': not args.no_graph,
-                           'l2': 'per-step working set (activations, several GB) far exceeds the 126 MB L2',
-                           'frames_per_s': 2 * value},
+                'config': dict(workload_config(args, world, not args.no_graph),
+                               l2='per-step working set (activations, several GB) far exceeds the 126 MB L2',
+                               frames_per_s=2 * value),
                 'e2e': {'value': e2e, 'unit': 'pairs/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': 8,
                         'ms_per_step': ms_e2e / args.steps},
                 'gpu_launches': (launches if launches is not None else (calls_per_step or 0) * args.steps),
