@@ -289,9 +289,11 @@ def main():
                 for t_ms, name, tg, fl in sorted(calls, key=lambda c: -c[0]):
                     fh.write(f'{t_ms:8.4f} ms  {name:24s} {tg:40s} {fl / t_ms / 1e9 if fl else 0:8.1f} TFLOP/s\n')
         total_ms = sum(d[1] for d in agg.values())
-        tc_ms = sum(agg[k][1] for k in ('kp_conv_tc', 'kp_conv_wgrad_tc') if k in agg)
-        tc_fl = sum(agg[k][2] for k in ('kp_conv_tc', 'kp_conv_wgrad_tc') if k in agg)
-        tc_n = sum(agg[k][0] for k in ('kp_conv_tc', 'kp_conv_wgrad_tc') if k in agg)
+        fam = ('kp_conv_tc', 'kp_conv_wgrad_tc', 'kp_conv_wgrad_tc_img')
+        # the deferred fold of the staging gradients belongs to the weight-gradient kernels' time (no flops of its own)
+        tc_ms = sum(agg[k][1] for k in fam + ('kp_wgrad_finalize_multi',) if k in agg)
+        tc_fl = sum(agg[k][2] for k in fam if k in agg)
+        tc_n = sum(agg[k][0] for k in fam if k in agg)
         ach = tc_fl / (tc_ms / 1e3) / 1e12 if tc_ms > 0 else 0.0
         traffic, traffic_note = None, None
         tpath = os.path.join(ROOT, 'profiles', 'r1_tc_traffic.json')

@@ -91,6 +91,10 @@ int kp_conv_tc(kp_stream stream, const void* in_bf16, int64_t Q, int Cin, const 
 int kp_conv_wgrad_tc(kp_stream stream, const void* x_bf16, const void* dy_bf16, int64_t Q, int Cin,
                      int CinP, int Cout, int taps, const int32_t* shifts, float* stg,
                      float* dw_oihw);
+/* Deferred folding: kp_conv_wgrad_tc / _img called with dw_oihw == NULL neither zero `stg` nor fold it; the caller zeroes
+ * its staging arena once per step and folds all layers with one launch.  table_dev: n_layers rows of 7 int64
+ * {stg, dw_oihw, taps, Cout, Cin, CinP, Cout % 128 == 0} in device memory. */
+int kp_wgrad_finalize_multi(kp_stream stream, const void* table_dev, int n_layers);
 /* Image-aware form of the same gradient: x = replicate-padded input [N][H+2][W+2][CinP], dy = interior-aligned
  * gradient [N][H+2][W+2][Cout]; the contraction runs over the N*H*W valid pixels only (4-D TMA boxes of bx x by = 64
  * pixels), so no MMA work is spent on the pad / zero-border pixels the flat form multiplies (3 % of the pixels at

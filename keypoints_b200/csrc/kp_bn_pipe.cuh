@@ -210,13 +210,21 @@ template <int ACT, int MODE>
 __global__ void __launch_bounds__(pipe::THREADS, 2)
 bn_bwd_none_pipe_k(Rows<const bf16> dout, Rows<const bf16> y, Rows<bf16> dy, const float* __restrict__ scale,
                    const float* __restrict__ shift, const float* __restrict__ mean, const float* __restrict__ invstd,
-                   double* sums, double count, int pad, int N, int H, int W, int C, int cg_shift, int cpr) {
+                   double* sums, double count, int pad, int N, int H, int W, int C, int cg_shift, int cpr, float* dgamma,
+                   float* dbeta) {
     extern __shared__ __align__(128) uint8_t smem[];
     const int tid = threadIdx.x;
     const int ncg = C >> 3;
     const int c0 = (tid & (ncg - 1)) * 8;
     float2 sc[4], sh[4], nmu[4], s1[4], s2[4];
     bwd_consts(MODE, scale, shift, mean, invstd, sums, count, C, c0, sc, sh, nmu, s1, s2);
+    if (MODE == PASS2_GATHER && blockIdx.x == 0 && tid < pipe::CONSUMERS && (tid >> cg_shift) == 0) {     // fused kp_bn_grad_finalize
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            if (dbeta) dbeta[c0 + i] = (float)sums[c0 + i];
+            if (dgamma) dgamma[c0 + i] = (float)sums[C + c0 + i];
+        }
+    }
     const int units = N * H * cpr;
     // stage layout: [ext | dout chunk | ext | y chunk]; with a replicate-padded dout the chunk is loaded together with
     // the pixel before and after it, so the left / right border copies of the edge pixels come from shared memory
@@ -437,13 +445,21 @@ template <int ACT, int MODE>
 __global__ void __launch_bounds__(pipe::THREADS, 2)
 bn_bwd_pool_pipe_k(Rows<const bf16> dout, Rows<const bf16> y, Rows<bf16> dy, const float* __restrict__ scale,
                    const float* __restrict__ shift, const float* __restrict__ mean, const float* __restrict__ invstd,
-                   double* sums, double count, int pad, int N, int OH, int OW, int C, int cg_shift, int cpr) {
+                   double* sums, double count, int pad, int N, int OH, int OW, int C, int cg_shift, int cpr, float* dgamma,
+                   float* dbeta) {
     extern __shared__ __align__(128) uint8_t smem[];
     const int tid = threadIdx.x;
     const int ncg = C >> 3;
     const int cg = tid & (ncg - 1), c0 = cg * 8;
     float2 sc[4], sh[4], nmu[4], s1[4], s2[4];
     bwd_consts(MODE, scale, shift, mean, invstd, sums, count, C, c0, sc, sh, nmu, s1, s2);
+    if (MODE == PASS2_GATHER && blockIdx.x == 0 && tid < pipe::CONSUMERS && (tid >> cg_shift) == 0) {     // fused kp_bn_grad_finalize
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            if (dbeta) dbeta[c0 + i] = (float)sums[c0 + i];
+            if (dgamma) dgamma[c0 + i] = (float)sums[C + c0 + i];
+        }
+    }
     const int units = N * OH * cpr;
     const int ext = pad ? C * 2 : 0;
     constexpr int DOFF = 2 * PIPE_POOL_YBYTES + PIPE_EXT;       // dout chunk inside the stage

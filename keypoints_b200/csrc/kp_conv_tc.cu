@@ -1217,6 +1217,24 @@ __global__ void wgrad_finalize_k(const float* __restrict__ stg, float* __restric
     }
 }
 
+struct FoldDesc {
+    const float* stg;
+    float* dw;
+    long long taps, cout, cin, cin_stg, m_is_cout;
+};
+// every layer's staging gradient -> OIHW bucket in one launch (blockIdx.y = layer)
+__global__ void wgrad_finalize_multi_k(const FoldDesc* __restrict__ table) {
+    const FoldDesc d = table[blockIdx.y];
+    const int taps = (int)d.taps, Cout = (int)d.cout, Cin = (int)d.cin, CinStg = (int)d.cin_stg;
+    const unsigned total = (unsigned)(Cout * Cin * taps);
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const unsigned r = i / (unsigned)taps, t = i - r * (unsigned)taps;
+        const unsigned co = r / (unsigned)Cin, ci = r - co * (unsigned)Cin;
+        const float v = d.m_is_cout ? d.stg[((long long)t * Cout + co) * CinStg + ci] : d.stg[((long long)t * CinStg + ci) * Cout + co];
+        d.dw[i] += v;
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
@@ -1444,7 +1462,7 @@ static void choose_split(int tiles, int workers, long long blocks64, long long* 
 // img != nullptr: image mode {N, H, W} (contraction over the valid pixels through 4-D tensor maps)
 static int wgrad_tc_impl(kp_stream stream, const void* x_bf16, const void* dy_bf16, int64_t Q, int Cin, int CinP,
                          int Cout, int taps, const int32_t* shifts, float* stg, float* dw_oihw, const int* img) {
-    KP_CHECK_ARG(x_bf16 && dy_bf16 && stg && dw_oihw && (shifts || img) && (img || (Q > 0 && Q < (1LL << 31) - 4096)) && taps >= 1 &&
+    KP_CHECK_ARG(x_bf16 && dy_bf16 && stg && (shifts || img) && (img || (Q > 0 && Q < (1LL << 31) - 4096)) && taps >= 1 &&
                      taps <= 9 && CinP % 64 == 0 && Cout % 64 == 0 && Cin <= CinP && (Cout % 128 == 0 || CinP % 128 == 0),
                  "kp_conv_wgrad_tc: unsupported shape Q=%lld Cin=%d/%d Cout=%d taps=%d", (long long)Q, Cin, CinP, Cout, taps);
     cudaStream_t st = (cudaStream_t)stream;
@@ -1488,7 +1506,9 @@ static int wgrad_tc_impl(kp_stream stream, const void* x_bf16, const void* dy_bf
     const int tiles = (Mtot / 128) * (Ntot / BN) * taps;
     long long blocks64 = (Q + 63) / 64;
     choose_split(tiles, kp_sm_count(), blocks64, &p.kchunk, &p.splits);
-    KP_CUDA(cudaMemsetAsync(stg, 0, sizeof(float) * (size_t)taps * Mtot * Ntot, st));
+    // dw_oihw == NULL: deferred mode — the caller zeroes its staging arena once per step and folds every layer with one
+    // kp_wgrad_finalize_multi launch (saves a memset and a fold launch per layer)
+    if (dw_oihw) KP_CUDA(cudaMemsetAsync(stg, 0, sizeof(float) * (size_t)taps * Mtot * Ntot, st));
     static int wpair_on = -1;
     if (wpair_on < 0) { const char* e = getenv("KP_TC_PAIR"); wpair_on = (e && e[0] == '0') ? 0 : 1; }
     if (wpair_on && Mtot % 256 == 0 && BN >= 128) {
@@ -1501,6 +1521,7 @@ static int wgrad_tc_impl(kp_stream stream, const void* x_bf16, const void* dy_bf
     else if (BN == 128) rc = launch_wgrad_persist<128, 6>(st, ta, tb, p, taps);
     else rc = launch_wgrad_persist<64, 8>(st, ta, tb, p, taps);
     if (rc) return rc;
+    if (!dw_oihw) return KP_OK;
     long long total = (long long)Cout * Cin * taps;
     int blocks = (int)((total + 255) / 256);
     if (blocks > kp_sm_count() * 8) blocks = kp_sm_count() * 8;
@@ -1523,4 +1544,13 @@ extern "C" int kp_conv_wgrad_tc_img(kp_stream stream, const void* x_bf16, const 
                  "kp_conv_wgrad_tc_img: unsupported image %dx%dx%d k%d", N, H, W, ks);
     const int img[3] = {N, H, W};
     return wgrad_tc_impl(stream, x_bf16, dy_bf16, 0, Cin, CinP, Cout, ks * ks, nullptr, stg, dw_oihw, img);
+}
+
+// table_dev: n_layers rows of 7 int64 {stg, dw_oihw, taps, Cout, Cin, CinP, m_is_cout (= Cout % 128 == 0)} in device memory
+extern "C" int kp_wgrad_finalize_multi(kp_stream stream, const void* table_dev, int n_layers) {
+    KP_CHECK_ARG(table_dev && n_layers > 0 && n_layers <= 65535, "kp_wgrad_finalize_multi: bad arguments");
+    dim3 grid(64u, (unsigned)n_layers, 1);
+    wgrad_finalize_multi_k<<<grid, 256, 0, (cudaStream_t)stream>>>((const FoldDesc*)table_dev);
+    KP_LAUNCH_CHECK();
+    return KP_OK;
 }

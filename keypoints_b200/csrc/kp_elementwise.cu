@@ -1177,13 +1177,13 @@ extern "C" int kp_bn_act_bwd_reduce(kp_stream stream, const kp_view* dout, const
             if (rc_) return rc_;                                                                                       \
             bn_bwd_none_pipe_k<ACTV, PASS1_WRITE><<<pipe_grid(units), pipe::THREADS, smem, st>>>(                      \
                 make_rows<const bf16>(dout), make_rows<const bf16>(y), make_rows<bf16>(dyv), scale, shift, mean,       \
-                invstd, sums, 1.0, pad, N, H, W, C, sh, cpr);                                                          \
+                invstd, sums, 1.0, pad, N, H, W, C, sh, cpr, nullptr, nullptr);                                        \
         } else {                                                                                                       \
             int rc_ = pipe_attr(bn_bwd_none_pipe_k<ACTV, PASS1_SUMS>, smem);                                           \
             if (rc_) return rc_;                                                                                       \
             bn_bwd_none_pipe_k<ACTV, PASS1_SUMS><<<pipe_grid(units), pipe::THREADS, smem, st>>>(                       \
                 make_rows<const bf16>(dout), make_rows<const bf16>(y), make_rows<bf16>(dyv), scale, shift, mean,       \
-                invstd, sums, 1.0, pad, N, H, W, C, sh, cpr);                                                          \
+                invstd, sums, 1.0, pad, N, H, W, C, sh, cpr, nullptr, nullptr);                                        \
         }                                                                                                              \
     } while (0)
                     KP_ACT_SWITCH(act, KP_BWDP);
@@ -1201,13 +1201,13 @@ extern "C" int kp_bn_act_bwd_reduce(kp_stream stream, const kp_view* dout, const
             if (rc_) return rc_;                                                                                       \
             bn_bwd_pool_pipe_k<ACTV, PASS1_WRITE><<<pipe_grid(units), pipe::THREADS, smem, st>>>(                      \
                 make_rows<const bf16>(dout), make_rows<const bf16>(y), make_rows<bf16>(dyv), scale, shift, mean,       \
-                invstd, sums, 1.0, pad, N, OH, OW, C, sh, cpr);                                                        \
+                invstd, sums, 1.0, pad, N, OH, OW, C, sh, cpr, nullptr, nullptr);                                      \
         } else {                                                                                                       \
             int rc_ = pipe_attr(bn_bwd_pool_pipe_k<ACTV, PASS1_SUMS>, smem);                                           \
             if (rc_) return rc_;                                                                                       \
             bn_bwd_pool_pipe_k<ACTV, PASS1_SUMS><<<pipe_grid(units), pipe::THREADS, smem, st>>>(                       \
                 make_rows<const bf16>(dout), make_rows<const bf16>(y), make_rows<bf16>(dyv), scale, shift, mean,       \
-                invstd, sums, 1.0, pad, N, OH, OW, C, sh, cpr);                                                        \
+                invstd, sums, 1.0, pad, N, OH, OW, C, sh, cpr, nullptr, nullptr);                                      \
         }                                                                                                              \
     } while (0)
                     KP_ACT_SWITCH(act, KP_BWDPP);
@@ -1306,11 +1306,10 @@ extern "C" int kp_bn_act_bwd_apply_gather(kp_stream stream, const kp_view* dout,
         if (rc_) return rc_;                                                                                           \
         bn_bwd_none_pipe_k<ACTV, PASS2_GATHER><<<pipe_grid(units), pipe::THREADS, smem, st>>>(                         \
             make_rows<const bf16>(dout), make_rows<const bf16>(y), make_rows<bf16>(dy), scale, shift, mean, invstd,    \
-            const_cast<double*>(sums), count, pad, N, H, W, C, sh, cpr);                                               \
+            const_cast<double*>(sums), count, pad, N, H, W, C, sh, cpr, dgamma, dbeta);                                \
     } while (0)
         KP_ACT_SWITCH(act, KP_GATHN);
 #undef KP_GATHN
-        if (dgamma || dbeta) bn_grad_finalize_k<<<(C + 127) / 128, 128, 0, st>>>(sums, C, dgamma, dbeta);
         KP_LAUNCH_CHECK();
         return KP_OK;
     }
@@ -1324,11 +1323,10 @@ extern "C" int kp_bn_act_bwd_apply_gather(kp_stream stream, const kp_view* dout,
         if (rc_) return rc_;                                                                                           \
         bn_bwd_pool_pipe_k<ACTV, PASS2_GATHER><<<pipe_grid(units), pipe::THREADS, smem, st>>>(                         \
             make_rows<const bf16>(dout), make_rows<const bf16>(y), make_rows<bf16>(dy), scale, shift, mean, invstd,    \
-            const_cast<double*>(sums), count, pad, N, OH, OW, C, sh, cpr);                                             \
+            const_cast<double*>(sums), count, pad, N, OH, OW, C, sh, cpr, dgamma, dbeta);                              \
     } while (0)
         KP_ACT_SWITCH(act, KP_GATHP);
 #undef KP_GATHP
-        if (dgamma || dbeta) bn_grad_finalize_k<<<(C + 127) / 128, 128, 0, st>>>(sums, C, dgamma, dbeta);
         KP_LAUNCH_CHECK();
         return KP_OK;
     }

@@ -250,7 +250,7 @@ def unit_forward(specs: List[ConvSpec], params: List[LayerParams], x_pad: torch.
 
 def unit_backward(specs: List[ConvSpec], params: List[LayerParams], grads: List[LayerGrads], ctxs: List[LayerCtx],
                   dout: torch.Tensor, dout_pad: int, precision: str, need_dx: bool,
-                  alloc: Callable = default_alloc, tag: str = 'u') -> Optional[torch.Tensor]:
+                  alloc: Callable = default_alloc, tag: str = 'u', defer_stg: Optional[List] = None) -> Optional[torch.Tensor]:
     """Backward of one Unit.  ``dout``: gradient w.r.t. the last activation, indexed [n,y,x,c] (ptr at the
     padded origin when dout_pad=1).  Weight gradients are ACCUMULATED into ``grads`` (zero them per step);
     BatchNorm / bias gradients are overwritten.  Returns d(padded input) [N][H+2][W+2][Cp] or None."""
@@ -298,18 +298,22 @@ def unit_backward(specs: List[ConvSpec], params: List[LayerParams], grads: List[
         want_dx = i > 0 or need_dx
         if c.tc:
             sh = bshifts(s.k, PW)
-            stg = alloc(f'{tag}.stg', (max(sp.k * sp.k * sp.cout * cx.x.shape[3] for sp, cx in zip(specs, ctxs) if cx.tc),),
-                        torch.float32, dev)
+            if defer_stg is not None:       # fused trainer: per-layer slice of one arena, zeroed and folded once per step
+                stg, dw_ptr = defer_stg[i], None
+            else:
+                stg = alloc(f'{tag}.stg', (max(sp.k * sp.k * sp.cout * cx.x.shape[3] for sp, cx in zip(specs, ctxs) if cx.tc),),
+                            torch.float32, dev)
+                dw_ptr = L.ptr(g.dw)
             # measured (gpurun_out/calls_s10/s11): the 4-D loads cost more per k-block than the flat 2-D ones, so the image form
             # wins where the flat form wastes many pixels (W <= 32: 13-27 %) or the tiles are wide (>= 256 channels both sides)
             if (WGRAD_IMG and w >= 16 and w & (w - 1) == 0 and (w >= 64 or h % (64 // w) == 0)
                     and (w <= 32 or min(cinp, s.cout) >= 256)):
                 # contraction over the valid pixels only (no MMA work on the pad / zero border)
                 L.call('kp_conv_wgrad_tc_img', st, L.ptr(c.x), L.ptr(dyp), N, h, w, s.cin, cinp, s.cout, s.k, L.ptr(stg),
-                       L.ptr(g.dw), flops=2.0 * N * h * w * s.cin * s.cout * s.k * s.k, tag=f'{tag}{i} {s.cin}->{s.cout}@{h}x{w} k{s.k}')
+                       dw_ptr, flops=2.0 * N * h * w * s.cin * s.cout * s.k * s.k, tag=f'{tag}{i} {s.cin}->{s.cout}@{h}x{w} k{s.k}')
             else:
                 L.call('kp_conv_wgrad_tc', st, L.ptr(c.x), L.ptr(dyp), Q, s.cin, cinp, s.cout, len(sh), L.shifts_array(sh),
-                       L.ptr(stg), L.ptr(g.dw), flops=2.0 * N * h * w * s.cin * s.cout * s.k * s.k, tag=f'{tag}{i} {s.cin}->{s.cout}@{h}x{w} k{s.k}')
+                       L.ptr(stg), dw_ptr, flops=2.0 * N * h * w * s.cin * s.cout * s.k * s.k, tag=f'{tag}{i} {s.cin}->{s.cout}@{h}x{w} k{s.k}')
             if want_dx:
                 dx = alloc(f'{tag}.dx{i}', (N, PH, PW, cinp), T, dev)
                 L.call('kp_conv_tc', st, L.ptr(dyp), Q, s.cout, L.ptr(c.pack['tc_d']), len(sh), L.shifts_array(sh), None,

@@ -43,6 +43,7 @@ SIGNATURES = {
     'kp_conv_tc': [_P, _P, _L, _I, _P, _I, C.POINTER(C.c_int32), _P, _P, _I, _P, _I, _I, _I, _I],
     'kp_conv_wgrad_tc': [_P, _P, _P, _L, _I, _I, _I, _I, C.POINTER(C.c_int32), _P, _P],
     'kp_conv_wgrad_tc_img': [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P, _P],
+    'kp_wgrad_finalize_multi': [_P, _P, _I],
     'kp_pack_weights': [_P, _P, _I, _I, _I, _I, _P, _P, _P, _P],
     'kp_pack_weights_multi': [_P, _P, _I],
     'kp_bn_finalize': [_P, _P, _I, _D, _P, _P, _F, _F, _P, _P, _P, _P, _P, _P, _P],

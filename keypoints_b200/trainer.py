@@ -21,6 +21,9 @@ from .models.keynet import KeyNet
 from .models.transporter import TransporterNet
 
 
+DEFER_FOLD = os.environ.get('KP_DEFER_FOLD', '1') != '0'
+
+
 class _UnitState:
     """Specs, parameter / gradient views into the flat buckets and static buffers of one Unit."""
 
@@ -76,6 +79,7 @@ class Trainer:
         self.step_dev = torch.zeros(1, dtype=torch.int32, device=self.device)
         self.loss_sum = torch.zeros(1, dtype=torch.float64, device=self.device)
         self.numel = 1
+        self._stg, self._fold_table = {}, None
 
     # ------------------------------------------------------------------------------------------
     def _flatten(self):
@@ -139,7 +143,33 @@ class Trainer:
 
     def _bwd_unit(self, u: _UnitState, dout, dout_pad, need_dx):
         return engine.unit_backward(u.specs, u.params, u.grads, u.ctxs, dout, dout_pad, self.precision, need_dx,
-                                    alloc=u.alloc, tag='b')
+                                    alloc=u.alloc, tag='b', defer_stg=self._stg.get(u.name))
+
+    def _staging(self, shapes):
+        """One fp32 arena for the tensor-core weight-gradient staging of every layer (zeroed once per step) and the
+        device table kp_wgrad_finalize_multi folds it with."""
+        key = tuple((n, tuple(v)) for n, v in sorted(shapes.items()))
+        if getattr(self, '_stg_key', None) == key:
+            return
+        self._stg_key, self._stg, self._fold_table = key, {}, None
+        if self.precision != 'bf16' or not DEFER_FOLD:
+            return
+        sizes, off = [], 0
+        for u in self.units.values():
+            for i, (sp, cp) in enumerate(zip(u.specs, shapes[u.name])):
+                if engine.uses_tc(sp, cp, self.precision):
+                    n = sp.k * sp.k * sp.cout * cp
+                    sizes.append((u, i, sp, cp, off, n))
+                    off += (n + 63) // 64 * 64
+        if not sizes:
+            return
+        self._stg_arena = torch.zeros(off, dtype=torch.float32, device=self.device)
+        rows = []
+        for u, i, sp, cp, o, n in sizes:
+            self._stg.setdefault(u.name, [None] * len(u.specs))[i] = self._stg_arena[o:o + n]
+            rows.append([self._stg_arena[o:o + n].data_ptr(), u.grads[i].dw.data_ptr(), sp.k * sp.k, sp.cout, sp.cin, cp,
+                         1 if sp.cout % 128 == 0 else 0])
+        self._fold_table = torch.tensor(rows, dtype=torch.int64).to(self.device)
 
     def _fork(self):
         """Run the following block on the side stream, ordered after everything issued so far (captured as a parallel
@@ -212,8 +242,9 @@ class Trainer:
         cin_p = engine.pitch(c, prec)
         dec_cin = dec.specs[0].cin
         dec_cp = engine.pitch(dec_cin, prec)
-        self._pack({'encoder': self._pitches(enc, cin_p), 'keypoint': self._pitches(kp, cin_p),
-                    'decoder': self._pitches(dec, dec_cp)})
+        shapes = {'encoder': self._pitches(enc, cin_p), 'keypoint': self._pitches(kp, cin_p), 'decoder': self._pitches(dec, dec_cp)}
+        self._pack(shapes)
+        self._staging(shapes)
         dec_in = self.misc('dec_in', (n, h + 2, w + 2, dec_cp), self.T, dev, zero=True)
         heat = self.misc('heat', (n, K, h, w), f32, dev)
         k_t = self.misc('k_t', (n, K, 2), f32, dev)
@@ -266,6 +297,8 @@ class Trainer:
 
         # ---- backward ----
         self.flat_g.zero_()
+        if self._fold_table is not None:
+            self._stg_arena.zero_()
         ddec = self._bwd_unit(dec, dxhat.permute(0, 2, 3, 1), 0, True)
         self._bucket_ready('decoder')
         dk = self.misc('dk', (n, K, 2), f32, dev)
@@ -277,6 +310,7 @@ class Trainer:
                 self._bwd_unit(enc, ddec[..., :C], 1, False)
             self._bwd_unit(kp, dheat.permute(0, 2, 3, 1), 0, False)
             self._join()
+            self._fold_wgrads()
             self._bucket_ready('keypoint')
             self._bucket_ready('encoder')
         else:
@@ -290,8 +324,13 @@ class Trainer:
                 self._bwd_unit(enc, dphi, 0, False)
             self._bwd_unit(kp, dheat.permute(0, 2, 3, 1), 0, False)
             self._join()
+            self._fold_wgrads()
             self._bucket_ready('keypoint')
             self._bucket_ready('encoder')
+
+    def _fold_wgrads(self):
+        if self._fold_table is not None:
+            L.call('kp_wgrad_finalize_multi', L.stream(), L.ptr(self._fold_table), self._fold_table.shape[0])
 
     # ------------------------------------------------------------------------------------------
     def _bucket_ready(self, name):
