@@ -97,9 +97,11 @@ class ClockSampler:
                 'reasons': sorted(reasons), 'samples': len(sm)}
 
 
-def cpu_reference_rate(wl, batch, steps, warmup, threads=None):
+def cpu_reference_rate(wl, batch, steps, warmup, threads=None, check=None):
     """The reference algorithm (oracle port of the reference's PyTorch graph, fp32) on the host cores: full train
-    step (forward, loss, autograd backward, Adam) on a bounded sample of the workload.  Returns (pairs/s, cores, s/step)."""
+    step (forward, loss, autograd backward, Adam) on a bounded sample of the workload.  Returns (pairs/s, cores, s/step).
+    `check` (optional callable) receives the first step's inputs and the oracle's outputs, so the baseline leg doubles as
+    the checker of the CUDA path on the benchmark shapes (the second half of BASELINE's metric: keypoint max-abs-err)."""
     import torch
     from oracle import keypoints_oracle as O
     kind, mt, cin, z, K, H, W, aug = WORKLOADS[wl]
@@ -118,11 +120,40 @@ def cpu_reference_rate(wl, batch, steps, warmup, threads=None):
             a, b, mask = O.tps_and_rotate(x, p1, p2)
         else:
             a, b, mask = x, x.flip(0), None
-        tr.step(a, b, mask)
+        loss, out = tr.step(a, b, mask)
         if i >= warmup:
             times.append(time.perf_counter() - t0)
+        if i == 0 and check is not None:
+            check(a, b, mask, float(loss), out)
     per = sum(times) / len(times)
     return batch / per, torch.get_num_threads(), per
+
+
+def parity_check(args, dev, result):
+    """Returns the `check` callback: the fp32 (parity-mode) CUDA path on the same weights (oracle.init_state_dict seed 0 is
+    what cpu_reference_rate trains) and the same first-step inputs, compared with the oracle's outputs."""
+    def check(a, b, mask, ref_loss, ref_out):
+        import torch
+        from oracle import keypoints_oracle as O
+        from keypoints_b200.models import keynet, transporter
+        from keypoints_b200.trainer import Trainer
+        kind, mt, cin, z, K, H, W, aug = WORKLOADS[args.workload]
+        ops = O.transporter_ops(mt, cin, z, K) if kind == 'transporter' else O.keynet_ops(mt, cin, z, K)
+        net = transporter.make(mt, cin, z, K) if kind == 'transporter' else keynet.build(mt, cin, z, K)
+        net.load_state_dict(O.init_state_dict(ops, 0), strict=True)
+        tr = Trainer(net, precision='fp32', use_graph=False, augment=None, device=dev, process_group=False)
+        tr.step(a.to(dev), b.to(dev), None if mask is None else mask.to(dev))
+        k_t, xhat = tr.outputs()
+        ref_x, ref_k = ref_out[0].detach(), ref_out[2].detach()
+        result.update({
+            'keypoint_max_abs_err': float((k_t.cpu() - ref_k).abs().max()),
+            'recon_max_rel_err': float((xhat.cpu() - ref_x).abs().max() / ref_x.abs().max()),
+            'loss_rel_err': abs(tr.loss() - ref_loss) / abs(ref_loss),
+            'what': f'fp32 parity-mode CUDA path vs the CPU oracle port, first train step of the cpu_baseline sample '
+                    f'({args.workload}, batch {a.shape[0]}, same weights and augmented inputs); bar: 1e-3'})
+        del tr, net
+        torch.cuda.empty_cache()
+    return check
 
 
 def workload_config(args, world, graph=None):
@@ -312,8 +343,9 @@ def main():
         calls_per_step = len(rec)
 
     cpu = None
+    parity = {}
     if rank == 0 and not args.no_cpu_baseline:
-        rate, cores, per = cpu_reference_rate(args.workload, args.cpu_batch, 2, 1)
+        rate, cores, per = cpu_reference_rate(args.workload, args.cpu_batch, 2, 1, check=parity_check(args, dev, parity))
         cpu = {'value': rate, 'unit': 'pairs/s', 'cores': cores, 'kind': 'port',
                'sample': f'2 full train steps of {args.workload} at batch {args.cpu_batch} ({per:.2f} s/step, fp32 torch CPU ops)'}
 
@@ -328,7 +360,7 @@ def main():
                         'ms_per_step': ms_e2e / args.steps},
                 'gpu_launches': (launches if launches is not None else (calls_per_step or 0) * args.steps),
                 'gpu_launches_note': 'C-ABI kernel-launching calls inside the timed region (each >= 1 kernel; replayed from a CUDA graph)',
-                'clocks': clocks, 'roofline': roof, 'cpu_baseline': cpu, 'loss': loss_val,
+                'clocks': clocks, 'roofline': roof, 'cpu_baseline': cpu, 'parity': parity or None, 'loss': loss_val,
                 'activation_bytes': tr.activation_bytes(), 'params': tr.n_params}
         print(json.dumps(line))
     if world > 1:

@@ -63,7 +63,9 @@ class Trainer:
         self.use_graph = use_graph
         self.pg = process_group
         self.world = 1
-        if process_group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()):
+        if process_group is False:           # single-process trainer inside a distributed job (checks, rank-0-only legs)
+            self.pg = None
+        elif process_group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()):
             self.world = torch.distributed.get_world_size(process_group)
         first = net.encoder if self.kind == 'keynet' else net.feature
         # bucket order = order in which backward finishes units
