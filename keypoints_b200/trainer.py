@@ -438,5 +438,50 @@ class Trainer:
         """Keypoints (N,K,2) (y,x) and reconstruction of the last step (static buffers)."""
         return self.misc.bufs[('misc', 'k_t')], self.misc.bufs[('misc', 'xhat')]
 
+    # ------------------------------------------------------------------------------------------
+    # Resume support (SURVEY 8f.3).  The reference checkpoints only the module weights (9 .mdl files, knn.py:143-167) and
+    # restarts Adam from zero; `save` writes those same files through the module plus the optimiser state next to them.
+    def state_dict(self):
+        """Optimiser state of the fused trainer: Adam moments as tensors shaped like the parameters (keyed like
+        ``net.state_dict()``), the step count and the hyper-parameters."""
+        names = {id(p): n for n, p in self.net.named_parameters()}
+        m, v = {}, {}
+        for u in self.units.values():
+            for t in u.tensors():
+                o = t.data.data_ptr() - self.flat_p.data_ptr()
+                assert o % 4 == 0
+                o //= 4
+                k = t.numel()
+                m[names[id(t)]] = self.flat_m[o:o + k].view_as(t).clone()
+                v[names[id(t)]] = self.flat_v[o:o + k].view_as(t).clone()
+        return {'exp_avg': m, 'exp_avg_sq': v, 'step': int(self.step_dev.item()), 'lr': self.lr, 'betas': tuple(self.betas),
+                'eps': self.eps, 'precision': self.precision}
+
+    def load_state_dict(self, sd):
+        names = {n: p for n, p in self.net.named_parameters()}
+        for key, dst in (('exp_avg', self.flat_m), ('exp_avg_sq', self.flat_v)):
+            for n, src in sd[key].items():
+                t = names[n]
+                o = (t.data.data_ptr() - self.flat_p.data_ptr()) // 4
+                dst[o:o + t.numel()].copy_(src.reshape(-1).to(self.device, torch.float32))
+        self.step_dev.fill_(int(sd['step']))
+        self.steps_done = int(sd['step'])
+        self.lr, self.betas, self.eps = float(sd['lr']), tuple(sd['betas']), float(sd['eps'])
+        self.graph = None                      # lr / betas are baked into the captured Adam launch
+
+    def save(self, directory):
+        """Module weights in the reference's layout (loadable by the reference's ``net.load``) + ``trainer.pt``."""
+        import os as _os
+        self.net.save(directory)
+        torch.save(self.state_dict(), _os.path.join(directory, 'trainer.pt'))
+
+    def load(self, directory, map_device=None):
+        import os as _os
+        # the module's parameters alias the flat bucket: load_state_dict copies in place, the aliasing survives
+        self.net.load(directory, map_device=map_device or str(self.device))
+        path = _os.path.join(directory, 'trainer.pt')
+        if _os.path.exists(path):
+            self.load_state_dict(torch.load(path, map_location=self.device))
+
     def activation_bytes(self):
         return sum(u.alloc.nbytes() for u in self.units.values()) + self.misc.nbytes()

@@ -84,3 +84,39 @@ def test_autoencoder_vs_reference_golden(dev, golden):
             e = np.abs(sd[key[5:]].cpu().numpy().astype(np.float64) - g[key]).max()
             R.rows.append((key, e, 0.05 * 1e-4))
     R.finish()
+
+
+def test_trainer_resume_matches_uninterrupted_run(dev, tmp_path):
+    """`Trainer.save` writes the reference's 9 .mdl files plus the Adam state; a fresh trainer that loads
+    them continues exactly where the first one stopped (3 steps == 2 steps + save/load + 1 step, up to the fp32-atomic
+    noise of one step)."""
+    import os
+    from keypoints_b200.models import transporter
+    from keypoints_b200.trainer import Trainer
+    torch.manual_seed(2)
+    xa = torch.rand(4, 1, 32, 32, device=dev) * 2 - 1
+    xb = torch.rand(4, 1, 32, 32, device=dev) * 2 - 1
+
+    def fresh():
+        torch.manual_seed(9)
+        return Trainer(transporter.make('VGG_PONG', 1, 8, 3), precision='fp32', use_graph=False)
+
+    ref = fresh()
+    for _ in range(3):
+        ref.step(xa, xb)
+    a = fresh()
+    for _ in range(2):
+        a.step(xa, xb)
+    a.save(str(tmp_path / 'ck'))
+    files = sorted(os.listdir(tmp_path / 'ck'))
+    assert files == ['decoder', 'encoder', 'keypoint', 'trainer.pt']
+    b = Trainer(transporter.make('VGG_PONG', 1, 8, 3), precision='fp32', use_graph=False)
+    b.load(str(tmp_path / 'ck'))
+    assert int(b.step_dev.item()) == 2
+    assert torch.equal(b.flat_p, a.flat_p) and torch.equal(b.flat_m, a.flat_m) and torch.equal(b.flat_v, a.flat_v)
+    b.step(xa, xb)
+    d = float((b.flat_p - ref.flat_p).abs().max())
+    assert d <= 2e-5, d                                      # a fifth of one lr-sized (1e-4) Adam step
+    # running statistics travel with the module files
+    for (n1, t1), (n2, t2) in zip(ref.net.named_buffers(), b.net.named_buffers()):
+        assert n1 == n2 and torch.allclose(t1.float(), t2.float(), rtol=1e-4, atol=1e-5), n1
