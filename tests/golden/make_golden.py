@@ -188,6 +188,34 @@ def autoencoder_fixture(name, model_type, cin, z, n, h, w, seed, lo, hi):
     print(name, 'loss', float(loss), 'bytes', os.path.getsize(os.path.join(HERE, f'{name}.npz')))
 
 
+def eval_fixture(name, model_type, cin, z, K, h, w, seed):
+    """The demo / inference path (atari_demo.py:20-36): a trained-for-one-step Transporter in eval() mode, key-points of a
+    single frame from `net.keypoint` + the spatial soft-max, and the full eval forward.  BatchNorm uses running statistics."""
+    rng = np.random.default_rng(seed)
+    net = ref_transporter.make(model_type, cin, z, K)
+    ops = O.transporter_ops(model_type, cin, z, K)
+    net.load_state_dict(O.init_state_dict(ops, seed), strict=True)
+    a = synth_images(rng, 3, cin, h, w, -1.0, 1.0)
+    b = synth_images(rng, 3, cin, h, w, -1.0, 1.0)
+    net.train()
+    for _ in range(3):                       # move the running statistics away from (0, 1)
+        net(a, b)
+    net.eval()
+    out = {'meta': np.array([cin, z, K, 1, h, w, seed])}
+    for key, v in net.state_dict().items():
+        out[f'state/{key}'] = npy(v)
+    s_t = synth_images(rng, 1, cin, h, w, -1.0, 1.0)
+    s_u = synth_images(rng, 1, cin, h, w, -1.0, 1.0)
+    with torch.no_grad():
+        heat = net.keypoint(s_t)
+        k = RF.spacial_logsoftmax(heat)
+        res = net(s_t, s_u)
+    out.update({'s_t': npy(s_t), 's_u': npy(s_u), 'eval/heat': npy(heat), 'eval/k': npy(k), 'eval/x_hat': npy(res[0]),
+                'eval/k_full': npy(res[2])})
+    np.savez_compressed(os.path.join(HERE, f'{name}.npz'), **out)
+    print(name, 'bytes', os.path.getsize(os.path.join(HERE, f'{name}.npz')))
+
+
 def model_fixture(name, kind, model_type, cin, z, K, n, h, w, seed, lo, hi, with_mask, adam=False, combine_mode='max'):
     rng = np.random.default_rng(seed)
     if kind == 'transporter':
@@ -258,4 +286,5 @@ if __name__ == '__main__':
         model_fixture('transporter_pong_sum', 'transporter', 'VGG_PONG_LAYERNECK', 1, 16, 4, 2, 36, 28, 106, -1.0, 1.0,
                       with_mask=False, combine_mode='sum_and_clamp')
         autoencoder_fixture('autoencoder_pong', 'VGG_PONG', 1, 8, 3, 24, 16, 107, -1.0, 1.0)
+        eval_fixture('transporter_pong_eval', 'VGG_PONG', 1, 8, 3, 32, 24, 108)
     print('done')

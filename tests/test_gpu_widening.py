@@ -120,3 +120,30 @@ def test_trainer_resume_matches_uninterrupted_run(dev, tmp_path):
     # running statistics travel with the module files
     for (n1, t1), (n2, t2) in zip(ref.net.named_buffers(), b.net.named_buffers()):
         assert n1 == n2 and torch.allclose(t1.float(), t2.float(), rtol=1e-4, atol=1e-5), n1
+
+
+def test_eval_mode_inference_vs_reference_golden(dev, golden):
+    """The demo path (atari_demo.py:35-36): `net.eval()`, `net.keypoint(s_t)` + spatial soft-max at batch 1 and the full
+    eval forward, BatchNorm on the running statistics the reference accumulated; fp32, 1e-3 bar."""
+    import keypoints_b200
+    from keypoints_b200.models import functional as MF, transporter
+    keypoints_b200.set_precision('fp32')
+    g = golden('transporter_pong_eval')
+    cin, z, K, n, h, w, seed = (int(v) for v in g['meta'])
+    net = transporter.make('VGG_PONG', cin, z, K)
+    net.load_state_dict({k[6:]: torch.from_numpy(v) for k, v in g.items() if k.startswith('state/')}, strict=True)
+    net = net.to(dev).eval()
+    s_t, s_u = torch.from_numpy(g['s_t']).to(dev), torch.from_numpy(g['s_u']).to(dev)
+    R = Report()
+    with torch.no_grad():
+        heat = net.keypoint(s_t)
+        k = MF.spacial_logsoftmax(heat)
+        res = net(s_t, s_u)
+    R.close(heat, g['eval/heat'], TOL, 'heat'); R.close(k, g['eval/k'], TOL, 'k')
+    R.close(res[0], g['eval/x_hat'], TOL, 'x_hat'); R.close(res[2], g['eval/k_full'], TOL, 'k_full')
+    R.rows.append(('k max-abs', float((k.cpu() - torch.from_numpy(g['eval/k'])).abs().max()), TOL))
+    # running statistics must not move in eval mode
+    for key, v in g.items():
+        if key.startswith('state/') and 'running' in key:
+            R.close(net.state_dict()[key[6:]], v, 1e-7, key)
+    R.finish()

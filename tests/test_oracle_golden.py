@@ -195,3 +195,18 @@ def test_reference_checkpoint_interop(golden, tmp_path):
         assert list(a.keys()) == list(b.keys())
         for k in a:
             assert torch.equal(a[k], b[k]), (f, k)
+
+
+def test_eval_mode_inference_path(golden):
+    """atari_demo.py:20-36: eval() forward (BatchNorm on running statistics), key-points of one frame."""
+    g = golden('transporter_pong_eval')
+    cin, z, K, n, h, w, seed = (int(v) for v in g['meta'])
+    ops = O.transporter_ops('VGG_PONG', cin, z, K)
+    sd = {k[6:]: torch.from_numpy(v) for k, v in g.items() if k.startswith('state/')}
+    s_t, s_u = torch.from_numpy(g['s_t']), torch.from_numpy(g['s_u'])
+    with torch.no_grad():
+        heat = O.unit_forward(s_t, sd, 'keypoint.', ops['keypoint'], False)
+        k, _ = O.spatial_logsoftmax(heat)
+        res = O.transporter_forward(s_t, s_u, sd, ops, training=False)
+    close(heat, g['eval/heat'], 2e-5, 'heat'); close(k, g['eval/k'], 2e-5, 'k')
+    close(res[0], g['eval/x_hat'], 2e-5, 'x_hat'); close(res[2], g['eval/k_full'], 2e-5, 'k_full')
