@@ -137,9 +137,10 @@ int kp_thin_mma_wgrad(cudaStream_t st, const kp_view* x, const kp_view* dy, floa
 // mma.sync kernels for 3x3 convolutions with 16 / 32 input and output channels in bf16 mode (kp_conv_small_mma.cu)
 bool kp_small_mma_conv_ok(const kp_view* in, const kp_view* out, int N, int OH, int OW, int Cin, int Cout, int ks);
 int kp_small_mma_conv(cudaStream_t st, const kp_view* in, const float* wk, const float* bias, const kp_view* out,
-                      double* stats, int N, int OH, int OW, int IH, int IW, int Cin, int Cout, int off);
+                      double* stats, int N, int OH, int OW, int IH, int IW, int Cin, int Cout, int ks, int off);
 bool kp_small_mma_wgrad_ok(const kp_view* x, const kp_view* dy, int N, int H, int W, int Cin, int Cout, int ks);
-int kp_small_mma_wgrad(cudaStream_t st, const kp_view* x, const kp_view* dy, float* dw, int N, int H, int W, int Cin, int Cout);
+int kp_small_mma_wgrad(cudaStream_t st, const kp_view* x, const kp_view* dy, float* dw, int N, int H, int W, int Cin, int Cout,
+                       int ks);
 // streaming kernels for a 1x1 head with <= 4 outputs on a 64..256-channel bf16 input (kp_conv_thin_mma.cu)
 bool kp_head1x1_ok(const kp_view* wide, const kp_view* thin, int Cw, int Ct);
 int kp_head1x1_fprop(cudaStream_t st, const kp_view* in, const float* wk, const float* bias, const kp_view* out, int N, int H,

@@ -539,7 +539,7 @@ extern "C" int kp_conv_simt(kp_stream stream, const kp_view* in, const float* wk
             return kp_head1x1_dgrad((cudaStream_t)stream, in, wk, out, N, OH, OW, Cout, Cin);
     }
     if (thin_mma_enabled() && kp_small_mma_conv_ok(in, out, N, OH, OW, Cin, Cout, ks))
-        return kp_small_mma_conv((cudaStream_t)stream, in, wk, bias, out, stats, N, OH, OW, IH, IW, Cin, Cout, off);
+        return kp_small_mma_conv((cudaStream_t)stream, in, wk, bias, out, stats, N, OH, OW, IH, IW, Cin, Cout, ks, off);
     if (thin_mma_enabled() && out->dtype == KP_BF16 && kp_thin_mma_fprop_ok(in, out, OH, OW, IH, IW, Cin, Cout, ks, off))
         return kp_thin_mma_fprop((cudaStream_t)stream, in, wk, bias, out, stats, N, OH, OW, Cin, Cout);
     if (thin_fast_enabled() && KKt <= THIN_MAX && Cout % 64 == 0 && out2) {      // thin-K: first conv / dgrad of a thin head
@@ -599,7 +599,7 @@ extern "C" int kp_conv_wgrad_simt(kp_stream stream, const kp_view* x, const kp_v
     if (thin_mma_enabled() && ks == 1 && P < (1LL << 31) && dy->dtype == KP_BF16 && kp_head1x1_ok(x, dy, Cin, Cout))
         return kp_head1x1_wgrad((cudaStream_t)stream, x, dy, dw_oihw, N, H, W, Cin, Cout);
     if (thin_mma_enabled() && kp_small_mma_wgrad_ok(x, dy, N, H, W, Cin, Cout, ks))
-        return kp_small_mma_wgrad((cudaStream_t)stream, x, dy, dw_oihw, N, H, W, Cin, Cout);
+        return kp_small_mma_wgrad((cudaStream_t)stream, x, dy, dw_oihw, N, H, W, Cin, Cout, ks);
     if (thin_mma_enabled() && dy->dtype == KP_BF16 && kp_thin_mma_wgrad_ok(x, dy, W, Cin, Cout, ks))
         return kp_thin_mma_wgrad((cudaStream_t)stream, x, dy, dw_oihw, N, H, W, Cin, Cout);
     if (thin_fast_enabled() && KK <= THIN_MAX && Cout % 64 == 0 && pair_ok(dy)) {

@@ -27,11 +27,11 @@ __device__ __forceinline__ uint32_t ld16(const bf16* p) { return (uint32_t)*rein
 constexpr int SM_WARPS = 8;
 
 // tile = 16 consecutive x of one output row; tiles_per_row = ceil(OW / 16)
-template <int CIN, int COUT, bool CHECK>
+template <int CIN, int COUT, bool CHECK, int TAPS>
 __global__ void __launch_bounds__(SM_WARPS * 32, 2)
 small_mma_conv_k(View<bf16> in, const float* __restrict__ wk, const float* __restrict__ bias, View<bf16> out, double* stats,
                  int N, int OH, int OW, int IH, int IW, int off) {
-    constexpr int KH = CIN / 16, KS = 9 * KH, NT = COUT / 8;
+    constexpr int KH = CIN / 16, KS = TAPS * KH, NT = COUT / 8;      // TAPS = 9 (3x3) or 1 (1x1)
     __shared__ uint2 wf[KS][NT][32];
     __shared__ float red[SM_WARPS][2][COUT];
     __shared__ float sbias[COUT];
@@ -67,8 +67,8 @@ small_mma_conv_k(View<bf16> in, const float* __restrict__ wk, const float* __res
             c[j][0] = b0; c[j][1] = b1; c[j][2] = b0; c[j][3] = b1;
         }
 #pragma unroll
-        for (int t = 0; t < 9; ++t) {
-            const int ty = t / 3, tx = t % 3;
+        for (int t = 0; t < TAPS; ++t) {
+            const int ty = TAPS == 9 ? t / 3 : 0, tx = TAPS == 9 ? t % 3 : 0;
             bool oa = va, ob = vb;
             if (CHECK) {
                 const int iy = y + ty + off;
@@ -128,13 +128,15 @@ small_mma_conv_k(View<bf16> in, const float* __restrict__ wk, const float* __res
 }
 
 // block = 9 warps, warp t accumulates tap t: D[ci (M)][co (N)] over the block's pixel tiles
-template <int CIN, int COUT>
+template <int CIN, int COUT, int TAPS>
 __global__ void __launch_bounds__(288, 2)
 small_mma_wgrad_k(View<bf16> x, View<bf16> dy, float* __restrict__ dw, int N, int H, int W) {
     constexpr int MT = CIN / 16, NJ = COUT / 16;
-    const int lane = threadIdx.x & 31, t = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int g = lane >> 2, q = lane & 3;
-    const int ty = t / 3, tx = t % 3;
+    // 3x3: warp = tap, every warp walks all tiles of the block.  1x1: one tap, the 9 warps split the tiles.
+    const int t = TAPS == 9 ? wid : 0;
+    const int ty = TAPS == 9 ? t / 3 : 0, tx = TAPS == 9 ? t % 3 : 0;
     float c[MT][2 * NJ][4];
 #pragma unroll
     for (int m = 0; m < MT; ++m)
@@ -142,7 +144,8 @@ small_mma_wgrad_k(View<bf16> x, View<bf16> dy, float* __restrict__ dw, int N, in
         for (int j = 0; j < 2 * NJ; ++j) { c[m][j][0] = c[m][j][1] = c[m][j][2] = c[m][j][3] = 0.f; }
     const unsigned tpr = (unsigned)(W + 15) >> 4;
     const unsigned ntiles = (unsigned)N * (unsigned)H * tpr;
-    for (unsigned tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const unsigned first = TAPS == 9 ? blockIdx.x : blockIdx.x * 9 + wid, stride = TAPS == 9 ? gridDim.x : gridDim.x * 9;
+    for (unsigned tile = first; tile < ntiles; tile += stride) {
         const unsigned r = tile / tpr;
         const int x0 = (int)(tile - r * tpr) << 4;
         const int n = (int)(r / (unsigned)H), y = (int)(r - (unsigned)n * (unsigned)H);
@@ -191,7 +194,7 @@ small_mma_wgrad_k(View<bf16> x, View<bf16> dy, float* __restrict__ dw, int N, in
                 const int ci = 16 * m + g + 8 * (e >> 1);
                 const int col = 2 * q + (e & 1);
                 const int co = 16 * (j >> 1) + 2 * col + (j & 1);
-                atomicAdd(&dw[((long long)co * CIN + ci) * 9 + t], c[m][j][e]);
+                atomicAdd(&dw[((long long)co * CIN + ci) * TAPS + t], c[m][j][e]);
             }
 }
 
@@ -203,26 +206,29 @@ static bool small_view_ok(const kp_view* v, int C) {
 }  // namespace
 
 bool kp_small_mma_conv_ok(const kp_view* in, const kp_view* out, int N, int OH, int OW, int Cin, int Cout, int ks) {
-    return ks == 3 && (Cin == 16 || Cin == 32) && (Cout == 16 || Cout == 32) && small_view_ok(in, Cin) && small_view_ok(out, Cout) &&
+    return (ks == 3 || ks == 1) && (Cin == 16 || Cin == 32) && (Cout == 16 || Cout == 32) && small_view_ok(in, Cin) && small_view_ok(out, Cout) &&
            (long long)N * OH * ((OW + 15) / 16) < (1LL << 31);
 }
 
 int kp_small_mma_conv(cudaStream_t st, const kp_view* in, const float* wk, const float* bias, const kp_view* out,
-                      double* stats, int N, int OH, int OW, int IH, int IW, int Cin, int Cout, int off) {
+                      double* stats, int N, int OH, int OW, int IH, int IW, int Cin, int Cout, int ks, int off) {
     const long long tiles = (long long)N * OH * ((OW + 15) / 16);
     long long blocks = (tiles + SM_WARPS - 1) / SM_WARPS;
     const long long cap = (long long)kp_sm_count() * 4;
     if (blocks > cap) blocks = cap;
-    const bool check = !(off >= 0 && OH + off + 2 <= IH && OW + off + 2 <= IW);
+    const bool check = ks == 3 && !(off >= 0 && OH + off + 2 <= IH && OW + off + 2 <= IW);
     const dim3 grid((unsigned)blocks);
 #define KP_SM(CI, CO)                                                                                                       \
     do {                                                                                                                    \
-        if (check)                                                                                                          \
-            small_mma_conv_k<CI, CO, true><<<grid, SM_WARPS * 32, 0, st>>>(make_view<bf16>(in), wk, bias, make_view<bf16>(out), \
-                                                                          stats, N, OH, OW, IH, IW, off);                   \
+        if (ks == 1)                                                                                                        \
+            small_mma_conv_k<CI, CO, false, 1><<<grid, SM_WARPS * 32, 0, st>>>(make_view<bf16>(in), wk, bias,               \
+                                                                              make_view<bf16>(out), stats, N, OH, OW, IH, IW, off); \
+        else if (check)                                                                                                     \
+            small_mma_conv_k<CI, CO, true, 9><<<grid, SM_WARPS * 32, 0, st>>>(make_view<bf16>(in), wk, bias, make_view<bf16>(out), \
+                                                                             stats, N, OH, OW, IH, IW, off);                \
         else                                                                                                                \
-            small_mma_conv_k<CI, CO, false><<<grid, SM_WARPS * 32, 0, st>>>(make_view<bf16>(in), wk, bias,                  \
-                                                                           make_view<bf16>(out), stats, N, OH, OW, IH, IW, off); \
+            small_mma_conv_k<CI, CO, false, 9><<<grid, SM_WARPS * 32, 0, st>>>(make_view<bf16>(in), wk, bias,               \
+                                                                              make_view<bf16>(out), stats, N, OH, OW, IH, IW, off); \
     } while (0)
     if (Cin == 16 && Cout == 16) KP_SM(16, 16);
     else if (Cin == 16 && Cout == 32) KP_SM(16, 32);
@@ -234,17 +240,22 @@ int kp_small_mma_conv(cudaStream_t st, const kp_view* in, const float* wk, const
 }
 
 bool kp_small_mma_wgrad_ok(const kp_view* x, const kp_view* dy, int N, int H, int W, int Cin, int Cout, int ks) {
-    return ks == 3 && (Cin == 16 || Cin == 32) && (Cout == 16 || Cout == 32) && small_view_ok(x, Cin) && small_view_ok(dy, Cout) &&
+    return (ks == 3 || ks == 1) && (Cin == 16 || Cin == 32) && (Cout == 16 || Cout == 32) && small_view_ok(x, Cin) && small_view_ok(dy, Cout) &&
            (long long)N * H * ((W + 15) / 16) < (1LL << 31);
 }
 
-int kp_small_mma_wgrad(cudaStream_t st, const kp_view* x, const kp_view* dy, float* dw, int N, int H, int W, int Cin, int Cout) {
+int kp_small_mma_wgrad(cudaStream_t st, const kp_view* x, const kp_view* dy, float* dw, int N, int H, int W, int Cin, int Cout,
+                       int ks) {
     const long long tiles = (long long)N * H * ((W + 15) / 16);
     long long blocks = tiles;
     const long long cap = (long long)kp_sm_count() * 2;
     if (blocks > cap) blocks = cap;
     const dim3 grid((unsigned)blocks);
-#define KP_SW(CI, CO) small_mma_wgrad_k<CI, CO><<<grid, 288, 0, st>>>(make_view<bf16>(x), make_view<bf16>(dy), dw, N, H, W)
+#define KP_SW(CI, CO)                                                                                                    \
+    do {                                                                                                                 \
+        if (ks == 1) small_mma_wgrad_k<CI, CO, 1><<<grid, 288, 0, st>>>(make_view<bf16>(x), make_view<bf16>(dy), dw, N, H, W); \
+        else small_mma_wgrad_k<CI, CO, 9><<<grid, 288, 0, st>>>(make_view<bf16>(x), make_view<bf16>(dy), dw, N, H, W);   \
+    } while (0)
     if (Cin == 16 && Cout == 16) KP_SW(16, 16);
     else if (Cin == 16 && Cout == 32) KP_SW(16, 32);
     else if (Cin == 32 && Cout == 16) KP_SW(32, 16);

@@ -291,17 +291,18 @@ def test_tensor_core_conv_vs_fp32(dev, cin, cout, k, n, h, w):
     close(dx, xr.grad, 2e-2, 'dgrad')
 
 
-@pytest.mark.parametrize('cin,cout,n,h,w', [(16, 32, 2, 20, 20), (32, 32, 3, 84, 84), (32, 16, 2, 9, 33), (16, 16, 2, 16, 48)])
-def test_small_channel_mma_conv_vs_fp32(dev, cin, cout, n, h, w):
+@pytest.mark.parametrize('cin,cout,n,h,w,k', [(16, 32, 2, 20, 20, 3), (32, 32, 3, 84, 84, 3), (32, 16, 2, 9, 33, 3),
+                                                  (16, 16, 2, 16, 48, 3), (32, 16, 2, 84, 84, 1), (16, 32, 3, 10, 21, 1)])
+def test_small_channel_mma_conv_vs_fp32(dev, cin, cout, n, h, w, k):
     """The 16/32-channel 3x3 layers of the VGG_PONG* nets in bf16 mode (mma.sync kernels, kp_conv_small_mma.cu): fprop,
     dgrad (bounds-checked taps) and wgrad against an fp32 reference fed the same bf16-rounded operands; odd widths
     exercise the masked row tails."""
     from keypoints_b200 import engine
     from keypoints_b200.engine import ConvSpec, LayerParams, LayerGrads
     torch.manual_seed(cin * 100 + cout + w)
-    spec = ConvSpec(k=3, cin=cin, cout=cout, bn=True, act='none')
+    spec = ConvSpec(k=k, cin=cin, cout=cout, bn=True, act='none')
     x = torch.randn(n, cin, h, w).bfloat16().float()
-    wt = (torch.randn(cout, cin, 3, 3) / (cin * 9) ** 0.5).bfloat16().float()
+    wt = (torch.randn(cout, cin, k, k) / (cin * k * k) ** 0.5).bfloat16().float()
     bias = torch.randn(cout) * 0.1
     p = LayerParams(w=wt.to(dev), b=bias.to(dev), gamma=torch.ones(cout, device=dev), beta=torch.zeros(cout, device=dev),
                     rmean=torch.zeros(cout, device=dev), rvar=torch.ones(cout, device=dev),
@@ -320,7 +321,7 @@ def test_small_channel_mma_conv_vs_fp32(dev, cin, cout, n, h, w):
     wr = wt.clone().requires_grad_(True)
     ref = torch.nn.functional.batch_norm(_conv_ref(xr, wr, bias), None, None, training=True)
     ref.backward(dout)
-    g = LayerGrads(dw=torch.zeros(cout, cin, 3, 3, device=dev), db=torch.zeros(cout, device=dev),
+    g = LayerGrads(dw=torch.zeros(cout, cin, k, k, device=dev), db=torch.zeros(cout, device=dev),
                    dgamma=torch.zeros(cout, device=dev), dbeta=torch.zeros(cout, device=dev))
     dxp = engine.unit_backward([spec], [p], [g], ctxs, dout.to(dev).permute(0, 2, 3, 1), 0, 'bf16', True)
     dx = engine.fold_to_nchw(dxp, cin, h, w)
