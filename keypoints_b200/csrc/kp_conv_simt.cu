@@ -538,6 +538,8 @@ extern "C" int kp_conv_simt(kp_stream stream, const kp_view* in, const float* wk
         if (!bias && out->dtype == KP_BF16 && in->dtype == KP_BF16 && kp_head1x1_ok(out, in, Cout, Cin))
             return kp_head1x1_dgrad((cudaStream_t)stream, in, wk, out, N, OH, OW, Cout, Cin);
     }
+    if (thin_mma_enabled() && kp_c1_conv_ok(in, out, OH, OW, IH, IW, Cin, Cout, ks, off))
+        return kp_c1_fprop((cudaStream_t)stream, in, wk, bias, out, stats, N, OH, OW, Cout);
     if (thin_mma_enabled() && kp_small_mma_conv_ok(in, out, N, OH, OW, Cin, Cout, ks))
         return kp_small_mma_conv((cudaStream_t)stream, in, wk, bias, out, stats, N, OH, OW, IH, IW, Cin, Cout, ks, off);
     if (thin_mma_enabled() && out->dtype == KP_BF16 && kp_thin_mma_fprop_ok(in, out, OH, OW, IH, IW, Cin, Cout, ks, off))
@@ -598,6 +600,8 @@ extern "C" int kp_conv_wgrad_simt(kp_stream stream, const kp_view* x, const kp_v
     };
     if (thin_mma_enabled() && ks == 1 && P < (1LL << 31) && dy->dtype == KP_BF16 && kp_head1x1_ok(x, dy, Cin, Cout))
         return kp_head1x1_wgrad((cudaStream_t)stream, x, dy, dw_oihw, N, H, W, Cin, Cout);
+    if (thin_mma_enabled() && kp_c1_wgrad_ok(x, dy, Cin, Cout, ks))
+        return kp_c1_wgrad((cudaStream_t)stream, x, dy, dw_oihw, N, H, W, Cout);
     if (thin_mma_enabled() && kp_small_mma_wgrad_ok(x, dy, N, H, W, Cin, Cout, ks))
         return kp_small_mma_wgrad((cudaStream_t)stream, x, dy, dw_oihw, N, H, W, Cin, Cout, ks);
     if (thin_mma_enabled() && dy->dtype == KP_BF16 && kp_thin_mma_wgrad_ok(x, dy, W, Cin, Cout, ks))

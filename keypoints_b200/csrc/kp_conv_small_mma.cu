@@ -198,6 +198,112 @@ small_mma_wgrad_k(View<bf16> x, View<bf16> dy, float* __restrict__ dw, int N, in
             }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Single-channel first layer (grey-scale nets: 1 -> Cout, 3x3).  9 MACs per output: a streaming kernel, one thread per
+// (pixel, 8 output channels), the 3x3 window comes from L1 (the 1-channel padded image is contiguous in x).
+// ------------------------------------------------------------------------------------------------
+template <int G>        // G = Cout / 8 threads per pixel
+__global__ void __launch_bounds__(256)
+c1_fprop_k(View<bf16> in, const float* __restrict__ wk /*[9][Cout]*/, const float* __restrict__ bias, View<bf16> out,
+           double* stats, int N, int OH, int OW) {
+    constexpr int COUT = 8 * G, PPB = 256 / G;                   // pixels per block iteration
+    __shared__ float red[2][256 * 8];
+    const int gl = threadIdx.x % G, px = threadIdx.x / G;
+    float w[9][8], b[8], s1[8], s2[8];
+#pragma unroll
+    for (int t = 0; t < 9; ++t)
+#pragma unroll
+        for (int i = 0; i < 8; ++i) w[t][i] = wk[t * COUT + gl * 8 + i];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { b[i] = bias ? bias[gl * 8 + i] : 0.f; s1[i] = 0.f; s2[i] = 0.f; }
+    const int rows = N * OH;
+    for (int row = blockIdx.x; row < rows; row += gridDim.x) {
+        const int n = row / OH, y = row - n * OH;
+        const bf16* r0 = in.at(n, y, 0, 0);
+        bf16* orow = out.at(n, y, 0, gl * 8);
+        for (int x = px; x < OW; x += PPB) {
+            float v[9];
+#pragma unroll
+            for (int t = 0; t < 9; ++t) v[t] = __bfloat162float(r0[(t / 3) * in.sy + (x + t % 3) * in.sx]);
+            float o[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                float a = b[i];
+#pragma unroll
+                for (int t = 0; t < 9; ++t) a = fmaf(v[t], w[t][i], a);
+                o[i] = a;
+                s1[i] += a;
+                s2[i] = fmaf(a, a, s2[i]);
+            }
+            uint4 u;
+            u.x = pk2(o[0], o[1]); u.y = pk2(o[2], o[3]); u.z = pk2(o[4], o[5]); u.w = pk2(o[6], o[7]);
+            *reinterpret_cast<uint4*>(orow + (long long)x * out.sx) = u;
+        }
+    }
+    if (stats) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { red[0][threadIdx.x * 8 + i] = s1[i]; red[1][threadIdx.x * 8 + i] = s2[i]; }
+        __syncthreads();
+        for (int ch = threadIdx.x; ch < COUT; ch += 256) {
+            const int g8 = ch >> 3, i = ch & 7;
+            float a = 0.f, c = 0.f;
+            for (int t = g8; t < 256; t += G) { a += red[0][t * 8 + i]; c += red[1][t * 8 + i]; }
+            atomicAdd(&stats[ch], (double)a);
+            atomicAdd(&stats[COUT + ch], (double)c);
+        }
+    }
+}
+
+// dw[co][0][t] += sum_pix dy[pix][co] * x[pix + tap t]
+template <int G>
+__global__ void __launch_bounds__(256)
+c1_wgrad_k(View<bf16> x, View<bf16> dy, float* __restrict__ dw, int N, int H, int W) {
+    constexpr int COUT = 8 * G, PPB = 256 / G;
+    __shared__ float red[9 * 64];
+    const int gl = threadIdx.x % G, px = threadIdx.x / G;
+    float acc[9][8];
+#pragma unroll
+    for (int t = 0; t < 9; ++t)
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[t][i] = 0.f;
+    const int rows = N * H;
+    for (int row = blockIdx.x; row < rows; row += gridDim.x) {
+        const int n = row / H, y = row - n * H;
+        const bf16* r0 = x.at(n, y, 0, 0);
+        const bf16* drow = dy.at(n, y, 0, gl * 8);
+        for (int xx = px; xx < W; xx += PPB) {
+            const uint4 u = *reinterpret_cast<const uint4*>(drow + (long long)xx * dy.sx);
+            const uint32_t uw[4] = {u.x, u.y, u.z, u.w};
+            float g[8];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) { g[2 * i] = __uint_as_float(uw[i] << 16); g[2 * i + 1] = __uint_as_float(uw[i] & 0xffff0000u); }
+#pragma unroll
+            for (int t = 0; t < 9; ++t) {
+                const float v = __bfloat162float(r0[(t / 3) * x.sy + (xx + t % 3) * x.sx]);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) acc[t][i] = fmaf(v, g[i], acc[t][i]);
+            }
+        }
+    }
+    for (int i = threadIdx.x; i < 9 * COUT; i += 256) red[i] = 0.f;
+    __syncthreads();
+#pragma unroll
+    for (int t = 0; t < 9; ++t)
+#pragma unroll
+        for (int i = 0; i < 8; ++i) atomicAdd(&red[t * COUT + gl * 8 + i], acc[t][i]);
+    __syncthreads();
+    for (int i = threadIdx.x; i < 9 * COUT; i += 256) {
+        const int t = i / COUT, co = i - t * COUT;
+        atomicAdd(&dw[co * 9 + t], red[i]);
+    }
+}
+
+static bool c1_view_ok(const kp_view* v) { return v->dtype == KP_BF16 && v->sc == 1; }
+static bool c1_wide_ok(const kp_view* v, int C) {
+    return v->dtype == KP_BF16 && v->sc == 1 && C % 8 == 0 && C >= 8 && C <= 64 && (C & (C - 1)) == 0 &&
+           (((uintptr_t)v->ptr) % 16) == 0 && v->sx % 8 == 0 && v->sy % 8 == 0 && v->sn % 8 == 0;
+}
+
 static bool small_view_ok(const kp_view* v, int C) {
     return v->dtype == KP_BF16 && v->sc == 1 && (((uintptr_t)v->ptr) % 4) == 0 && v->sx % 2 == 0 && v->sy % 2 == 0 &&
            v->sn % 2 == 0 && v->sx >= C;
@@ -261,6 +367,37 @@ int kp_small_mma_wgrad(cudaStream_t st, const kp_view* x, const kp_view* dy, flo
     else if (Cin == 32 && Cout == 16) KP_SW(32, 16);
     else KP_SW(32, 32);
 #undef KP_SW
+    KP_LAUNCH_CHECK();
+    return KP_OK;
+}
+
+bool kp_c1_conv_ok(const kp_view* in, const kp_view* out, int OH, int OW, int IH, int IW, int Cin, int Cout, int ks, int off) {
+    return ks == 3 && Cin == 1 && off == 0 && IH >= OH + 2 && IW >= OW + 2 && c1_view_ok(in) && c1_wide_ok(out, Cout);
+}
+
+int kp_c1_fprop(cudaStream_t st, const kp_view* in, const float* wk, const float* bias, const kp_view* out, double* stats, int N,
+                int OH, int OW, int Cout) {
+    long long rows = (long long)N * OH;
+    const long long cap = (long long)kp_sm_count() * 8;
+    const int grid = (int)(rows < cap ? rows : cap);
+#define KP_C1(GV) c1_fprop_k<GV><<<grid, 256, 0, st>>>(make_view<bf16>(in), wk, bias, make_view<bf16>(out), stats, N, OH, OW)
+    if (Cout == 8) KP_C1(1); else if (Cout == 16) KP_C1(2); else if (Cout == 32) KP_C1(4); else KP_C1(8);
+#undef KP_C1
+    KP_LAUNCH_CHECK();
+    return KP_OK;
+}
+
+bool kp_c1_wgrad_ok(const kp_view* x, const kp_view* dy, int Cin, int Cout, int ks) {
+    return ks == 3 && Cin == 1 && c1_view_ok(x) && c1_wide_ok(dy, Cout);
+}
+
+int kp_c1_wgrad(cudaStream_t st, const kp_view* x, const kp_view* dy, float* dw, int N, int H, int W, int Cout) {
+    long long rows = (long long)N * H;
+    const long long cap = (long long)kp_sm_count() * 4;
+    const int grid = (int)(rows < cap ? rows : cap);
+#define KP_C1W(GV) c1_wgrad_k<GV><<<grid, 256, 0, st>>>(make_view<bf16>(x), make_view<bf16>(dy), dw, N, H, W)
+    if (Cout == 8) KP_C1W(1); else if (Cout == 16) KP_C1W(2); else if (Cout == 32) KP_C1W(4); else KP_C1W(8);
+#undef KP_C1W
     KP_LAUNCH_CHECK();
     return KP_OK;
 }

@@ -292,7 +292,8 @@ def test_tensor_core_conv_vs_fp32(dev, cin, cout, k, n, h, w):
 
 
 @pytest.mark.parametrize('cin,cout,n,h,w,k', [(16, 32, 2, 20, 20, 3), (32, 32, 3, 84, 84, 3), (32, 16, 2, 9, 33, 3),
-                                                  (16, 16, 2, 16, 48, 3), (32, 16, 2, 84, 84, 1), (16, 32, 3, 10, 21, 1)])
+                                                  (16, 16, 2, 16, 48, 3), (32, 16, 2, 84, 84, 1), (16, 32, 3, 10, 21, 1),
+                                                  (1, 16, 2, 84, 84, 3), (1, 32, 3, 20, 13, 3)])
 def test_small_channel_mma_conv_vs_fp32(dev, cin, cout, n, h, w, k):
     """The 16/32-channel 3x3 layers of the VGG_PONG* nets in bf16 mode (mma.sync kernels, kp_conv_small_mma.cu): fprop,
     dgrad (bounds-checked taps) and wgrad against an fp32 reference fed the same bf16-rounded operands; odd widths
