@@ -8,6 +8,7 @@
 //   wgrad : dw[co][ci][t] += sum_pix in[pix + tap t][ci] dy[pix][co]; one warp per tap, the dy fragments are built from
 //           4-byte loads with byte permutes (both operands have pixels as the slow axis; output columns relabelled)
 #include "kp_common.cuh"
+#include <stdlib.h>
 
 namespace {
 
@@ -287,10 +288,18 @@ c1_wgrad_k(View<bf16> x, View<bf16> dy, float* __restrict__ dw, int N, int H, in
     }
     for (int i = threadIdx.x; i < 9 * COUT; i += 256) red[i] = 0.f;
     __syncthreads();
+    // lanes l and l + G, l + 2G, ... of a warp hold the same channel group: combine them with shuffles first (128-way
+    // contended shared-memory atomics were the whole run time of this kernel)
+    const int lane = threadIdx.x & 31;
 #pragma unroll
     for (int t = 0; t < 9; ++t)
 #pragma unroll
-        for (int i = 0; i < 8; ++i) atomicAdd(&red[t * COUT + gl * 8 + i], acc[t][i]);
+        for (int i = 0; i < 8; ++i) {
+            float v = acc[t][i];
+#pragma unroll
+            for (int o = G; o < 32; o <<= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+            if (lane < G) atomicAdd(&red[t * COUT + gl * 8 + i], v);
+        }
     __syncthreads();
     for (int i = threadIdx.x; i < 9 * COUT; i += 256) {
         const int t = i / COUT, co = i - t * COUT;
@@ -354,7 +363,9 @@ int kp_small_mma_wgrad(cudaStream_t st, const kp_view* x, const kp_view* dy, flo
                        int ks) {
     const long long tiles = (long long)N * H * ((W + 15) / 16);
     long long blocks = tiles;
-    const long long cap = (long long)kp_sm_count() * 2;
+    static int mult = -1;
+    if (mult < 0) { const char* e = getenv("KP_SMALL_WGRAD_MULT"); mult = e ? atoi(e) : 2; if (mult < 1) mult = 1; }
+    const long long cap = (long long)kp_sm_count() * mult;
     if (blocks > cap) blocks = cap;
     const dim3 grid((unsigned)blocks);
 #define KP_SW(CI, CO)                                                                                                    \
@@ -393,7 +404,9 @@ bool kp_c1_wgrad_ok(const kp_view* x, const kp_view* dy, int Cin, int Cout, int 
 
 int kp_c1_wgrad(cudaStream_t st, const kp_view* x, const kp_view* dy, float* dw, int N, int H, int W, int Cout) {
     long long rows = (long long)N * H;
-    const long long cap = (long long)kp_sm_count() * 4;
+    static int mult = -1;
+    if (mult < 0) { const char* e = getenv("KP_C1_WGRAD_MULT"); mult = e ? atoi(e) : 2; if (mult < 1) mult = 1; }
+    const long long cap = (long long)kp_sm_count() * mult;
     const int grid = (int)(rows < cap ? rows : cap);
 #define KP_C1W(GV) c1_wgrad_k<GV><<<grid, 256, 0, st>>>(make_view<bf16>(x), make_view<bf16>(dy), dw, N, H, W)
     if (Cout == 8) KP_C1W(1); else if (Cout == 16) KP_C1W(2); else if (Cout == 32) KP_C1W(4); else KP_C1W(8);
