@@ -391,10 +391,15 @@ head1x1_wgrad_k(View<bf16> x, View<bf16> dy, float* __restrict__ dw, int N, int 
     }
     for (int i = threadIdx.x; i < CT * Cw; i += blockDim.x) red[i] = 0.f;
     __syncthreads();
+    // lanes gl, gl + G, ... of a warp hold the same channels: combine them with shuffles before the shared-memory atomics
 #pragma unroll
     for (int c = 0; c < CT; ++c)
 #pragma unroll
-        for (int i = 0; i < 8; ++i) atomicAdd(&red[c * Cw + gl * 8 + i], acc[c][i]);
+        for (int i = 0; i < 8; ++i) {
+            float v = acc[c][i];
+            for (int o = G; o < 32; o <<= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+            if ((threadIdx.x & 31) < G) atomicAdd(&red[c * Cw + gl * 8 + i], v);
+        }
     __syncthreads();
     for (int i = threadIdx.x; i < CT * Cw; i += blockDim.x) atomicAdd(&dw[i], red[i]);      // dw OIHW [co][ci] for a 1x1 conv
 }
