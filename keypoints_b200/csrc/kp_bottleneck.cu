@@ -180,6 +180,113 @@ transport_fwd_k(View<TP> phi_s, View<TP> phi_t, const float* __restrict__ k_s, c
     }
 }
 
+// Vectorised 'max' transport (the shapes the nets use: C % 8 == 0, C / 8 a power of two <= 32, 16-byte aligned views).
+// G = C / 8 threads share one padded output pixel: the 2K rendered maps are evaluated ONCE per pixel (keypoints strided over
+// the group, max / first-argmax folded with shuffles) and every thread moves one 128-bit vector of 8 channels.
+template <typename TP, typename TO, int G>
+__global__ void __launch_bounds__(256)
+transport_fwd_vec_k(View<TP> phi_s, View<TP> phi_t, const float* __restrict__ k_s, const float* __restrict__ k_t,
+                    View<TO> out, int pad, float* mask_s, float* mask_t, int* argmax_t, int N, int h, int w, int K,
+                    float two_s2, float eps) {
+    const unsigned PH = h + 2 * pad, PW = w + 2 * pad;
+    const unsigned total = (unsigned)N * PH * PW;
+    const unsigned gl = threadIdx.x % G, ppb = 256 / G;
+    const unsigned step = gridDim.x * ppb;
+    const unsigned trips = (total + step - 1) / step;
+    unsigned p = blockIdx.x * ppb + threadIdx.x / G;
+    for (unsigned it = 0; it < trips; ++it, p += step) {
+        const bool valid = p < total;
+        const unsigned pc = valid ? p : 0;
+        const unsigned r = pc / PW, px = pc - r * PW;
+        const unsigned n = r / PH, py = r - n * PH;
+        const int i = min(max((int)py - pad, 0), h - 1), j = min(max((int)px - pad, 0), w - 1);
+        const float yi = ruler(i, h), xj = ruler(j, w);
+        float ms = -INFINITY, mt = -INFINITY;
+        int am = K;
+        const float2* ks2 = reinterpret_cast<const float2*>(k_s) + (size_t)n * K;
+        const float2* kt2 = reinterpret_cast<const float2*>(k_t) + (size_t)n * K;
+        for (int q = gl; q < K; q += G) {
+            const float2 a2 = ks2[q], b2 = kt2[q];
+            const float a = gauss(yi, xj, a2.x, a2.y, two_s2, eps);
+            const float b = gauss(yi, xj, b2.x, b2.y, two_s2, eps);
+            ms = fmaxf(ms, a);
+            if (b > mt) { mt = b; am = q; }
+        }
+#pragma unroll
+        for (int o = 1; o < G; o <<= 1) {
+            ms = fmaxf(ms, __shfl_xor_sync(0xffffffffu, ms, o));
+            const float omt = __shfl_xor_sync(0xffffffffu, mt, o);
+            const int oam = __shfl_xor_sync(0xffffffffu, am, o);
+            if (omt > mt || (omt == mt && oam < am)) { mt = omt; am = oam; }   // first maximum wins, as torch.max(dim=1)
+        }
+        if (!valid) continue;
+        float ps[8], pt[8], o8[8];
+        Vec<TP, 8>::load(phi_s.at(n, i, j, gl * 8), ps);
+        Vec<TP, 8>::load(phi_t.at(n, i, j, gl * 8), pt);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) o8[e] = ps[e] * (1.f - ms) * (1.f - mt) + pt[e] * mt;
+        Vec<TO, 8>::store(out.at(n, py, px, gl * 8), o8);
+        if (gl == 0 && (int)py - pad == i && (int)px - pad == j) {
+            const size_t e = ((size_t)n * h + i) * w + j;
+            if (mask_s) mask_s[e] = ms;
+            if (mask_t) mask_t[e] = mt;
+            if (argmax_t) argmax_t[e] = am;
+        }
+    }
+}
+
+template <typename TG, typename TP, typename TD, int G>
+__global__ void __launch_bounds__(256)
+transport_bwd_vec_k(View<TG> dout, int pad, View<TP> phi_s, View<TP> phi_t, const float* __restrict__ mask_s,
+                    const float* __restrict__ mask_t, View<TD> dphi_t, float* dmask_t, int N, int h, int w) {
+    const unsigned total = (unsigned)N * h * w;
+    const unsigned gl = threadIdx.x % G, ppb = 256 / G;
+    const unsigned step = gridDim.x * ppb;
+    const unsigned trips = (total + step - 1) / step;
+    unsigned p = blockIdx.x * ppb + threadIdx.x / G;
+    for (unsigned it = 0; it < trips; ++it, p += step) {
+        const bool valid = p < total;
+        const unsigned pc = valid ? p : 0;
+        const unsigned r = pc / (unsigned)w;
+        const int j = (int)(pc - r * w);
+        const int n = (int)(r / (unsigned)h), i = (int)(r - (unsigned)n * h);
+        const float ms = mask_s[pc], mt = mask_t[pc];
+        float g[8], ps[8], pt[8], d8[8];
+        Vec<TG, 8>::load(dout.at(n, i + pad, j + pad, gl * 8), g);
+        if (pad && (i == 0 || i == h - 1 || j == 0 || j == w - 1)) {      // fold the replicate-pad border into the edge pixel
+            int ys[3], xs[3], ny = 0, nx = 0;
+            ys[ny++] = i + 1; if (i == 0) ys[ny++] = 0; if (i == h - 1) ys[ny++] = h + 1;
+            xs[nx++] = j + 1; if (j == 0) xs[nx++] = 0; if (j == w - 1) xs[nx++] = w + 1;
+            for (int a = 0; a < ny; ++a)
+                for (int b = 0; b < nx; ++b) {
+                    if (a == 0 && b == 0) continue;
+                    float t[8];
+                    Vec<TG, 8>::load(dout.at(n, ys[a], xs[b], gl * 8), t);
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) g[e] += t[e];
+                }
+        }
+        Vec<TP, 8>::load(phi_s.at(n, i, j, gl * 8), ps);
+        Vec<TP, 8>::load(phi_t.at(n, i, j, gl * 8), pt);
+        float acc = 0.f;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            d8[e] = g[e] * mt;
+            acc += g[e] * (pt[e] - ps[e] * (1.f - ms));
+        }
+#pragma unroll
+        for (int o = 1; o < G; o <<= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        if (!valid) continue;
+        Vec<TD, 8>::store(dphi_t.at(n, i, j, gl * 8), d8);
+        if (gl == 0) dmask_t[pc] = acc;
+    }
+}
+
+static inline int transport_group(int C) {
+    const int g = C / 8;
+    return (C % 8 == 0 && g >= 1 && g <= 32 && (g & (g - 1)) == 0) ? g : 0;
+}
+
 // one warp per pixel: dphi_t = dout * M_t ; dmask_t = sum_c dout (phi_t - phi_s (1 - M_s))
 template <typename TG, typename TP, typename TD>
 __global__ void __launch_bounds__(256)
@@ -414,6 +521,33 @@ extern "C" int kp_transport_fwd(kp_stream stream, const kp_view* phi_s, const kp
     const float two_s2 = (float)(2.0 * (double)sigma * (double)sigma);
     long long total = (long long)N * (h + 2 * pad) * (w + 2 * pad) * C;
     int grid = grid_for(total, 256);
+    const int G = transport_group(C);
+    const long long pix = (long long)N * (h + 2 * pad) * (w + 2 * pad);
+    if (G && pix < (1LL << 31) && view_vec8_ok(phi_s, C) && view_vec8_ok(phi_t, C) && view_vec8_ok(out, C) &&
+        ((uintptr_t)k_s % 8) == 0 && ((uintptr_t)k_t % 8) == 0) {
+        const int vgrid = grid_for(pix * G, 256);
+        return dispatch1(phi_s->dtype, [&](auto tp) -> int {
+            return dispatch1(out->dtype, [&](auto to) -> int {
+                using TP = decltype(tp);
+                using TO = decltype(to);
+#define KP_TF(GV)                                                                                                          \
+    transport_fwd_vec_k<TP, TO, GV><<<vgrid, 256, 0, (cudaStream_t)stream>>>(                                              \
+        make_view<TP>(phi_s), make_view<TP>(phi_t), k_s, k_t, make_view<TO>(out), pad, mask_s, mask_t, argmax_t, N, h, w, K, \
+        two_s2, eps)
+                switch (G) {
+                    case 1: KP_TF(1); break;
+                    case 2: KP_TF(2); break;
+                    case 4: KP_TF(4); break;
+                    case 8: KP_TF(8); break;
+                    case 16: KP_TF(16); break;
+                    default: KP_TF(32); break;
+                }
+#undef KP_TF
+                KP_LAUNCH_CHECK();
+                return KP_OK;
+            });
+        });
+    }
     return dispatch1(phi_s->dtype, [&](auto tp) -> int {
         return dispatch1(out->dtype, [&](auto to) -> int {
             using TP = decltype(tp);
@@ -435,6 +569,35 @@ extern "C" int kp_transport_bwd(kp_stream stream, const kp_view* dout, int pad, 
                  "kp_transport_bwd: bad arguments");
     long long P = (long long)N * h * w;
     int grid = grid_for(P * 32, 256);
+    const int G = transport_group(C);
+    if (G && P < (1LL << 31) && view_vec8_ok(dout, C) && view_vec8_ok(phi_s, C) && view_vec8_ok(phi_t, C) &&
+        view_vec8_ok(dphi_t, C)) {
+        const int vgrid = grid_for(P * G, 256);
+        return dispatch1(dout->dtype, [&](auto tg) -> int {
+            return dispatch1(phi_s->dtype, [&](auto tp) -> int {
+                return dispatch1(dphi_t->dtype, [&](auto td) -> int {
+                    using TG = decltype(tg);
+                    using TP = decltype(tp);
+                    using TD = decltype(td);
+#define KP_TB(GV)                                                                                                          \
+    transport_bwd_vec_k<TG, TP, TD, GV><<<vgrid, 256, 0, (cudaStream_t)stream>>>(                                          \
+        make_view<TG>(dout), pad, make_view<TP>(phi_s), make_view<TP>(phi_t), mask_s, mask_t, make_view<TD>(dphi_t), dmask_t, \
+        N, h, w)
+                    switch (G) {
+                        case 1: KP_TB(1); break;
+                        case 2: KP_TB(2); break;
+                        case 4: KP_TB(4); break;
+                        case 8: KP_TB(8); break;
+                        case 16: KP_TB(16); break;
+                        default: KP_TB(32); break;
+                    }
+#undef KP_TB
+                    KP_LAUNCH_CHECK();
+                    return KP_OK;
+                });
+            });
+        });
+    }
     return dispatch1(dout->dtype, [&](auto tg) -> int {
         return dispatch1(phi_s->dtype, [&](auto tp) -> int {
             return dispatch1(dphi_t->dtype, [&](auto td) -> int {

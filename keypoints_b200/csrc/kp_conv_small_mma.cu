@@ -200,6 +200,164 @@ small_mma_wgrad_k(View<bf16> x, View<bf16> dy, float* __restrict__ dw, int N, in
 }
 
 // ------------------------------------------------------------------------------------------------
+// Pipelined 3x3 wgrad: the register-gather kernel above has one 2 KB tile in flight per block and is bound by global-load
+// latency (~1 us per tile).  Here every thread issues one 16-byte cp.async per tile into an SW_STAGES-deep shared-memory
+// ring (x: 3 rows x 18 pixels, dy: 16 pixels; out-of-row pixels zero-filled), and the nine tap warps read both operands
+// with ldmatrix.trans (pixels are the contraction axis and the slow axis of both NHWC buffers).  The 16-byte chunks of a
+// pixel are XOR-swizzled with the pixel index so the eight rows of one ldmatrix phase hit distinct bank groups.
+// ------------------------------------------------------------------------------------------------
+constexpr int SW_STAGES = 4, SW_TPS = 4;        // ring depth, 16-pixel tiles per stage
+
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void ldsm4t(uint32_t (&r)[4], uint32_t addr) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void red_add_v4(float* p, float4 v) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+// 16-byte chunk position of logical chunk ch of pixel p (CH chunks per pixel)
+template <int CH>
+__device__ __forceinline__ int swz(int p, int ch) { return CH == 4 ? ch ^ ((p >> 1) & 3) : ch ^ ((p >> 2) & 1); }
+
+template <int CIN, int COUT>
+__global__ void __launch_bounds__(288, 2)
+small_mma_wgrad_pipe_k(View<bf16> x, View<bf16> dy, float* __restrict__ dw, int N, int H, int W, unsigned per_block) {
+    constexpr int MT = CIN / 16, NJ = COUT / 16, XCH = CIN / 8, DCH = COUT / 8;
+    constexpr int XROW = 18 * XCH * 16, XB = 3 * XROW, DB = 16 * DCH * 16, TB = XB + DB;   // bytes per tile
+    constexpr int SB = SW_TPS * TB;                                                      // bytes per stage
+    constexpr int NX = 3 * 18 * XCH, ND = 16 * DCH;                                      // 16-byte chunks per tile
+    static_assert(NX + ND <= 288, "one chunk per thread per tile");
+    extern __shared__ __align__(128) unsigned char sw_smem[];
+    const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(sw_smem);
+    const int lane = threadIdx.x & 31, t = threadIdx.x >> 5;
+    const int g = lane >> 2, q = lane & 3;
+    const int ty = t / 3, tx = t % 3;
+    const unsigned tpr = (unsigned)(W + 15) >> 4;
+    const unsigned ntiles = (unsigned)N * (unsigned)H * tpr;
+    // the block owns the contiguous tile range [first, first + mine): the copy cursor (n, y, x0) advances without divisions
+    const unsigned first = blockIdx.x * per_block;
+    const unsigned mine = first < ntiles ? min(per_block, ntiles - first) : 0u;
+    const unsigned nstages = (mine + SW_TPS - 1) / SW_TPS;
+
+    // this thread's chunk of every tile (tile-invariant part of the addresses)
+    const int i = threadIdx.x;
+    const bool is_x = i < NX, is_d = !is_x && i < NX + ND;
+    int cp_p, cp_lim;
+    long long cp_src;
+    uint32_t cp_dst;
+    if (is_x) {
+        const int row = i / (18 * XCH), rem = i - row * (18 * XCH), p = rem / XCH, ch = rem - p * XCH;
+        cp_p = p; cp_lim = W + 2;
+        cp_src = row * x.sy + p * x.sx + ch * 8;
+        cp_dst = row * XROW + (p * XCH + swz<XCH>(p, ch)) * 16;
+    } else {
+        const int k2 = is_d ? i - NX : 0, p = k2 / DCH, ch = k2 - p * DCH;
+        cp_p = p; cp_lim = W;
+        cp_src = p * dy.sx + ch * 8;
+        cp_dst = XB + (p * DCH + swz<DCH>(p, ch)) * 16;
+    }
+    const bf16* cp_base = is_x ? x.p : dy.p;
+    const long long s_n = is_x ? x.sn : dy.sn, s_y = is_x ? x.sy : dy.sy, s_x = is_x ? x.sx : dy.sx;
+    int cn, cy, cx0;                                   // cursor of the next tile to copy
+    {
+        const unsigned r = first / tpr;
+        cx0 = (int)(first - r * tpr) << 4;
+        cn = (int)(r / (unsigned)H); cy = (int)(r - (unsigned)cn * (unsigned)H);
+    }
+    unsigned copied = 0;
+    auto issue_stage = [&](unsigned stage) {
+        const uint32_t st = sbase + (stage % SW_STAGES) * SB;
+#pragma unroll
+        for (int j = 0; j < SW_TPS; ++j) {
+            if (copied < mine) {
+                if (is_x || is_d) {
+                    const uint32_t dst = st + j * TB + cp_dst;
+                    if (cx0 + cp_p < cp_lim) cp_async16(dst, cp_base + cn * s_n + cy * s_y + cx0 * s_x + cp_src);
+                    else *reinterpret_cast<uint4*>(sw_smem + (dst - sbase)) = make_uint4(0u, 0u, 0u, 0u);
+                }
+                ++copied;
+                cx0 += 16;
+                if (cx0 >= W) { cx0 = 0; if (++cy == H) { cy = 0; ++cn; } }
+            }
+        }
+    };
+
+    float c[MT][2 * NJ][4];
+#pragma unroll
+    for (int m = 0; m < MT; ++m)
+#pragma unroll
+        for (int j = 0; j < 2 * NJ; ++j) { c[m][j][0] = c[m][j][1] = c[m][j][2] = c[m][j][3] = 0.f; }
+    // ldmatrix row addresses of this lane: matrix mi = lane / 8, row rr = lane % 8
+    const int mi = lane >> 3, rr = lane & 7;
+    const int pa = rr + 8 * (mi >> 1) + tx, ca = mi & 1;           // A (x): pixel, chunk parity
+    const int pb = rr + 8 * (mi & 1), cb = mi >> 1;                // B (dy)
+    uint32_t offa[MT], offb[NJ];
+#pragma unroll
+    for (int m = 0; m < MT; ++m) offa[m] = ty * XROW + (pa * XCH + swz<XCH>(pa, 2 * m + ca)) * 16;
+#pragma unroll
+    for (int jj = 0; jj < NJ; ++jj) offb[jj] = XB + (pb * DCH + swz<DCH>(pb, 2 * jj + cb)) * 16;
+
+    for (unsigned k = 0; k < SW_STAGES - 1; ++k) {
+        if (k < nstages) issue_stage(k);
+        cp_async_commit();
+    }
+    for (unsigned k = 0; k < nstages; ++k) {
+        cp_async_wait<SW_STAGES - 2>();
+        __syncthreads();
+        if (k + SW_STAGES - 1 < nstages) issue_stage(k + SW_STAGES - 1);
+        cp_async_commit();
+        const uint32_t st = sbase + (k % SW_STAGES) * SB;
+        const unsigned left = mine - k * SW_TPS;
+#pragma unroll
+        for (int j = 0; j < SW_TPS; ++j) {
+            if ((unsigned)j < left) {
+                uint32_t a[MT][4];
+#pragma unroll
+                for (int m = 0; m < MT; ++m) ldsm4t(a[m], st + j * TB + offa[m]);
+#pragma unroll
+                for (int jj = 0; jj < NJ; ++jj) {
+                    uint32_t b[4];
+                    ldsm4t(b, st + j * TB + offb[jj]);
+#pragma unroll
+                    for (int m = 0; m < MT; ++m) {
+                        mma16816(c[m][2 * jj], a[m], b[0], b[1]);
+                        mma16816(c[m][2 * jj + 1], a[m], b[2], b[3]);
+                    }
+                }
+            }
+        }
+    }
+    cp_async_wait<0>();
+    __syncthreads();
+    // block partial [co][ci][9] staged in shared memory (the ring is free now), then added to dw with coalesced vector REDs
+    float* part = reinterpret_cast<float*>(sw_smem);
+#pragma unroll
+    for (int m = 0; m < MT; ++m)
+#pragma unroll
+        for (int j = 0; j < 2 * NJ; ++j)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int ci = 16 * m + g + 8 * (e >> 1);
+                const int co = 8 * j + 2 * q + (e & 1);
+                part[(co * CIN + ci) * 9 + t] = c[m][j][e];
+            }
+    __syncthreads();
+    if (mine == 0) return;
+    constexpr int TOT = CIN * COUT * 9;
+    if ((reinterpret_cast<uintptr_t>(dw) & 15) == 0) {
+        for (int v = threadIdx.x; v < TOT / 4; v += 288) red_add_v4(dw + 4 * v, *reinterpret_cast<const float4*>(part + 4 * v));
+    } else {
+        for (int v = threadIdx.x; v < TOT; v += 288) atomicAdd(dw + v, part[v]);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // Single-channel first layer (grey-scale nets: 1 -> Cout, 3x3).  9 MACs per output: a streaming kernel, one thread per
 // (pixel, 8 output channels), the 3x3 window comes from L1 (the 1-channel padded image is contiguous in x).
 // ------------------------------------------------------------------------------------------------
@@ -368,6 +526,29 @@ int kp_small_mma_wgrad(cudaStream_t st, const kp_view* x, const kp_view* dy, flo
     const long long cap = (long long)kp_sm_count() * mult;
     if (blocks > cap) blocks = cap;
     const dim3 grid((unsigned)blocks);
+    static int pipe = -1;
+    if (pipe < 0) { const char* e = getenv("KP_SMALL_WGRAD_PIPE"); pipe = e ? atoi(e) : 1; }
+    if (pipe && ks == 3 && (((uintptr_t)x->ptr) % 16) == 0 && (((uintptr_t)dy->ptr) % 16) == 0 && x->sx % 8 == 0 && x->sy % 8 == 0 &&
+        x->sn % 8 == 0 && dy->sx % 8 == 0 && dy->sy % 8 == 0 && dy->sn % 8 == 0) {
+#define KP_SWP(CI, CO)                                                                                                   \
+    do {                                                                                                                 \
+        constexpr int smem = SW_STAGES * SW_TPS * (3 * 18 * CI * 2 + 16 * CO * 2);                                       \
+        static bool attr = false;                                                                                        \
+        if (!attr) {                                                                                                     \
+            cudaFuncSetAttribute(small_mma_wgrad_pipe_k<CI, CO>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);     \
+            attr = true;                                                                                                 \
+        }                                                                                                                \
+        small_mma_wgrad_pipe_k<CI, CO><<<grid, 288, smem, st>>>(make_view<bf16>(x), make_view<bf16>(dy), dw, N, H, W,    \
+                                                                (unsigned)((tiles + blocks - 1) / blocks));              \
+    } while (0)
+        if (Cin == 16 && Cout == 16) KP_SWP(16, 16);
+        else if (Cin == 16 && Cout == 32) KP_SWP(16, 32);
+        else if (Cin == 32 && Cout == 16) KP_SWP(32, 16);
+        else KP_SWP(32, 32);
+#undef KP_SWP
+        KP_LAUNCH_CHECK();
+        return KP_OK;
+    }
 #define KP_SW(CI, CO)                                                                                                    \
     do {                                                                                                                 \
         if (ks == 1) small_mma_wgrad_k<CI, CO, 1><<<grid, 288, 0, st>>>(make_view<bf16>(x), make_view<bf16>(dy), dw, N, H, W); \
