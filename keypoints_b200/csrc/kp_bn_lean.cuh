@@ -96,6 +96,46 @@ bn_fwd_lean_k(Rows<const T> y, Rows<T> out, const float* __restrict__ scale, con
     const int PH = OH + 2 * pad, PW = OW + 2 * pad, rows = N * PH;
     constexpr int NL = POST == KP_POST_POOL ? 4 : 1;
     constexpr int U = POST == KP_POST_POOL ? 2 : 4;
+    if (POST == KP_POST_NONE) {
+        // slot j of a pass -> (row offset jr, pixel offset jx).  Rows shorter than the block's pixel span put several
+        // rows in flight per pass (S slots per row, RB = U / S rows) instead of leaving the upper slots idle.
+        const int S = (PW + xstep - 1) / xstep, RB = (sizeof(T) == 2 && S <= U) ? U / S : 1;   // fp32 (parity) mode keeps one row per pass
+        int jr[U], jx[U];
+#pragma unroll
+        for (int j = 0; j < U; ++j) { jr[j] = RB > 1 ? j / S : 0; jx[j] = (RB > 1 ? j - jr[j] * S : j) * xstep; }
+        for (int row0 = blockIdx.x * RB; row0 < rows; row0 += gridDim.x * RB) {
+            for (int pxb = x0; pxb < PW; pxb += U * xstep) {
+                Raw r[U];
+                T* op[U];
+                bool ok[U];
+#pragma unroll
+                for (int j = 0; j < U; ++j) {
+                    const int row = row0 + jr[j], px = pxb + jx[j];
+                    ok[j] = jr[j] < RB && row < rows && px < PW;
+                    if (ok[j]) {
+                        const int n = row / PH, py = row - n * PH;
+                        const int oy = min(max(py - pad, 0), OH - 1), ox = min(max(px - pad, 0), OW - 1);
+                        r[j] = P8<T>::ld(y.row(n, oy) + c0 + ox * y.sx);
+                        op[j] = out.row(n, py) + c0 + px * out.sx;
+                    }
+                }
+#pragma unroll
+                for (int j = 0; j < U; ++j) {
+                    if (ok[j]) {
+                        float2 v[4];
+                        P8<T>::up(r[j], v);
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            const float2 z = fma2(v[i], sc[i], sh[i]);
+                            v[i] = make_float2(actv<ACT>(z.x), actv<ACT>(z.y));
+                        }
+                        P8<T>::st(op[j], v);
+                    }
+                }
+            }
+        }
+        return;
+    }
     for (int row = blockIdx.x; row < rows; row += gridDim.x) {
         const int n = row / PH, py = row - n * PH;
         const int oy = min(max(py - pad, 0), OH - 1);
@@ -203,8 +243,9 @@ bn_bwd_lean_k(Rows<const T> dout, Rows<const T> y, Rows<T> dy, const float* __re
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
             const int c = c0 + 2 * i;
-            const float m1x = (float)(sums[c] / count), m1y = (float)(sums[c + 1] / count);
-            const float m2x = (float)(sums[C + c] / count), m2y = (float)(sums[C + c + 1] / count);
+            const double rc = 1.0 / count;
+            const float m1x = (float)(sums[c] * rc), m1y = (float)(sums[c + 1] * rc);
+            const float m2x = (float)(sums[C + c] * rc), m2y = (float)(sums[C + c + 1] * rc);
             s1[i] = make_float2(-sc[i].x * m1x, -sc[i].y * m1y);
             s2[i] = make_float2(-sc[i].x * invstd[c] * m2x, -sc[i].y * invstd[c + 1] * m2y);
         }
@@ -232,28 +273,35 @@ bn_bwd_lean_k(Rows<const T> dout, Rows<const T> y, Rows<T> dy, const float* __re
     if (POST == KP_POST_NONE) {
         constexpr int U = 4;
         const int rows = N * H;
-        for (int row = blockIdx.x; row < rows; row += gridDim.x) {
-            const int n = row / H, yy = row - n * H;
-            const T* drow = dout.row(n, yy + pad) + pad * dout.sx + c0;
-            const T* yrow = y.row(n, yy) + c0;
-            T* orow = dy.p ? dy.row(n, yy) + c0 : nullptr;
-            const bool rowb = pad && (yy == 0 || yy == H - 1);
+        // slot mapping as in the forward kernel: short rows put RB rows in flight per pass
+        const int S = (W + xstep - 1) / xstep, RB = (sizeof(T) == 2 && S <= U) ? U / S : 1;   // fp32 (parity) mode keeps one row per pass
+        int jr[U], jx[U];
+#pragma unroll
+        for (int j = 0; j < U; ++j) { jr[j] = RB > 1 ? j / S : 0; jx[j] = (RB > 1 ? j - jr[j] * S : j) * xstep; }
+        for (int row0 = blockIdx.x * RB; row0 < rows; row0 += gridDim.x * RB) {
             for (int xb = x0; xb < W; xb += U * xstep) {
                 Raw rg[U], ry[U];
+                int sn[U], sy[U];
+                bool ok[U];
 #pragma unroll
                 for (int j = 0; j < U; ++j) {
-                    const int xx = xb + j * xstep;
-                    if (xx < W) { rg[j] = P8<T>::ld(drow + xx * dout.sx); ry[j] = P8<T>::ld(yrow + xx * y.sx); }
+                    const int row = row0 + jr[j], xx = xb + jx[j];
+                    ok[j] = jr[j] < RB && row < rows && xx < W;
+                    if (ok[j]) {
+                        sn[j] = row / H; sy[j] = row - sn[j] * H;
+                        rg[j] = P8<T>::ld(dout.row(sn[j], sy[j] + pad) + (xx + pad) * dout.sx + c0);
+                        ry[j] = P8<T>::ld(y.row(sn[j], sy[j]) + xx * y.sx + c0);
+                    }
                 }
 #pragma unroll
                 for (int j = 0; j < U; ++j) {
-                    const int xx = xb + j * xstep;
-                    if (xx < W) {
+                    if (ok[j]) {
+                        const int xx = xb + jx[j], yy = sy[j];
                         float2 g[4], yv[4];
                         P8<T>::up(rg[j], g);
                         P8<T>::up(ry[j], yv);
-                        if (pad && (rowb || xx == 0 || xx == W - 1)) add_fold<T>(dout, n, yy, xx, OH, OW, c0, g);
-                        emit(orow ? orow + xx * dy.sx : nullptr, g, yv);
+                        if (pad && (yy == 0 || yy == H - 1 || xx == 0 || xx == W - 1)) add_fold<T>(dout, sn[j], yy, xx, OH, OW, c0, g);
+                        emit(dy.p ? dy.row(sn[j], yy) + xx * dy.sx + c0 : nullptr, g, yv);
                     }
                 }
             }

@@ -196,8 +196,9 @@ __device__ __forceinline__ void bwd_consts(int MODE, const float* scale, const f
         nmu[i] = make_float2(-nmu[i].x, -nmu[i].y);
         if (MODE == PASS2_GATHER) {
             const int c = c0 + 2 * i;
-            const float m1x = (float)(sums[c] / count), m1y = (float)(sums[c + 1] / count);
-            const float m2x = (float)(sums[C + c] / count), m2y = (float)(sums[C + c + 1] / count);
+            const double rc = 1.0 / count;
+            const float m1x = (float)(sums[c] * rc), m1y = (float)(sums[c + 1] * rc);
+            const float m2x = (float)(sums[C + c] * rc), m2y = (float)(sums[C + c + 1] * rc);
             s1[i] = make_float2(-sc[i].x * m1x, -sc[i].y * m1y);
             s2[i] = make_float2(-sc[i].x * invstd[c] * m2x, -sc[i].y * invstd[c + 1] * m2y);
         } else {
@@ -326,7 +327,8 @@ bn_bwd_apply_pipe_k(Rows<const bf16> y, Rows<bf16> dy, const float* __restrict__
         for (int i = 0; i < 8; ++i) {
             const int c = c0 + i;
             const float sc = scale[c], mu = mean[c], is = invstd[c];
-            const float m1 = (float)(sums[c] / count), m2 = (float)(sums[C + c] / count);
+            const double rc = 1.0 / count;
+            const float m1 = (float)(sums[c] * rc), m2 = (float)(sums[C + c] * rc);
             const float v0 = sc, v1 = -sc * is * m2, v2 = -sc * m1 + sc * is * m2 * mu;
             if (i & 1) { a0[i >> 1].y = v0; a1[i >> 1].y = v1; a2[i >> 1].y = v2; }
             else { a0[i >> 1].x = v0; a1[i >> 1].x = v1; a2[i >> 1].x = v2; }

@@ -358,6 +358,159 @@ small_mma_wgrad_pipe_k(View<bf16> x, View<bf16> dy, float* __restrict__ dw, int 
 }
 
 // ------------------------------------------------------------------------------------------------
+// Pipelined 3x3 fprop / dgrad: small_mma_conv_k gathers the A fragments with 4-byte global loads and is bound by L1
+// throughput (ncu: l1tex 94 %, 9 taps x 16 pixels re-read per tile).  Here every warp owns a contiguous range of tiles and a
+// private SC_DEPTH-deep cp.async ring: the 3 x 18-pixel input window of a tile is copied once in 16-byte chunks (zero
+// outside the image: the bounds check of the dgrad halo comes for free), A fragments come from ldmatrix, weights from the
+// B-fragment table in shared memory as before.  No block barrier in the main loop.
+// ------------------------------------------------------------------------------------------------
+constexpr int SC_DEPTH = 3;
+
+__device__ __forceinline__ void ldsm4(uint32_t (&r)[4], uint32_t addr) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+
+struct TileCursor {
+    int n, y, x0;
+    __device__ __forceinline__ void seek(unsigned tile, unsigned tpr, int OH) {
+        const unsigned r = tile / tpr;
+        x0 = (int)(tile - r * tpr) << 4;
+        n = (int)(r / (unsigned)OH); y = (int)(r - (unsigned)n * (unsigned)OH);
+    }
+    __device__ __forceinline__ void next(int OH, int OW) {
+        x0 += 16;
+        if (x0 >= OW) { x0 = 0; if (++y == OH) { y = 0; ++n; } }
+    }
+};
+
+template <int CIN, int COUT>
+__global__ void __launch_bounds__(SM_WARPS * 32, 2)
+small_mma_conv_pipe_k(View<bf16> in, const float* __restrict__ wk, const float* __restrict__ bias, View<bf16> out, double* stats,
+                      int N, int OH, int OW, int IH, int IW, int off, unsigned per_warp) {
+    constexpr int KH = CIN / 16, KS = 9 * KH, NT = COUT / 8, XCH = CIN / 8;
+    constexpr int XROW = 18 * XCH * 16, TB = 3 * XROW, NXC = 3 * 18 * XCH;
+    __shared__ uint2 wf[KS][NT][32];
+    __shared__ float red[SM_WARPS][2][COUT];
+    __shared__ float sbias[COUT];
+    extern __shared__ __align__(128) unsigned char sc_smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int g = lane >> 2, q = lane & 3;
+    for (int i = threadIdx.x; i < KS * NT * 32; i += blockDim.x) {
+        const int ln = i & 31, nt = (i >> 5) % NT, ks = (i >> 5) / NT;
+        const int co = nt * 8 + (ln >> 2), k0 = ks * 16 + 2 * (ln & 3);
+        uint2 v;
+        v.x = pk2(wk[(k0)*COUT + co], wk[(k0 + 1) * COUT + co]);
+        v.y = pk2(wk[(k0 + 8) * COUT + co], wk[(k0 + 9) * COUT + co]);
+        wf[ks][nt][ln] = v;
+    }
+    if (threadIdx.x < COUT) sbias[threadIdx.x] = bias ? bias[threadIdx.x] : 0.f;
+    __syncthreads();
+    float s1[NT][2], s2[NT][2];
+#pragma unroll
+    for (int j = 0; j < NT; ++j) { s1[j][0] = s1[j][1] = s2[j][0] = s2[j][1] = 0.f; }
+    const unsigned tpr = (unsigned)(OW + 15) >> 4;
+    const unsigned ntiles = (unsigned)N * (unsigned)OH * tpr;
+    const unsigned first = (blockIdx.x * SM_WARPS + warp) * per_warp;
+    const unsigned mine = first < ntiles ? min(per_warp, ntiles - first) : 0u;
+    unsigned char* ring = sc_smem + warp * (SC_DEPTH * TB);
+    const uint32_t ring_s = (uint32_t)__cvta_generic_to_shared(ring);
+    TileCursor cc, cu;
+    cc.seek(first, tpr, OH);
+    cu = cc;
+
+    auto copy_tile = [&](int slot) {
+        const uint32_t st = ring_s + slot * TB;
+        for (int i = lane; i < NXC; i += 32) {
+            const int row = i / (18 * XCH), rem = i - row * (18 * XCH), p = rem / XCH, ch = rem - p * XCH;
+            const int iy = cc.y + row + off, ix = cc.x0 + p + off;
+            const uint32_t dst = st + row * XROW + (p * XCH + swz<XCH>(p, ch)) * 16;
+            if (iy >= 0 && iy < IH && ix >= 0 && ix < IW) cp_async16(dst, in.at(cc.n, iy, ix, ch * 8));
+            else *reinterpret_cast<uint4*>(ring + (dst - ring_s)) = make_uint4(0u, 0u, 0u, 0u);
+        }
+        cc.next(OH, OW);
+    };
+    // ldmatrix lane addressing: matrix mi = lane / 8 (a0..a3), row rr = lane % 8
+    const int mi = lane >> 3, rr = lane & 7;
+    uint32_t offa[3][KH];
+#pragma unroll
+    for (int tx = 0; tx < 3; ++tx)
+#pragma unroll
+        for (int h = 0; h < KH; ++h) {
+            const int p = rr + 8 * (mi & 1) + tx;
+            offa[tx][h] = (p * XCH + swz<XCH>(p, 2 * h + (mi >> 1))) * 16;
+        }
+
+    for (unsigned k = 0; k < SC_DEPTH - 1; ++k) {
+        if (k < mine) copy_tile(k);
+        cp_async_commit();
+    }
+    for (unsigned k = 0; k < mine; ++k) {
+        cp_async_wait<SC_DEPTH - 2>();
+        __syncwarp();
+        if (k + SC_DEPTH - 1 < mine) copy_tile((k + SC_DEPTH - 1) % SC_DEPTH);
+        cp_async_commit();
+        const uint32_t st = ring_s + (k % SC_DEPTH) * TB;
+        float c[NT][4];
+#pragma unroll
+        for (int j = 0; j < NT; ++j) {
+            const float b0 = sbias[8 * j + 2 * q], b1 = sbias[8 * j + 2 * q + 1];
+            c[j][0] = b0; c[j][1] = b1; c[j][2] = b0; c[j][3] = b1;
+        }
+#pragma unroll
+        for (int t = 0; t < 9; ++t) {
+#pragma unroll
+            for (int h = 0; h < KH; ++h) {
+                uint32_t a[4];
+                ldsm4(a, st + (t / 3) * XROW + offa[t % 3][h]);
+#pragma unroll
+                for (int j = 0; j < NT; ++j) {
+                    const uint2 w = wf[t * KH + h][j][lane];
+                    mma16816(c[j], a, w.x, w.y);
+                }
+            }
+        }
+        const int xa = cu.x0 + g, xb = xa + 8;
+        const bool va = xa < OW, vb = xb < OW;
+        bf16* oa_p = out.at(cu.n, cu.y, xa, 2 * q);
+        bf16* ob_p = oa_p + 8 * out.sx;
+#pragma unroll
+        for (int j = 0; j < NT; ++j) {
+            if (va) {
+                *reinterpret_cast<uint32_t*>(oa_p + 8 * j) = pk2(c[j][0], c[j][1]);
+                s1[j][0] += c[j][0]; s1[j][1] += c[j][1];
+                s2[j][0] = fmaf(c[j][0], c[j][0], s2[j][0]); s2[j][1] = fmaf(c[j][1], c[j][1], s2[j][1]);
+            }
+            if (vb) {
+                *reinterpret_cast<uint32_t*>(ob_p + 8 * j) = pk2(c[j][2], c[j][3]);
+                s1[j][0] += c[j][2]; s1[j][1] += c[j][3];
+                s2[j][0] = fmaf(c[j][2], c[j][2], s2[j][0]); s2[j][1] = fmaf(c[j][3], c[j][3], s2[j][1]);
+            }
+        }
+        cu.next(OH, OW);
+    }
+    cp_async_wait<0>();
+    if (stats) {
+#pragma unroll
+        for (int j = 0; j < NT; ++j)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                float a = s1[j][e], b = s2[j][e];
+#pragma unroll
+                for (int o = 4; o < 32; o <<= 1) { a += __shfl_xor_sync(0xffffffffu, a, o); b += __shfl_xor_sync(0xffffffffu, b, o); }
+                if (g == 0) { red[warp][0][8 * j + 2 * q + e] = a; red[warp][1][8 * j + 2 * q + e] = b; }
+            }
+        __syncthreads();
+        if (threadIdx.x < 2 * COUT) {
+            const int w = threadIdx.x / COUT, ch = threadIdx.x % COUT;
+            float a = 0.f;
+            for (int k = 0; k < SM_WARPS; ++k) a += red[k][w][ch];
+            atomicAdd(&stats[w * COUT + ch], (double)a);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // Single-channel first layer (grey-scale nets: 1 -> Cout, 3x3).  9 MACs per output: a streaming kernel, one thread per
 // (pixel, 8 output channels), the 3x3 window comes from L1 (the 1-channel padded image is contiguous in x).
 // ------------------------------------------------------------------------------------------------
@@ -490,6 +643,33 @@ int kp_small_mma_conv(cudaStream_t st, const kp_view* in, const float* wk, const
     const long long cap = (long long)kp_sm_count() * 4;
     if (blocks > cap) blocks = cap;
     const bool check = ks == 3 && !(off >= 0 && OH + off + 2 <= IH && OW + off + 2 <= IW);
+    static int pipe = -1;
+    if (pipe < 0) { const char* e = getenv("KP_SMALL_CONV_PIPE"); pipe = e ? atoi(e) : 1; }
+    if (pipe && ks == 3 && (((uintptr_t)in->ptr) % 16) == 0 && in->sx % 8 == 0 && in->sy % 8 == 0 && in->sn % 8 == 0) {
+        long long pb = (tiles + SM_WARPS - 1) / SM_WARPS;
+        const long long pcap = (long long)kp_sm_count() * 2;
+        if (pb > pcap) pb = pcap;
+        const unsigned per_warp = (unsigned)((tiles + pb * SM_WARPS - 1) / (pb * SM_WARPS));
+#define KP_SMP(CI, CO)                                                                                                    \
+    do {                                                                                                                  \
+        constexpr int smem = SM_WARPS * SC_DEPTH * 3 * 18 * CI * 2;                                                       \
+        static bool attr = false;                                                                                         \
+        if (!attr) {                                                                                                      \
+            cudaFuncSetAttribute(small_mma_conv_pipe_k<CI, CO>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);       \
+            attr = true;                                                                                                  \
+        }                                                                                                                 \
+        small_mma_conv_pipe_k<CI, CO><<<(unsigned)pb, SM_WARPS * 32, smem, st>>>(make_view<bf16>(in), wk, bias,           \
+                                                                                make_view<bf16>(out), stats, N, OH, OW, IH, IW, \
+                                                                                off, per_warp);                          \
+    } while (0)
+        if (Cin == 16 && Cout == 16) KP_SMP(16, 16);
+        else if (Cin == 16 && Cout == 32) KP_SMP(16, 32);
+        else if (Cin == 32 && Cout == 16) KP_SMP(32, 16);
+        else KP_SMP(32, 32);
+#undef KP_SMP
+        KP_LAUNCH_CHECK();
+        return KP_OK;
+    }
     const dim3 grid((unsigned)blocks);
 #define KP_SM(CI, CO)                                                                                                       \
     do {                                                                                                                    \

@@ -333,13 +333,16 @@ struct BnFuse {
 };
 
 __device__ __forceinline__ void fused_affine(const BnFuse& f, int C, int c0, bool publish, float (&sc)[8], float (&sh)[8]) {
+    // every thread of every block runs this: one double division, the rest double FMAs and fp32 (a double division or
+    // square root per channel per thread costs ~15 us per launch on the fp64 pipe)
+    const double rcount = 1.0 / f.count;
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
         const int c = c0 + i;
-        const double mean = f.stats[c] / f.count;
-        double var = f.stats[C + c] / f.count - mean * mean;
+        const double mean = f.stats[c] * rcount;
+        double var = f.stats[C + c] * rcount - mean * mean;
         if (var < 0) var = 0;
-        const float invstd = (float)(1.0 / sqrt(var + (double)f.eps));
+        const float invstd = 1.0f / sqrtf((float)var + f.eps);
         const float g = f.gamma ? f.gamma[c] : 1.f, b = f.beta ? f.beta[c] : 0.f;
         sc[i] = g * invstd;
         sh[i] = b - (float)mean * sc[i];
@@ -495,7 +498,7 @@ bn_act_bwd_rows_k(View<TG> dout, View<TY> y, View<TD> dy, const float* __restric
     for (int i = 0; i < V8; ++i) {
         sc[i] = scale ? scale[c0 + i] : 1.f; sh[i] = shift ? shift[c0 + i] : 0.f;
         mu[i] = mean ? mean[c0 + i] : 0.f; is[i] = invstd ? invstd[c0 + i] : 1.f;
-        if (APPLY) { s1[i] = (float)(sums[c0 + i] / count); s2[i] = (float)(sums[C + c0 + i] / count); }
+        if (APPLY) { const double rc = 1.0 / count; s1[i] = (float)(sums[c0 + i] * rc); s2[i] = (float)(sums[C + c0 + i] * rc); }
         else { s1[i] = 0.f; s2[i] = 0.f; }
     }
     const float ry = (OH > 1) ? (float)(H - 1) / (float)(OH - 1) : 0.f;
@@ -681,7 +684,8 @@ bn_bwd_apply_rows_k(View<TY> y, View<TD> dy, const float* __restrict__ scale, co
 #pragma unroll
     for (int i = 0; i < V8; ++i) {
         const float sc = scale[c0 + i], mu = mean[c0 + i], is = invstd[c0 + i];
-        const float m1 = (float)(sums[c0 + i] / count), m2 = (float)(sums[C + c0 + i] / count);
+        const double rc = 1.0 / count;
+        const float m1 = (float)(sums[c0 + i] * rc), m2 = (float)(sums[C + c0 + i] * rc);
         a0[i] = sc;
         a1[i] = -sc * is * m2;
         a2[i] = -sc * m1 + sc * is * m2 * mu;

@@ -195,7 +195,14 @@ def test_module_api_vs_reference_golden(dev, golden, name, kind, model_type):
         sd = net.state_dict()
         for key in g:
             if key.startswith('adam/') and bn_sibling('grad/' + key[5:], g) is None:
-                e = np.abs(sd[key[5:]].cpu().numpy().astype(np.float64) - g[key]).max()
+                d = np.abs(sd[key[5:]].cpu().numpy().astype(np.float64) - g[key])
+                # Adam's first step is lr * g / (|g| + 1e-8): where the reference gradient itself is below 1e-6 the step
+                # amplifies fp32 summation noise (a 4e-9 difference in g moves it by 9 % of lr), so those elements are
+                # judged by the gradient comparison above, not by the step
+                gk = 'grad/' + key[5:]
+                if gk in g:
+                    d = d[np.abs(g[gk]) >= 1e-6]
+                e = d.max() if d.size else 0.0
                 R.rows.append((key, e, 0.05 * 1e-4))          # within 5 % of one lr-sized step
     R.finish()
 
