@@ -54,7 +54,9 @@ def test_sass_is_blackwell_native(built):
             assert 'thin_mma' in k or 'small_mma' in k, f'legacy mma.sync code in {k}'
     conv = [k for k in body if 'conv_tc_pair' in k or 'wgrad_tc_pair_k' in k]
     assert conv and all('UTCHMMA' in body[k] and 'UTMALDG' in body[k] for k in conv)
-    pipe = [k for k in body if '_pipe_k' in k]
+    pipe = [k for k in body if '_pipe_k' in k and 'small_mma' not in k]
+    small = [k for k in body if '_pipe_k' in k and 'small_mma' in k]       # 16/32-channel layers: cp.async ring + ldmatrix
+    assert len(small) >= 8 and all('LDGSTS' in body[k] and 'LDSM' in body[k] and 'HMMA' in body[k] for k in small)
     assert len(pipe) >= 10 and all('UBLKCP' in body[k] and 'SYNCS' in body[k] for k in pipe)
     assert any('FFMA2' in body[k] for k in pipe), 'packed fp32x2 math expected in the streaming kernels'
 
