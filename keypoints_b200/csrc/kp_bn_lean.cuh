@@ -76,7 +76,7 @@ __device__ __forceinline__ void load_c8(const float* p, int c0, float dflt, floa
 // forward: out = post(act(scale * y + shift)) written into the (optionally replicate-padded) next input
 // ------------------------------------------------------------------------------------------------
 template <typename T, int POST, int ACT>
-__global__ void __launch_bounds__(256, 2)
+__global__ void __launch_bounds__(256, (POST == KP_POST_NONE && sizeof(T) == 2) ? 3 : 2)
 bn_fwd_lean_k(Rows<const T> y, Rows<T> out, const float* __restrict__ scale, const float* __restrict__ shift, int pad, int N,
               int H, int W, int C, int OH, int OW, int cg_shift, const BnFuse fuse) {
     typedef typename P8<T>::Raw Raw;
