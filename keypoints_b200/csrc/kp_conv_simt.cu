@@ -482,29 +482,44 @@ pack_weights_multi_k(const PackDesc* __restrict__ table) {
     const int row = 32 * T;
     for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
         const int co0 = (tile / tiles_ci) * 32, ci0 = (tile % tiles_ci) * 32;
-#pragma unroll 4
+#pragma unroll 12
         for (int idx = threadIdx.x; idx < 32 * row; idx += 256) {
             const int r = idx / row, j = idx - r * row;
             const int co = co0 + r, ci = ci0 + j / T;
             sm[r][j] = (co < Cout && ci < Cin) ? d.w[((long long)co * Cin + ci0) * T + j] : 0.f;
         }
         __syncthreads();
-        for (int idx = threadIdx.x; idx < 1024 * T; idx += 256) {       // ci fastest: [t][co][ci] layouts
-            const int c = idx & 31, r = (idx >> 5) & 31, t = idx >> 10;
-            const int co = co0 + r, ci = ci0 + c, tf = T - 1 - t;
-            const float v = sm[r][c * T + t];
-            if (co < Cout && ci < ci_pad) {
-                if (d.tc_f) d.tc_f[((long long)t * Cout + co) * ci_pad + ci] = __float2bfloat16_rn(v);
-                if (d.simt_d && ci < Cin) d.simt_d[((long long)tf * Cout + co) * Cin + ci] = v;
+        // bf16 layouts are written two elements (4 bytes) per thread; ci_pad and Cout of a tensor-core layer are multiples of 64
+        if (d.tc_f) {
+            for (int idx = threadIdx.x; idx < 512 * T; idx += 256) {    // ci fastest: [t][co][ci]
+                const int c = (idx & 15) * 2, r = (idx >> 4) & 31, t = idx >> 9;
+                const int co = co0 + r, ci = ci0 + c;
+                if (co < Cout && ci < ci_pad)
+                    *reinterpret_cast<__nv_bfloat162*>(d.tc_f + ((long long)t * Cout + co) * ci_pad + ci) =
+                        __floats2bfloat162_rn(sm[r][c * T + t], sm[r][(c + 1) * T + t]);
             }
         }
-        for (int idx = threadIdx.x; idx < 1024 * T; idx += 256) {       // co fastest: [t][ci][co] layouts
-            const int r = idx & 31, c = (idx >> 5) & 31, t = idx >> 10;
-            const int co = co0 + r, ci = ci0 + c, tf = T - 1 - t;
-            const float v = sm[r][c * T + t];
-            if (co < Cout && ci < ci_pad) {
-                if (d.tc_d) d.tc_d[((long long)tf * ci_pad + ci) * Cout + co] = __float2bfloat16_rn(v);
-                if (d.simt_f && ci < Cin) d.simt_f[((long long)t * Cin + ci) * Cout + co] = v;
+        if (d.tc_d) {
+            for (int idx = threadIdx.x; idx < 512 * T; idx += 256) {    // co fastest: [t][ci][co], taps flipped
+                const int r = (idx & 15) * 2, c = (idx >> 4) & 31, t = idx >> 9;
+                const int co = co0 + r, ci = ci0 + c, tf = T - 1 - t;
+                if (co < Cout && ci < ci_pad)
+                    *reinterpret_cast<__nv_bfloat162*>(d.tc_d + ((long long)tf * ci_pad + ci) * Cout + co) =
+                        __floats2bfloat162_rn(sm[r][c * T + t], sm[r + 1][c * T + t]);
+            }
+        }
+        if (d.simt_d) {
+            for (int idx = threadIdx.x; idx < 1024 * T; idx += 256) {
+                const int c = idx & 31, r = (idx >> 5) & 31, t = idx >> 10;
+                const int co = co0 + r, ci = ci0 + c, tf = T - 1 - t;
+                if (co < Cout && ci < Cin) d.simt_d[((long long)tf * Cout + co) * Cin + ci] = sm[r][c * T + t];
+            }
+        }
+        if (d.simt_f) {
+            for (int idx = threadIdx.x; idx < 1024 * T; idx += 256) {
+                const int r = idx & 31, c = (idx >> 5) & 31, t = idx >> 10;
+                const int co = co0 + r, ci = ci0 + c;
+                if (co < Cout && ci < Cin) d.simt_f[((long long)t * Cin + ci) * Cout + co] = sm[r][c * T + t];
             }
         }
         __syncthreads();
