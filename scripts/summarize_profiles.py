@@ -128,7 +128,8 @@ def bottleneck():
            '--warmup 3 --no-graph`; rows are the launches of the LAST step (between the last two `adam_k`), averaged per kernel.  '
            f'GB/s = (DRAM read + written bytes) / kernel time; peak = measured copy bandwidth {peak:.0f} GB/s (MEASURED_PEAKS.json).  '
            'Kernels whose working set fits the 126 MB L2 move few DRAM bytes by design (their inputs were just written by the '
-           'producer): for those the time column, not GB/s, is the figure of merit.\n']
+           'producer; at 84x84 batch 64 a whole activation is 15-30 MB): for those the L2 GB/s column (lts__t_bytes / time) and the '
+           'time itself are the figures of merit.\n']
     scale = {'byte': 1, 'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9, 'ns': 1e-3, 'us': 1.0, 'ms': 1e3, 'usecond': 1.0, 'nsecond': 1e-3}
     for wl, title in (('pong', 'Transporter Pong-grey 84x84 K=4, batch 64, bf16 (bottleneck kernels at full 84x84 resolution)'),
                       ('keynet', 'KeyNet F 128x128 K=10, batch 64, bf16 (TPS + rotate warps at 128x128; bottleneck at 16x16)')):
@@ -150,19 +151,20 @@ def bottleneck():
         ls = ls[idx[-2] + 1: idx[-1] + 1] if len(idx) >= 2 else ls
         agg = collections.OrderedDict()
         for l in ls:
-            a = agg.setdefault(l['kernel'][:64], [0, 0.0, 0.0, 0.0, 0.0, 0])
+            a = agg.setdefault(l['kernel'][:64], [0, 0.0, 0.0, 0.0, 0.0, 0, 0.0])
             a[0] += 1
             a[1] += l.get('gpu__time_duration.sum', 0)
             a[2] += l.get('dram__bytes_read.sum', 0)
             a[3] += l.get('dram__bytes_write.sum', 0)
             a[4] += l.get('gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed', 0)
             a[5] = int(l.get('launch__grid_size', 0))
-        out.append(f'\n## {title}\n\n| kernel | launches | us / launch | DRAM read MB | written MB | GB/s | frac of {peak:.0f} | ncu dram % | grid |\n'
-                   '|---|---:|---:|---:|---:|---:|---:|---:|---:|\n')
+            a[6] += l.get('lts__t_bytes.sum', 0)
+        out.append(f'\n## {title}\n\n| kernel | launches | us / launch | DRAM read MB | written MB | DRAM GB/s | frac of {peak:.0f} | L2 GB/s | ncu dram % | grid |\n'
+                   '|---|---:|---:|---:|---:|---:|---:|---:|---:|---:|\n')
         for k, a in sorted(agg.items(), key=lambda kv: -kv[1][1]):
             n = a[0]
             gbs = (a[2] + a[3]) / max(a[1], 1e-9) / 1e3
-            out.append(f'| `{k}` | {n} | {a[1] / n:.1f} | {a[2] / n / 1e6:.2f} | {a[3] / n / 1e6:.2f} | {gbs:.0f} | {gbs / peak:.2f} | '
+            out.append(f'| `{k}` | {n} | {a[1] / n:.1f} | {a[2] / n / 1e6:.2f} | {a[3] / n / 1e6:.2f} | {gbs:.0f} | {gbs / peak:.2f} | {a[6] / max(a[1], 1e-9) / 1e3:.0f} | '
                        f'{a[4] / n:.0f} | {a[5]} |\n')
     if len(out) > 2:
         with open(os.path.join(OUT, f'{TAG}_bottleneck_kernels.md'), 'w') as fh:
