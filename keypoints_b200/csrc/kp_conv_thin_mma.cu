@@ -76,39 +76,24 @@ thin_mma_fprop_k(View<bf16> in, const float* __restrict__ wk /*[KK][Cout]*/, con
 
     const int tiles_per_row = OW >> 4;
     const long long ntiles = (long long)N * OH * tiles_per_row;
-    // A fragments of one tile (16 two-byte gathers per lane); the next tile's are issued before this tile's MMAs and
-    // stores so that the load latency overlaps them
-    auto load_tile = [&](long long tile, uint32_t (&ra)[8], uint32_t (&rb)[8]) {
+    for (long long tile = (long long)blockIdx.x * THIN_WARPS + warp; tile < ntiles; tile += (long long)gridDim.x * THIN_WARPS) {
         const unsigned tu = (unsigned)tile, r = tu / (unsigned)tiles_per_row;      // 32-bit divisions (tiles < 2^31)
         const int xt = (int)(tu - r * (unsigned)tiles_per_row);
         const int n = (int)(r / (unsigned)OH), y = (int)(r - (unsigned)n * (unsigned)OH);
-        const bf16* pa = in.at(n, y, (xt << 4) + g, 0);
-        const bf16* pb = pa + 8 * in.sx;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {                        // i = 4 s + 2 h + e
-            const int o = off[i >> 2][(i >> 1) & 1][i & 1];
-            ra[i] = 0; rb[i] = 0;
-            if (o >= 0) { ra[i] = ldg_u16(pa + o); rb[i] = ldg_u16(pb + o); }
-        }
-    };
-    const long long tstep = (long long)gridDim.x * THIN_WARPS;
-    long long tile = (long long)blockIdx.x * THIN_WARPS + warp;
-    uint32_t ra[8], rb[8];
-    if (tile < ntiles) load_tile(tile, ra, rb);
-    for (; tile < ntiles; tile += tstep) {
-        const unsigned tu = (unsigned)tile, r = tu / (unsigned)tiles_per_row;
-        const int xt = (int)(tu - r * (unsigned)tiles_per_row);
-        const int n = (int)(r / (unsigned)OH), y = (int)(r - (unsigned)n * (unsigned)OH);
         const int x0 = xt << 4;
+        const bf16* pa = in.at(n, y, x0 + g, 0);
+        const bf16* pb = pa + 8 * in.sx;
         uint32_t a[2][4];
 #pragma unroll
         for (int s = 0; s < 2; ++s)
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
-                a[s][2 * h] = ra[4 * s + 2 * h] | (ra[4 * s + 2 * h + 1] << 16);          // row g
-                a[s][2 * h + 1] = rb[4 * s + 2 * h] | (rb[4 * s + 2 * h + 1] << 16);      // row g + 8
+                uint32_t lo_a = 0, hi_a = 0, lo_b = 0, hi_b = 0;
+                if (off[s][h][0] >= 0) { lo_a = ldg_u16(pa + off[s][h][0]); lo_b = ldg_u16(pb + off[s][h][0]); }
+                if (off[s][h][1] >= 0) { hi_a = ldg_u16(pa + off[s][h][1]); hi_b = ldg_u16(pb + off[s][h][1]); }
+                a[s][2 * h] = lo_a | (hi_a << 16);          // row g
+                a[s][2 * h + 1] = lo_b | (hi_b << 16);      // row g + 8
             }
-        if (tile + tstep < ntiles) load_tile(tile + tstep, ra, rb);
         float c[8][4];
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
@@ -180,8 +165,7 @@ thin_mma_wgrad_k(View<bf16> in, View<bf16> dy, float* __restrict__ dw, int N, in
 
     const int tiles_per_row = OW >> 4;
     const long long ntiles = (long long)N * OH * tiles_per_row;
-    // raw operands of one tile; the next tile's loads are issued before this tile's MMAs (the packing happens at use)
-    auto load_tile = [&](long long tile, uint32_t (&u)[4][2], uint32_t (&v)[4][4]) {
+    for (long long tile = (long long)blockIdx.x * THIN_WARPS + warp; tile < ntiles; tile += (long long)gridDim.x * THIN_WARPS) {
         const unsigned tu = (unsigned)tile, r = tu / (unsigned)tiles_per_row;      // 32-bit divisions (tiles < 2^31)
         const int xt = (int)(tu - r * (unsigned)tiles_per_row);
         const int n = (int)(r / (unsigned)OH), y = (int)(r - (unsigned)n * (unsigned)OH);
@@ -189,35 +173,24 @@ thin_mma_wgrad_k(View<bf16> in, View<bf16> dy, float* __restrict__ dw, int N, in
         const bf16* px = in.at(n, y, x0 + 2 * q, 0);
         // gradient rows of the 4 pixels this thread contracts over: channel pairs (2g, 2g+1) of each 16-channel group
         const bf16* pd = dy.at(n, y, x0 + 2 * q, cb + 2 * g);
+        uint32_t u[4][2];                                       // [pixel 2q, 2q+1, 2q+8, 2q+9][group]
 #pragma unroll
-        for (int pp = 0; pp < 4; ++pp) {                        // [pixel 2q, 2q+1, 2q+8, 2q+9][group]
+        for (int pp = 0; pp < 4; ++pp) {
             const bf16* row = pd + ((pp & 1) + 8 * (pp >> 1)) * dy.sx;
 #pragma unroll
             for (int jj = 0; jj < 2; ++jj) u[pp][jj] = __ldg(reinterpret_cast<const uint32_t*>(row + 16 * jj));
         }
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {                           // kk = g + 8 i
-            v[i][0] = v[i][1] = v[i][2] = v[i][3] = 0;
-            if (off[i] >= 0) {
-                const bf16* p0 = px + off[i];
-                v[i][0] = ldg_u16(p0); v[i][1] = ldg_u16(p0 + in.sx); v[i][2] = ldg_u16(p0 + 8 * in.sx); v[i][3] = ldg_u16(p0 + 9 * in.sx);
-            }
-        }
-    };
-    const long long tstep = (long long)gridDim.x * THIN_WARPS;
-    long long tile = (long long)blockIdx.x * THIN_WARPS + warp;
-    uint32_t un[4][2], vn[4][4];
-    if (tile < ntiles) load_tile(tile, un, vn);
-    for (; tile < ntiles; tile += tstep) {
-        uint32_t u[4][2], a[2][4];
-#pragma unroll
-        for (int pp = 0; pp < 4; ++pp) { u[pp][0] = un[pp][0]; u[pp][1] = un[pp][1]; }
+        uint32_t a[2][4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) {                           // kk = g + 8 i  ->  m-tile i >> 1, row half i & 1
-            a[i >> 1][i & 1] = vn[i][0] | (vn[i][1] << 16);                 // k = 2q, 2q+1
-            a[i >> 1][2 + (i & 1)] = vn[i][2] | (vn[i][3] << 16);           // k = 2q+8, 2q+9
+            uint32_t v0 = 0, v1 = 0, v8 = 0, v9 = 0;
+            if (off[i] >= 0) {
+                const bf16* p0 = px + off[i];
+                v0 = ldg_u16(p0); v1 = ldg_u16(p0 + in.sx); v8 = ldg_u16(p0 + 8 * in.sx); v9 = ldg_u16(p0 + 9 * in.sx);
+            }
+            a[i >> 1][i & 1] = v0 | (v1 << 16);                 // k = 2q, 2q+1
+            a[i >> 1][2 + (i & 1)] = v8 | (v9 << 16);           // k = 2q+8, 2q+9
         }
-        if (tile + tstep < ntiles) load_tile(tile + tstep, un, vn);
 #pragma unroll
         for (int jj = 0; jj < 2; ++jj) {
             const uint32_t e0 = __byte_perm(u[0][jj], u[1][jj], 0x5410), o0 = __byte_perm(u[0][jj], u[1][jj], 0x7632);
@@ -338,34 +311,24 @@ head1x1_fprop_k(View<bf16> in, const float* __restrict__ wk, const float* __rest
     const long long stride = ((long long)gridDim.x * blockDim.x) >> g_shift;
     // every lane of a warp runs the same number of iterations (the shuffles below are warp-wide)
     const long long first = ((long long)blockIdx.x * blockDim.x + (threadIdx.x & ~31)) >> g_shift;
-    constexpr int U = 4;                                 // pixels in flight per lane group (one 16-byte load each)
-    for (long long pb = first; pb < P; pb += U * stride) {
-        uint4 raw[U];
-        PixIdx q[U];
-        bool valid[U];
+    for (long long pb = first; pb < P; pb += stride) {
+        const long long pr = pb + ((threadIdx.x & 31) >> g_shift);
+        const bool valid = pr < P;
+        const long long p = valid ? pr : P - 1;
+        const PixIdx q = pix_of(p, H, W);
+        float f[8], acc[CT];
+        unpack8(*reinterpret_cast<const uint4*>(in.at(q.n, q.y, q.x, gl * 8)), f);
 #pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const long long pr = pb + u * stride + ((threadIdx.x & 31) >> g_shift);
-            valid[u] = pr < P;
-            q[u] = pix_of(valid[u] ? pr : P - 1, H, W);
-            raw[u] = *reinterpret_cast<const uint4*>(in.at(q[u].n, q[u].y, q[u].x, gl * 8));
+        for (int c = 0; c < CT; ++c) {
+            float a = 0.f;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) a = fmaf(f[i], w[i][c], a);
+            for (int o = 1; o < G; o <<= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+            acc[c] = a;
         }
+        if (gl == 0 && valid) {
 #pragma unroll
-        for (int u = 0; u < U; ++u) {
-            float f[8], acc[CT];
-            unpack8(raw[u], f);
-#pragma unroll
-            for (int c = 0; c < CT; ++c) {
-                float a = 0.f;
-#pragma unroll
-                for (int i = 0; i < 8; ++i) a = fmaf(f[i], w[i][c], a);
-                for (int o = 1; o < G; o <<= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
-                acc[c] = a;
-            }
-            if (gl == 0 && valid[u]) {
-#pragma unroll
-                for (int c = 0; c < CT; ++c) from_f(out.at(q[u].n, q[u].y, q[u].x, c), acc[c] + (bias ? bias[c] : 0.f));
-            }
+            for (int c = 0; c < CT; ++c) from_f(out.at(q.n, q.y, q.x, c), acc[c] + (bias ? bias[c] : 0.f));
         }
     }
 }
@@ -383,32 +346,22 @@ head1x1_dgrad_k(View<bf16> dy, const float* __restrict__ wd, View<bf16> dx, int 
         for (int i = 0; i < 8; ++i) w[c][i] = wd[c * Cw + gl * 8 + i];
     const long long P = (long long)N * H * W;
     const long long stride = ((long long)gridDim.x * blockDim.x) >> g_shift;
-    constexpr int U = 4;
-    for (long long p0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> g_shift; p0 < P; p0 += U * stride) {
-        PixIdx q[U];
-        bf16 graw[U][CT];
+    for (long long p = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> g_shift; p < P; p += stride) {
+        const PixIdx q = pix_of(p, H, W);
+        float g[CT];
 #pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const long long p = p0 + u * stride;
-            q[u] = pix_of(p < P ? p : P - 1, H, W);
+        for (int c = 0; c < CT; ++c) g[c] = to_f(*dy.at(q.n, q.y, q.x, c));
+        float o[8];
 #pragma unroll
-            for (int c = 0; c < CT; ++c) graw[u][c] = *dy.at(q[u].n, q[u].y, q[u].x, c);
+        for (int i = 0; i < 8; ++i) {
+            float a = 0.f;
+#pragma unroll
+            for (int c = 0; c < CT; ++c) a = fmaf(g[c], w[c][i], a);
+            o[i] = a;
         }
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-            if (p0 + u * stride >= P) break;
-            float o[8];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                float a = 0.f;
-#pragma unroll
-                for (int c = 0; c < CT; ++c) a = fmaf(to_f(graw[u][c]), w[c][i], a);
-                o[i] = a;
-            }
-            uint4 v;
-            v.x = pack_bf16(o[0], o[1]); v.y = pack_bf16(o[2], o[3]); v.z = pack_bf16(o[4], o[5]); v.w = pack_bf16(o[6], o[7]);
-            *reinterpret_cast<uint4*>(dx.at(q[u].n, q[u].y, q[u].x, gl * 8)) = v;
-        }
+        uint4 u;
+        u.x = pack_bf16(o[0], o[1]); u.y = pack_bf16(o[2], o[3]); u.z = pack_bf16(o[4], o[5]); u.w = pack_bf16(o[6], o[7]);
+        *reinterpret_cast<uint4*>(dx.at(q.n, q.y, q.x, gl * 8)) = u;
     }
 }
 
@@ -425,30 +378,16 @@ head1x1_wgrad_k(View<bf16> x, View<bf16> dy, float* __restrict__ dw, int N, int 
         for (int i = 0; i < 8; ++i) acc[c][i] = 0.f;
     const long long P = (long long)N * H * W;
     const long long stride = ((long long)gridDim.x * blockDim.x) >> g_shift;
-    constexpr int U = 4;
-    for (long long p0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> g_shift; p0 < P; p0 += U * stride) {
-        uint4 raw[U];
-        bf16 graw[U][CT];
+    for (long long p = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> g_shift; p < P; p += stride) {
+        const PixIdx q = pix_of(p, H, W);
+        float f[8], g[CT];
+        unpack8(*reinterpret_cast<const uint4*>(x.at(q.n, q.y, q.x, gl * 8)), f);
 #pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const long long p = p0 + u * stride;
-            const PixIdx q = pix_of(p < P ? p : P - 1, H, W);
-            raw[u] = *reinterpret_cast<const uint4*>(x.at(q.n, q.y, q.x, gl * 8));
+        for (int c = 0; c < CT; ++c) g[c] = to_f(*dy.at(q.n, q.y, q.x, c));
 #pragma unroll
-            for (int c = 0; c < CT; ++c) graw[u][c] = *dy.at(q.n, q.y, q.x, c);
-        }
+        for (int c = 0; c < CT; ++c)
 #pragma unroll
-        for (int u = 0; u < U; ++u) {
-            if (p0 + u * stride >= P) break;
-            float f[8];
-            unpack8(raw[u], f);
-#pragma unroll
-            for (int c = 0; c < CT; ++c) {
-                const float g = to_f(graw[u][c]);
-#pragma unroll
-                for (int i = 0; i < 8; ++i) acc[c][i] = fmaf(g, f[i], acc[c][i]);
-            }
-        }
+            for (int i = 0; i < 8; ++i) acc[c][i] = fmaf(g[c], f[i], acc[c][i]);
     }
     for (int i = threadIdx.x; i < CT * Cw; i += blockDim.x) red[i] = 0.f;
     __syncthreads();
