@@ -148,6 +148,9 @@ int kp_c1_fprop(cudaStream_t st, const kp_view* in, const float* wk, const float
 bool kp_c1_wgrad_ok(const kp_view* x, const kp_view* dy, int Cin, int Cout, int ks);
 int kp_c1_wgrad(cudaStream_t st, const kp_view* x, const kp_view* dy, float* dw, int N, int H, int W, int Cout);
 // streaming kernels for a 1x1 head with <= 4 outputs on a 64..256-channel bf16 input (kp_conv_thin_mma.cu)
+bool kp_head_mma_fprop_ok(const kp_view* in, const kp_view* out, int N, int H, int W, int Cw, int Ct);
+int kp_head_mma_fprop(cudaStream_t st, const kp_view* in, const float* wk, const float* bias, const kp_view* out, int N, int H,
+                      int W, int Cw, int Ct);
 bool kp_head1x1_ok(const kp_view* wide, const kp_view* thin, int Cw, int Ct);
 int kp_head1x1_fprop(cudaStream_t st, const kp_view* in, const float* wk, const float* bias, const kp_view* out, int N, int H,
                      int W, int Cw, int Ct);

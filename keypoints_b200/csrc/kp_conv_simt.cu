@@ -546,6 +546,8 @@ extern "C" int kp_conv_simt(kp_stream stream, const kp_view* in, const float* wk
     dim3 grid((unsigned)((M + BM - 1) / BM), (unsigned)((Cout + BN - 1) / BN), 1);
     const int KKt = ks * ks * Cin;
     const bool out2 = out->sc == 1 && (((uintptr_t)out->ptr) % 8) == 0 && out->sx % 2 == 0 && out->sy % 2 == 0 && out->sn % 2 == 0;
+    if (thin_mma_enabled() && ks == 1 && !stats && OH == IH && OW == IW && kp_head_mma_fprop_ok(in, out, N, OH, OW, Cin, Cout))
+        return kp_head_mma_fprop((cudaStream_t)stream, in, wk, bias, out, N, OH, OW, Cin, Cout);
     if (thin_mma_enabled() && ks == 1 && !stats && OH == IH && OW == IW && M < (1LL << 31)) {
         // 1x1 head: forward (wide -> <= 4) or its data gradient (<= 4 -> wide); wk is [Cin][Cout] in both cases
         if (kp_head1x1_ok(in, out, Cin, Cout))

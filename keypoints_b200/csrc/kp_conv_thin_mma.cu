@@ -416,6 +416,69 @@ static bool wide_ok(const kp_view* v, int Cw) {      // bf16, 16-byte aligned 8-
            v->sx % 8 == 0 && v->sy % 8 == 0 && v->sn % 8 == 0;
 }
 
+// 1x1 conv from a wide bf16 activation to <= 32 outputs (decoder 64 -> 3 head at full resolution, 512 -> K keypoint
+// heads) on mma.sync.m16n8k16: the lane-group kernels above spend ~440 instructions per 16 pixels on unpack / FMA / shuffle
+// chains and are issue-bound at 1.3 TB/s; here 16 flat pixels are one M tile, A fragments are 4-byte loads straight from
+// the NHWC rows, the (bf16-rounded, like every tensor-core layer) weights sit in shared memory in B-fragment order.
+template <int NT, typename TO>
+__global__ void __launch_bounds__(256)
+head_mma_fprop_k(View<bf16> in, const float* __restrict__ wk /*[Cw][Ct]*/, const float* __restrict__ bias, View<TO> out, int N,
+                 int H, int W, int Cw, int Ct) {
+    extern __shared__ uint2 hm_wf[];                 // [Cw / 16][NT][32]
+    const int KS = Cw >> 4;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, q = lane & 3;
+    for (int i = threadIdx.x; i < KS * NT * 32; i += blockDim.x) {
+        const int ln = i & 31, nt = (i >> 5) % NT, ks = (i >> 5) / NT;
+        const int co = nt * 8 + (ln >> 2), k0 = ks * 16 + 2 * (ln & 3);
+        uint2 v = make_uint2(0u, 0u);
+        if (co < Ct) {
+            v.x = pack_bf16(wk[(long long)k0 * Ct + co], wk[(long long)(k0 + 1) * Ct + co]);
+            v.y = pack_bf16(wk[(long long)(k0 + 8) * Ct + co], wk[(long long)(k0 + 9) * Ct + co]);
+        }
+        hm_wf[i] = v;
+    }
+    float bv[NT][2];
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) { const int co = nt * 8 + 2 * q + e; bv[nt][e] = (bias && co < Ct) ? bias[co] : 0.f; }
+    __syncthreads();
+    const unsigned P = (unsigned)N * (unsigned)H * (unsigned)W, ntiles = (P + 15) >> 4;
+    for (unsigned tile = blockIdx.x * 8 + warp; tile < ntiles; tile += gridDim.x * 8) {
+        const unsigned p0 = tile * 16 + g, p1 = p0 + 8;
+        const bool va = p0 < P, vb = p1 < P;
+        const PixIdx qa = pix_of(va ? p0 : P - 1, H, W), qb = pix_of(vb ? p1 : P - 1, H, W);
+        const bf16* pa = in.at(qa.n, qa.y, qa.x, 2 * q);
+        const bf16* pb = in.at(qb.n, qb.y, qb.x, 2 * q);
+        float c[NT][4];
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) { c[nt][0] = bv[nt][0]; c[nt][1] = bv[nt][1]; c[nt][2] = bv[nt][0]; c[nt][3] = bv[nt][1]; }
+#pragma unroll 4
+        for (int ks = 0; ks < KS; ++ks) {
+            uint32_t a[4];
+            a[0] = *reinterpret_cast<const uint32_t*>(pa + 16 * ks);
+            a[1] = *reinterpret_cast<const uint32_t*>(pb + 16 * ks);
+            a[2] = *reinterpret_cast<const uint32_t*>(pa + 16 * ks + 8);
+            a[3] = *reinterpret_cast<const uint32_t*>(pb + 16 * ks + 8);
+#pragma unroll
+            for (int nt = 0; nt < NT; ++nt) {
+                const uint2 w = hm_wf[(ks * NT + nt) * 32 + lane];
+                mma_bf16_16816(c[nt], a, w.x, w.y);
+            }
+        }
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int co = nt * 8 + 2 * q + e;
+                if (co < Ct) {
+                    if (va) from_f(out.at(qa.n, qa.y, qa.x, co), c[nt][e]);
+                    if (vb) from_f(out.at(qb.n, qb.y, qb.x, co), c[nt][2 + e]);
+                }
+            }
+    }
+}
+
 }  // namespace
 
 bool kp_head1x1_ok(const kp_view* wide, const kp_view* thin, int Cw, int Ct) {      // callers pass images of < 2^31 pixels
@@ -458,6 +521,30 @@ int kp_head1x1_wgrad(cudaStream_t st, const kp_view* x, const kp_view* dy, float
 #define KP_C(CT) head1x1_wgrad_k<CT><<<(int)blocks, 256, 0, st>>>(make_view<bf16>(x), make_view<bf16>(dy), dw, N, H, W, Cw, sh)
     KP_HEAD_CT(Ct, KP_C);
 #undef KP_C
+    KP_LAUNCH_CHECK();
+    return KP_OK;
+}
+
+bool kp_head_mma_fprop_ok(const kp_view* in, const kp_view* out, int N, int H, int W, int Cw, int Ct) {
+    static int on = -1;
+    if (on < 0) { const char* e = getenv("KP_HEAD_MMA"); on = e ? atoi(e) : 1; }
+    return on && in->dtype == KP_BF16 && in->sc == 1 && (((uintptr_t)in->ptr) % 4) == 0 && in->sx % 2 == 0 && in->sy % 2 == 0 &&
+           in->sn % 2 == 0 && Cw % 16 == 0 && Cw >= 16 && Cw <= 512 && Ct >= 1 && Ct <= 32 &&
+           (out->dtype == KP_BF16 || out->dtype == KP_F32) && (long long)N * H * W < (1LL << 31) - 16;
+}
+
+int kp_head_mma_fprop(cudaStream_t st, const kp_view* in, const float* wk, const float* bias, const kp_view* out, int N, int H,
+                      int W, int Cw, int Ct) {
+    const long long tiles = ((long long)N * H * W + 15) / 16;
+    long long blocks = (tiles + 7) / 8;
+    const long long cap = (long long)kp_sm_count() * 8;
+    if (blocks > cap) blocks = cap;
+    const int NT = Ct <= 8 ? 1 : (Ct <= 16 ? 2 : 4);
+    const size_t smem = (size_t)(Cw / 16) * NT * 32 * sizeof(uint2);
+#define KP_HM(NTV, TOV) head_mma_fprop_k<NTV, TOV><<<(int)blocks, 256, smem, st>>>(make_view<bf16>(in), wk, bias, make_view<TOV>(out), N, H, W, Cw, Ct)
+    if (out->dtype == KP_BF16) { if (NT == 1) KP_HM(1, bf16); else if (NT == 2) KP_HM(2, bf16); else KP_HM(4, bf16); }
+    else { if (NT == 1) KP_HM(1, float); else if (NT == 2) KP_HM(2, float); else KP_HM(4, float); }
+#undef KP_HM
     KP_LAUNCH_CHECK();
     return KP_OK;
 }

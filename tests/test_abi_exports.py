@@ -51,7 +51,7 @@ def test_sass_is_blackwell_native(built):
     body = {k: '\n'.join(v) for k, v in funcs.items()}
     for k, text in body.items():
         if 'HMMA' in text.replace('UTCHMMA', ''):
-            assert 'thin_mma' in k or 'small_mma' in k, f'legacy mma.sync code in {k}'
+            assert 'thin_mma' in k or 'small_mma' in k or 'head_mma' in k, f'legacy mma.sync code in {k}'
     conv = [k for k in body if 'conv_tc_pair' in k or 'wgrad_tc_pair_k' in k]
     assert conv and all('UTCHMMA' in body[k] and 'UTMALDG' in body[k] for k in conv)
     pipe = [k for k in body if '_pipe_k' in k and 'small_mma' not in k]

@@ -337,6 +337,27 @@ def test_small_channel_mma_conv_vs_fp32(dev, cin, cout, n, h, w, k):
     close(dx, xr.grad, 2e-2, 'dgrad')
 
 
+@pytest.mark.parametrize('cw,ct,n,h,w,odt', [(64, 3, 2, 128, 128, torch.bfloat16), (512, 10, 3, 16, 16, torch.float32),
+                                             (128, 30, 2, 16, 16, torch.bfloat16), (32, 4, 2, 84, 84, torch.float32),
+                                             (16, 1, 2, 21, 13, torch.bfloat16)])
+def test_head_mma_1x1_vs_fp32(dev, cw, ct, n, h, w, odt):
+    """Narrow 1x1 heads (decoder 64 -> 3, 512 -> K keypoint heads, the Pong heads) through the C ABI (kp_conv_simt ->
+    head_mma_fprop_k): interior view of a padded bf16 buffer in, dense bf16 / fp32 out, against an fp32 reference fed the
+    same bf16-rounded operands; pixel counts that are not multiples of 16 exercise the masked tile tail."""
+    from keypoints_b200 import lib as L
+    torch.manual_seed(cw + ct)
+    xp = torch.randn(n, h + 2, w + 2, cw, device=dev).bfloat16()
+    xin = xp[:, 1:h + 1, 1:w + 1, :]
+    wk = (torch.randn(cw, ct, device=dev) / cw ** 0.5).bfloat16().float().contiguous()      # [ci][co]
+    bias = torch.randn(ct, device=dev) * 0.1
+    out = torch.full((n, h, w, ct), float('nan'), device=dev, dtype=odt)
+    L.call('kp_conv_simt', L.stream(), L.view(xin), L.ptr(wk), L.ptr(bias), L.view(out), None, n, h, w, h, w, cw, ct, 1, 0)
+    torch.cuda.synchronize()
+    ref = torch.einsum('nhwc,co->nhwo', xin.float(), wk) + bias
+    assert torch.isfinite(out.float()).all()
+    close(out.float(), ref, 1e-2 if odt == torch.bfloat16 else 1e-4, f'1x1 head {cw}->{ct}')
+
+
 def test_adjoint_identity_full_size(dev):
     """Size-independent property at the BASELINE layer sizes: <conv(x,w), dy> == <w, wgrad(x,dy)> == <x, dgrad(dy,w)>
     for the tensor-core kernels (bf16 operands, fp32 accumulation), 128x128x64->128 at batch 8."""
