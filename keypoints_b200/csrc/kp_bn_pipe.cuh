@@ -50,12 +50,14 @@ __device__ __forceinline__ void consumer_sync() { asm volatile("bar.sync 1, 256;
 
 // Position of a CTA in the (image, row, chunk) unit space, advanced by gridDim.x units per step without divisions.
 struct Cursor {
-    int n, yy, ch;
+    int n, yy, ch;                     // n = image the unit belongs to (reversed order when nrev > 0)
+    int nf, nrev;
     int dn, dyy, dch, R, cpr;
-    __device__ __forceinline__ void init(int u0, int stride, int rows_per_image, int chunks_per_row) {
-        R = rows_per_image; cpr = chunks_per_row;
-        ch = u0 % cpr; int row = u0 / cpr; yy = row % R; n = row / R;
+    __device__ __forceinline__ void init(int u0, int stride, int rows_per_image, int chunks_per_row, int n_rev) {
+        R = rows_per_image; cpr = chunks_per_row; nrev = n_rev;
+        ch = u0 % cpr; int row = u0 / cpr; yy = row % R; nf = row / R;
         dch = stride % cpr; int drow = stride / cpr; dyy = drow % R; dn = drow / R;
+        n = nrev > 0 ? nrev - 1 - nf : nf;
     }
     __device__ __forceinline__ void next() {
         ch += dch;
@@ -64,14 +66,18 @@ struct Cursor {
         yy += dyy + c;
         c = yy >= R ? 1 : 0;
         yy -= c ? R : 0;
-        n += dn + c;
+        nf += dn + c;
+        n = nrev > 0 ? nrev - 1 - nf : nf;
     }
 };
 
+// n_rev = 0: images first to last; n_rev = N: last to first.  A pass that follows a producer sweeping the tensor front to
+// back (a conv, or the previous BatchNorm pass) starts where the producer ended, i.e. on the ~100 MB still in the L2.
 // Shared skeleton: STAGES-deep ring of STAGE_BYTES.  `issue(cur, stage, full)` (one producer thread) posts the expected
 // byte count and the bulk copies of the unit at cursor `cur`; `body(cur, stage)` consumes one unit (256 consumer threads).
 template <int STAGE_BYTES, int STAGES, class IssueFn, class BodyFn>
-__device__ __forceinline__ void pipe_run(uint8_t* smem, int units, int rows_per_image, int cpr, IssueFn issue, BodyFn body) {
+__device__ __forceinline__ void pipe_run(uint8_t* smem, int units, int rows_per_image, int cpr, int n_rev, IssueFn issue,
+                                         BodyFn body) {
     using namespace pipe;
     const uint32_t bars = s32(smem + STAGES * STAGE_BYTES);      // full[STAGES], empty[STAGES]
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -85,7 +91,7 @@ __device__ __forceinline__ void pipe_run(uint8_t* smem, int units, int rows_per_
     __syncthreads();
     const int mine = ((int)blockIdx.x < units) ? (units - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
     Cursor cur;
-    cur.init(blockIdx.x, gridDim.x, rows_per_image, cpr);
+    cur.init(blockIdx.x, gridDim.x, rows_per_image, cpr, n_rev);
     if (warp == CONSUMERS / 32) {
         if (lane == 0) {
             int s = 0, ph = 0;
@@ -123,7 +129,7 @@ constexpr int PIPE_APPLY_STAGE = 2 * pipe::CHUNK_BYTES, PIPE_APPLY_STAGES = 4;
 template <int ACT>
 __global__ void __launch_bounds__(pipe::THREADS, 2)
 bn_fwd_none_pipe_k(Rows<const bf16> y, Rows<bf16> out, const float* __restrict__ scale, const float* __restrict__ shift,
-                   int pad, int N, int H, int W, int C, int cg_shift, int cpr, const BnFuse fuse) {
+                   int pad, int N, int H, int W, int C, int cg_shift, int cpr, const BnFuse fuse, int rev) {
     extern __shared__ __align__(128) uint8_t smem[];
     const int tid = threadIdx.x;
     const int ncg = C >> 3;
@@ -173,7 +179,7 @@ bn_fwd_none_pipe_k(Rows<const bf16> y, Rows<bf16> out, const float* __restrict__
             }
         }
     };
-    pipe_run<PIPE_FWD_STAGE, PIPE_FWD_STAGES>(smem, units, PH, cpr, issue, body);
+    pipe_run<PIPE_FWD_STAGE, PIPE_FWD_STAGES>(smem, units, PH, cpr, rev, issue, body);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -212,7 +218,7 @@ __global__ void __launch_bounds__(pipe::THREADS, 2)
 bn_bwd_none_pipe_k(Rows<const bf16> dout, Rows<const bf16> y, Rows<bf16> dy, const float* __restrict__ scale,
                    const float* __restrict__ shift, const float* __restrict__ mean, const float* __restrict__ invstd,
                    double* sums, double count, int pad, int N, int H, int W, int C, int cg_shift, int cpr, float* dgamma,
-                   float* dbeta) {
+                   float* dbeta, int rev) {
     extern __shared__ __align__(128) uint8_t smem[];
     const int tid = threadIdx.x;
     const int ncg = C >> 3;
@@ -288,7 +294,7 @@ bn_bwd_none_pipe_k(Rows<const bf16> dout, Rows<const bf16> y, Rows<bf16> dy, con
             if (MODE != PASS1_SUMS) P8<bf16>::st(orow + e, g);
         }
     };
-    pipe_run<PIPE_BWD_STAGE, PIPE_BWD_STAGES>(smem, units, H, cpr, issue, body);
+    pipe_run<PIPE_BWD_STAGE, PIPE_BWD_STAGES>(smem, units, H, cpr, rev, issue, body);
     if (tid >= pipe::CONSUMERS || MODE == PASS2_GATHER) return;
     // every unit of this CTA has been consumed: the ring is free, reuse it for the block reduction
     pipe::consumer_sync();
@@ -363,7 +369,7 @@ bn_bwd_apply_pipe_k(Rows<const bf16> y, Rows<bf16> dy, const float* __restrict__
             P8<bf16>::st(orow + item * 8, g);
         }
     };
-    pipe_run<PIPE_APPLY_STAGE, PIPE_APPLY_STAGES>(smem, units, H, cpr, issue, body);
+    pipe_run<PIPE_APPLY_STAGE, PIPE_APPLY_STAGES>(smem, units, H, cpr, 0, issue, body);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -379,7 +385,7 @@ constexpr int PIPE_BPOOL_STAGE = 2 * PIPE_POOL_YBYTES + PIPE_POOL_ITEMS * 16 + 2
 template <int ACT>
 __global__ void __launch_bounds__(pipe::THREADS, 2)
 bn_fwd_pool_pipe_k(Rows<const bf16> y, Rows<bf16> out, const float* __restrict__ scale, const float* __restrict__ shift,
-                   int pad, int N, int OH, int OW, int C, int cg_shift, int cpr, const BnFuse fuse) {
+                   int pad, int N, int OH, int OW, int C, int cg_shift, int cpr, const BnFuse fuse, int rev) {
     extern __shared__ __align__(128) uint8_t smem[];
     const int tid = threadIdx.x;
     const int ncg = C >> 3;
@@ -439,7 +445,7 @@ bn_fwd_pool_pipe_k(Rows<const bf16> y, Rows<bf16> out, const float* __restrict__
             if (ox == OW - 1) *reinterpret_cast<uint4*>(dst + C) = o;
         }
     };
-    pipe_run<PIPE_FPOOL_STAGE, PIPE_FPOOL_STAGES>(smem, units, PH, cpr, issue, body);
+    pipe_run<PIPE_FPOOL_STAGE, PIPE_FPOOL_STAGES>(smem, units, PH, cpr, rev, issue, body);
 }
 
 // backward pass 1: the gradient of a pooled pixel goes to the first maximum of its window (row-major), zeros elsewhere
@@ -448,7 +454,7 @@ __global__ void __launch_bounds__(pipe::THREADS, 2)
 bn_bwd_pool_pipe_k(Rows<const bf16> dout, Rows<const bf16> y, Rows<bf16> dy, const float* __restrict__ scale,
                    const float* __restrict__ shift, const float* __restrict__ mean, const float* __restrict__ invstd,
                    double* sums, double count, int pad, int N, int OH, int OW, int C, int cg_shift, int cpr, float* dgamma,
-                   float* dbeta) {
+                   float* dbeta, int rev) {
     extern __shared__ __align__(128) uint8_t smem[];
     const int tid = threadIdx.x;
     const int ncg = C >> 3;
@@ -542,7 +548,7 @@ bn_bwd_pool_pipe_k(Rows<const bf16> dout, Rows<const bf16> y, Rows<bf16> dy, con
             }
         }
     };
-    pipe_run<PIPE_BPOOL_STAGE, PIPE_BPOOL_STAGES>(smem, units, OH, cpr, issue, body);
+    pipe_run<PIPE_BPOOL_STAGE, PIPE_BPOOL_STAGES>(smem, units, OH, cpr, rev, issue, body);
     if (tid >= pipe::CONSUMERS || MODE == PASS2_GATHER) return;
     pipe::consumer_sync();
     float* red = reinterpret_cast<float*>(smem);

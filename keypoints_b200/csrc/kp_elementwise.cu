@@ -987,6 +987,16 @@ static int pipe_grid(long long units) {
     return (int)(units < cap ? units : cap);
 }
 static int ilog2(int v) { int s = 0; while ((1 << s) < v) ++s; return s; }
+// image order of the bulk-async BatchNorm passes (kp_bn_pipe.cuh Cursor): bit 0 forward passes, bit 1 backward pass 1,
+// bit 2 backward pass 2 run last image first.  Default 5 (measured, KeyNet F batch 64: mask 0 4307-4333 pairs/s, 1 4363,
+// 2 4345, 3 4384, 7 4340, 5 4415): the forward pass starts on the tail of y the conv just wrote, pass 1 sweeps forward and
+// pass 2 comes back over the same (dout, y) tail; the convs that follow sweep forward again.  KP_BN_REV overrides the mask.
+static int bn_rev(int role, int N) {
+    static int mask = -1;
+    if (mask < 0) { const char* e = getenv("KP_BN_REV"); mask = e ? atoi(e) : 5; }
+    return (mask & role) ? N : 0;
+}
+
 static int rows_grid(long long rows) {
     long long cap = (long long)kp_sm_count() * 8;
     return (int)(rows < cap ? (rows < 1 ? 1 : rows) : cap);
@@ -1047,7 +1057,7 @@ static int bn_act_fwd_impl(kp_stream stream, const kp_view* y, const kp_view* ou
         int rc_ = pipe_attr(bn_fwd_none_pipe_k<ACTV>, smem);                                                           \
         if (rc_) return rc_;                                                                                           \
         bn_fwd_none_pipe_k<ACTV><<<pipe_grid(units), pipe::THREADS, smem, st>>>(                                       \
-            make_rows<const bf16>(y), make_rows<bf16>(out), scale, shift, pad, N, H, W, C, sh, cpr, fz);               \
+            make_rows<const bf16>(y), make_rows<bf16>(out), scale, shift, pad, N, H, W, C, sh, cpr, fz, bn_rev(1, N));              \
     } while (0)
                 KP_ACT_SWITCH(act, KP_FWDP);
 #undef KP_FWDP
@@ -1063,7 +1073,7 @@ static int bn_act_fwd_impl(kp_stream stream, const kp_view* y, const kp_view* ou
         int rc_ = pipe_attr(bn_fwd_pool_pipe_k<ACTV>, smem);                                                           \
         if (rc_) return rc_;                                                                                           \
         bn_fwd_pool_pipe_k<ACTV><<<pipe_grid(units), pipe::THREADS, smem, st>>>(                                       \
-            make_rows<const bf16>(y), make_rows<bf16>(out), scale, shift, pad, N, OH, OW, C, sh, cpr, fz);             \
+            make_rows<const bf16>(y), make_rows<bf16>(out), scale, shift, pad, N, OH, OW, C, sh, cpr, fz, bn_rev(1, N));            \
     } while (0)
                 KP_ACT_SWITCH(act, KP_FWDPP);
 #undef KP_FWDPP
@@ -1181,13 +1191,13 @@ extern "C" int kp_bn_act_bwd_reduce(kp_stream stream, const kp_view* dout, const
             if (rc_) return rc_;                                                                                       \
             bn_bwd_none_pipe_k<ACTV, PASS1_WRITE><<<pipe_grid(units), pipe::THREADS, smem, st>>>(                      \
                 make_rows<const bf16>(dout), make_rows<const bf16>(y), make_rows<bf16>(dyv), scale, shift, mean,       \
-                invstd, sums, 1.0, pad, N, H, W, C, sh, cpr, nullptr, nullptr);                                        \
+                invstd, sums, 1.0, pad, N, H, W, C, sh, cpr, nullptr, nullptr, bn_rev(2, N));                                       \
         } else {                                                                                                       \
             int rc_ = pipe_attr(bn_bwd_none_pipe_k<ACTV, PASS1_SUMS>, smem);                                           \
             if (rc_) return rc_;                                                                                       \
             bn_bwd_none_pipe_k<ACTV, PASS1_SUMS><<<pipe_grid(units), pipe::THREADS, smem, st>>>(                       \
                 make_rows<const bf16>(dout), make_rows<const bf16>(y), make_rows<bf16>(dyv), scale, shift, mean,       \
-                invstd, sums, 1.0, pad, N, H, W, C, sh, cpr, nullptr, nullptr);                                        \
+                invstd, sums, 1.0, pad, N, H, W, C, sh, cpr, nullptr, nullptr, bn_rev(2, N));                                       \
         }                                                                                                              \
     } while (0)
                     KP_ACT_SWITCH(act, KP_BWDP);
@@ -1205,13 +1215,13 @@ extern "C" int kp_bn_act_bwd_reduce(kp_stream stream, const kp_view* dout, const
             if (rc_) return rc_;                                                                                       \
             bn_bwd_pool_pipe_k<ACTV, PASS1_WRITE><<<pipe_grid(units), pipe::THREADS, smem, st>>>(                      \
                 make_rows<const bf16>(dout), make_rows<const bf16>(y), make_rows<bf16>(dyv), scale, shift, mean,       \
-                invstd, sums, 1.0, pad, N, OH, OW, C, sh, cpr, nullptr, nullptr);                                      \
+                invstd, sums, 1.0, pad, N, OH, OW, C, sh, cpr, nullptr, nullptr, bn_rev(2, N));                                     \
         } else {                                                                                                       \
             int rc_ = pipe_attr(bn_bwd_pool_pipe_k<ACTV, PASS1_SUMS>, smem);                                           \
             if (rc_) return rc_;                                                                                       \
             bn_bwd_pool_pipe_k<ACTV, PASS1_SUMS><<<pipe_grid(units), pipe::THREADS, smem, st>>>(                       \
                 make_rows<const bf16>(dout), make_rows<const bf16>(y), make_rows<bf16>(dyv), scale, shift, mean,       \
-                invstd, sums, 1.0, pad, N, OH, OW, C, sh, cpr, nullptr, nullptr);                                      \
+                invstd, sums, 1.0, pad, N, OH, OW, C, sh, cpr, nullptr, nullptr, bn_rev(2, N));                                     \
         }                                                                                                              \
     } while (0)
                     KP_ACT_SWITCH(act, KP_BWDPP);
@@ -1310,7 +1320,7 @@ extern "C" int kp_bn_act_bwd_apply_gather(kp_stream stream, const kp_view* dout,
         if (rc_) return rc_;                                                                                           \
         bn_bwd_none_pipe_k<ACTV, PASS2_GATHER><<<pipe_grid(units), pipe::THREADS, smem, st>>>(                         \
             make_rows<const bf16>(dout), make_rows<const bf16>(y), make_rows<bf16>(dy), scale, shift, mean, invstd,    \
-            const_cast<double*>(sums), count, pad, N, H, W, C, sh, cpr, dgamma, dbeta);                                \
+            const_cast<double*>(sums), count, pad, N, H, W, C, sh, cpr, dgamma, dbeta, bn_rev(4, N));                               \
     } while (0)
         KP_ACT_SWITCH(act, KP_GATHN);
 #undef KP_GATHN
@@ -1327,7 +1337,7 @@ extern "C" int kp_bn_act_bwd_apply_gather(kp_stream stream, const kp_view* dout,
         if (rc_) return rc_;                                                                                           \
         bn_bwd_pool_pipe_k<ACTV, PASS2_GATHER><<<pipe_grid(units), pipe::THREADS, smem, st>>>(                         \
             make_rows<const bf16>(dout), make_rows<const bf16>(y), make_rows<bf16>(dy), scale, shift, mean, invstd,    \
-            const_cast<double*>(sums), count, pad, N, OH, OW, C, sh, cpr, dgamma, dbeta);                              \
+            const_cast<double*>(sums), count, pad, N, OH, OW, C, sh, cpr, dgamma, dbeta, bn_rev(4, N));                             \
     } while (0)
         KP_ACT_SWITCH(act, KP_GATHP);
 #undef KP_GATHP
