@@ -24,6 +24,10 @@
 #ifdef __cplusplus
 extern "C" {
 #endif
+/* the library is built with -fvisibility=hidden: only the entry points declared here are exported */
+#if defined(__GNUC__)
+#pragma GCC visibility push(default)
+#endif
 
 typedef void* kp_stream;                 /* cudaStream_t */
 
@@ -218,9 +222,24 @@ int kp_l2_loss(kp_stream stream, const float* xhat, const float* target, const f
  * Augmentation (tps.py:10-87,128-131,154-166; data_augments.py:13-16).  fp32 NCHW.
  * TPS: grid = ((x,y) + a0 + a1 x + a2 y + sum_t w_t U(|p-c_t|)) * 2 - 1, U(d) = d^2 log(d+1e-6),
  * evaluated per output pixel in registers (never materialised), then bilinear grid_sample with
- * zeros padding, align_corners=False.  theta: [N][T+3][2] (or [N][T+2][2] if reduced), ctrl [N][T][2]. */
+ * zeros padding, align_corners=False.  theta: [N][T+3][2] (or [N][T+2][2] if reduced), ctrl [N][T][2].
+ * x == NULL samples the constant image 1 (the start of the loss-mask chain, data_augments.py:33). */
 int kp_tps_warp(kp_stream stream, const float* x, float* out, const float* theta, const float* ctrl,
                 int N, int C, int H, int W, int T, int reduced);
+/* Parameters of `draws` TpsAndRotate perturbations per image, drawn on the device (rand_peturb_params,
+ * data_augments.py:6-10; tps_sample_params, tps.py:122-125): theta ~ N(0, variance^2) [draws][N][T+3][2],
+ * ctrl ~ U[0,1) [draws][N][T][2], rot ~ U(-max_rotate, max_rotate) [draws][N].  Philox4x32-10 keyed by `seed`,
+ * counter = (draw*N+image, block, *step_dev): replaying a captured launch draws fresh parameters every step
+ * (step_dev is the device step counter kp_adam_step advances; NULL = step 0).  The reference draws on the
+ * CPU global RNG; the distribution, not the stream, is what is reproduced here (the parity tests pass the
+ * reference's own draws to kp_tps_warp / kp_rotate_warp). */
+int kp_aug_draw(kp_stream stream, uint64_t seed, const int32_t* step_dev, int draws, int N, int T,
+                float variance, float max_rotate, float* theta, float* ctrl, float* rot);
+/* Input conversion on the device (transforms.ToTensor + Normalize, datasets.py:287-300): uint8 NHWC frames as the
+ * loader ships them over PCIe -> fp32 NCHW, out = in * scale + bias (grey/color: scale 2/255, bias -1; celeba: 1/255, 0). */
+int kp_u8_to_f32(kp_stream stream, const uint8_t* in, float* out, int N, int H, int W, int C, float scale, float bias);
+/* cudaMemsetAsync(ptr, 0, bytes) on `stream` (gradient / statistics accumulators; graph-capturable). */
+int kp_zero(kp_stream stream, void* ptr, int64_t bytes);
 /* rotate_affine_grid_multi: affine_grid([[cos,sin,0],[-sin,cos,0]]) + grid_sample. rot: [N]. */
 int kp_rotate_warp(kp_stream stream, const float* x, float* out, const float* rot, int N, int C,
                    int H, int W);
@@ -234,6 +253,16 @@ int kp_adam_step(kp_stream stream, float* p, const float* g, float* m, float* v,
                  double lr, double beta1, double beta2, double eps, int step, float grad_scale,
                  int32_t* step_dev);
 
+/* Non-blocking loss log (replaces the per-step `loss.item()` host sync of ResultsLogger.log, utils.py:122-130):
+ * ring[2*(s % slots)] = s, ring[2*(s % slots)+1] = *loss_sum * scale with s = *step_dev (0 if NULL); ring is
+ * double[2*slots] in device memory.  The host copies the ring back every k steps on a side stream and reads the
+ * (step, loss) pairs without ever waiting for the step in flight (keypoints_b200/runlog.py). */
+int kp_loss_ring_push(kp_stream stream, const double* loss_sum, double scale, const int32_t* step_dev,
+                      double* ring, int slots);
+
+#if defined(__GNUC__)
+#pragma GCC visibility pop
+#endif
 #ifdef __cplusplus
 }
 #endif

@@ -12,12 +12,12 @@ void kp_set_error(const char* fmt, ...) {
 }
 
 int kp_sm_count() {
-    static int cached = 0;
-    if (cached) return cached;
+    static int cached[64] = {0};          // per device: one process may drive several GPUs
     int dev = 0, n = 0;
     if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+    if (cached[dev & 63]) return cached[dev & 63];
     if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) return 148;
-    cached = n;
+    cached[dev & 63] = n;
     return n;
 }
 

@@ -126,6 +126,19 @@ __device__ __forceinline__ float act_grad(float z, int act) {
 
 int kp_sm_count();
 
+// per-device one-time setup guard (cudaFuncSetAttribute is per device; one process may drive several GPUs)
+struct KpOncePerDevice {
+    unsigned long long mask = 0;
+    bool first() {
+        int d = 0;
+        cudaGetDevice(&d);
+        const unsigned long long b = 1ull << (d & 63);
+        if (mask & b) return false;
+        mask |= b;
+        return true;
+    }
+};
+
 // mma.sync kernels for the first (Cin <= 3) convolution of a Unit in bf16 mode (kp_conv_thin_mma.cu)
 bool kp_thin_mma_fprop_ok(const kp_view* in, const kp_view* out, int OH, int OW, int IH, int IW, int Cin, int Cout, int ks,
                           int off);

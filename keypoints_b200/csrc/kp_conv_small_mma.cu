@@ -653,10 +653,9 @@ int kp_small_mma_conv(cudaStream_t st, const kp_view* in, const float* wk, const
 #define KP_SMP(CI, CO)                                                                                                    \
     do {                                                                                                                  \
         constexpr int smem = SM_WARPS * SC_DEPTH * 3 * 18 * CI * 2;                                                       \
-        static bool attr = false;                                                                                         \
-        if (!attr) {                                                                                                      \
+        static KpOncePerDevice attr;                                                                                           \
+        if (attr.first()) {                                                                                                      \
             cudaFuncSetAttribute(small_mma_conv_pipe_k<CI, CO>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);       \
-            attr = true;                                                                                                  \
         }                                                                                                                 \
         small_mma_conv_pipe_k<CI, CO><<<(unsigned)pb, SM_WARPS * 32, smem, st>>>(make_view<bf16>(in), wk, bias,           \
                                                                                 make_view<bf16>(out), stats, N, OH, OW, IH, IW, \
@@ -713,10 +712,9 @@ int kp_small_mma_wgrad(cudaStream_t st, const kp_view* x, const kp_view* dy, flo
 #define KP_SWP(CI, CO)                                                                                                   \
     do {                                                                                                                 \
         constexpr int smem = SW_STAGES * SW_TPS * (3 * 18 * CI * 2 + 16 * CO * 2);                                       \
-        static bool attr = false;                                                                                        \
-        if (!attr) {                                                                                                     \
+        static KpOncePerDevice attr;                                                                                          \
+        if (attr.first()) {                                                                                                     \
             cudaFuncSetAttribute(small_mma_wgrad_pipe_k<CI, CO>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);     \
-            attr = true;                                                                                                 \
         }                                                                                                                \
         small_mma_wgrad_pipe_k<CI, CO><<<grid, 288, smem, st>>>(make_view<bf16>(x), make_view<bf16>(dy), dw, N, H, W,    \
                                                                 (unsigned)((tiles + blocks - 1) / blocks));              \

@@ -1289,10 +1289,9 @@ static int launch_conv_persist(cudaStream_t st, const CUtensorMap& a, const CUte
     constexpr int smem = STAGES * (STAGE_A_BYTES + BN * 128) + 2 * SLAB_BYTES + (8 * 32 * 17 + 4 * 2 * BN) * 4 +
                          8 * (2 * STAGES + 4) + 16 + 1024;
     static_assert(smem <= 227 * 1024, "shared memory budget");
-    static bool attr_done = false;
-    if (!attr_done) {
+    static KpOncePerDevice attr_done;
+    if (attr_done.first()) {
         KP_CUDA(cudaFuncSetAttribute(conv_tc_persist_k<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        attr_done = true;
     }
     long long total = ((p.Q + 127) / 128) * (p.Cout / BN);
     int grid = (int)(total < kp_sm_count() ? total : kp_sm_count());
@@ -1306,10 +1305,9 @@ static int launch_conv_pair(cudaStream_t st, const CUtensorMap& a, const CUtenso
     constexpr int smem = STAGES * (STAGE_A_BYTES + (BN / 2) * 128) + 2 * SLAB_BYTES + (8 * 32 * 17 + 4 * 2 * BN) * 4 +
                          8 * (2 * STAGES + 4) + 16 + 1024;
     static_assert(smem <= 227 * 1024, "shared memory budget");
-    static bool attr_done = false;
-    if (!attr_done) {
+    static KpOncePerDevice attr_done;
+    if (attr_done.first()) {
         KP_CUDA(cudaFuncSetAttribute(conv_tc_pair_k<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        attr_done = true;
     }
     long long total = ((p.Q + 255) / 256) * (p.Cout / BN);
     int clusters = kp_sm_count() / 2;
@@ -1325,10 +1323,9 @@ static int launch_conv_pair3(cudaStream_t st, const CUtensorMap& a, const CUtens
     constexpr int smem = AS * A3_SLOT + BS * (BN / 2) * 128 + 2 * SLAB_BYTES + (8 * 32 * 17 + 4 * 2 * BN) * 4 +
                          8 * (2 * AS + 2 * BS + 4) + 16 + 1024;
     static_assert(smem <= 227 * 1024, "shared memory budget");
-    static bool attr_done = false;
-    if (!attr_done) {
+    static KpOncePerDevice attr_done;
+    if (attr_done.first()) {
         KP_CUDA(cudaFuncSetAttribute(conv_tc_pair3_k<BN, AS, BS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        attr_done = true;
     }
     long long total = ((p.Q + 255) / 256) * (p.Cout / BN);
     int clusters = kp_sm_count() / 2;
@@ -1342,10 +1339,9 @@ static int launch_conv_pair3(cudaStream_t st, const CUtensorMap& a, const CUtens
 template <int BN, int STAGES>
 static int launch_wgrad_pair(cudaStream_t st, const CUtensorMap& a, const CUtensorMap& b, const WgradTcParams& p, int taps) {
     constexpr int smem = STAGES * (2 * 8192 + (BN / 128) * 8192) + 8 * (2 * STAGES + 4) + 16 + 1024;
-    static bool attr_done = false;
-    if (!attr_done) {
+    static KpOncePerDevice attr_done;
+    if (attr_done.first()) {
         KP_CUDA(cudaFuncSetAttribute(wgrad_tc_pair_k<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        attr_done = true;
     }
     long long total = (long long)(p.Mtot / 256) * (p.Ntot / BN) * taps * p.splits;
     int clusters = kp_sm_count() / 2;
@@ -1359,10 +1355,9 @@ static int launch_wgrad_pair(cudaStream_t st, const CUtensorMap& a, const CUtens
 template <int BN, int STAGES>
 static int launch_wgrad_persist(cudaStream_t st, const CUtensorMap& a, const CUtensorMap& b, const WgradTcParams& p, int taps) {
     constexpr int smem = STAGES * (2 * 8192 + (BN / 64) * 8192) + 8 * (2 * STAGES + 4) + 16 + 1024;
-    static bool attr_done = false;
-    if (!attr_done) {
+    static KpOncePerDevice attr_done;
+    if (attr_done.first()) {
         KP_CUDA(cudaFuncSetAttribute(wgrad_tc_persist_k<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        attr_done = true;
     }
     long long total = (long long)(p.Mtot / 128) * (p.Ntot / BN) * taps * p.splits;
     int grid = (int)(total < kp_sm_count() ? total : kp_sm_count());

@@ -15,6 +15,15 @@ __device__ __forceinline__ void sample_all_channels(const float* __restrict__ x,
     int x0 = (int)fx, y0 = (int)fy, x1 = x0 + 1, y1 = y0 + 1;
     float wx1 = ix - fx, wx0 = 1.f - wx1, wy1 = iy - fy, wy0 = 1.f - wy1;
     bool vx0 = x0 >= 0 && x0 < W, vx1 = x1 >= 0 && x1 < W, vy0 = y0 >= 0 && y0 < H, vy1 = y1 >= 0 && y1 < H;
+    if (x == nullptr) {       // constant-one source: the loss mask chain starts from P1(1) (data_augments.py:33)
+        float v = 0.f;
+        if (vy0 && vx0) v += wx0 * wy0;
+        if (vy0 && vx1) v += wx1 * wy0;
+        if (vy1 && vx0) v += wx0 * wy1;
+        if (vy1 && vx1) v += wx1 * wy1;
+        for (int c = 0; c < C; ++c) out[(((long long)n * C + c) * H + i) * W + j] = v;
+        return;
+    }
     for (int c = 0; c < C; ++c) {
         const float* pl = x + ((long long)n * C + c) * H * W;
         float v = 0.f;
@@ -98,11 +107,97 @@ __global__ void __launch_bounds__(256) rotate_warp_k(const float* __restrict__ x
     }
 }
 
+// Philox4x32-10 (Salmon et al. 2011), counter = (element, draw, step, 0), key = seed
+__device__ __forceinline__ uint4 philox4x32(uint4 c, uint2 k) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const unsigned hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
+        const unsigned hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
+        c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
+        k.x += 0x9E3779B9u; k.y += 0xBB67AE85u;
+    }
+    return c;
+}
+__device__ __forceinline__ float u01(unsigned r) { return (float)(r >> 8) * (1.0f / 16777216.0f); }     // [0,1)
+
+// one thread per (draw, image): theta ~ N(0, var^2) [T+3][2], ctrl ~ U[0,1) [T][2], rot ~ U(-max, max)
+__global__ void aug_draw_k(unsigned long long seed, const int* __restrict__ step_dev, int draws, int N, int T, float variance,
+                           float max_rotate, float* __restrict__ theta, float* __restrict__ ctrl, float* __restrict__ rot) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= draws * N) return;
+    const unsigned step = step_dev ? (unsigned)*step_dev : 0u;
+    const uint2 key = make_uint2((unsigned)seed, (unsigned)(seed >> 32));
+    unsigned blk = 0;
+    uint4 r = make_uint4(0, 0, 0, 0);
+    int have = 0;
+    auto next = [&]() -> unsigned {
+        if (have == 0) { r = philox4x32(make_uint4((unsigned)idx, blk++, step, 0x6b70u), key); have = 4; }
+        const unsigned v = have == 4 ? r.x : have == 3 ? r.y : have == 2 ? r.z : r.w;
+        --have;
+        return v;
+    };
+    float* th = theta + (long long)idx * (T + 3) * 2;
+    for (int e = 0; e < (T + 3) * 2; e += 2) {                     // Box-Muller pairs
+        const float u1 = 1.0f - u01(next()), u2 = u01(next());     // u1 in (0,1]
+        const float rad = sqrtf(-2.0f * logf(u1));
+        float s, c;
+        sincospif(2.0f * u2, &s, &c);
+        th[e] = rad * c * variance;
+        th[e + 1] = rad * s * variance;
+    }
+    float* ct = ctrl + (long long)idx * T * 2;
+    for (int e = 0; e < T * 2; ++e) ct[e] = u01(next());
+    rot[idx] = (2.0f * u01(next()) - 1.0f) * max_rotate;
+}
+
+// uint8 NHWC -> fp32 NCHW, out = in * scale + bias (ToTensor + Normalize on the device)
+__global__ void __launch_bounds__(256) u8_to_f32_k(const unsigned char* __restrict__ in, float* __restrict__ out, int N, int H,
+                                                   int W, int C, float scale, float bias) {
+    const long long total = (long long)N * C * H * W;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+         idx += (long long)gridDim.x * blockDim.x) {
+        const int x = (int)(idx % W);
+        long long r = idx / W;
+        const int y = (int)(r % H);
+        r /= H;
+        const int c = (int)(r % C);
+        const long long n = r / C;
+        out[idx] = fmaf((float)in[((n * H + y) * W + x) * C + c], scale, bias);
+    }
+}
+
 }  // namespace
+
+extern "C" int kp_u8_to_f32(kp_stream stream, const uint8_t* in, float* out, int N, int H, int W, int C, float scale,
+                            float bias) {
+    KP_CHECK_ARG(in && out && N > 0 && H > 0 && W > 0 && C > 0, "kp_u8_to_f32: bad arguments");
+    long long total = (long long)N * C * H * W;
+    long long g = (total + 255) / 256;
+    if (g > (long long)kp_sm_count() * 16) g = (long long)kp_sm_count() * 16;
+    u8_to_f32_k<<<(int)g, 256, 0, (cudaStream_t)stream>>>(in, out, N, H, W, C, scale, bias);
+    KP_LAUNCH_CHECK();
+    return KP_OK;
+}
+
+extern "C" int kp_aug_draw(kp_stream stream, uint64_t seed, const int32_t* step_dev, int draws, int N, int T, float variance,
+                           float max_rotate, float* theta, float* ctrl, float* rot) {
+    KP_CHECK_ARG(theta && ctrl && rot && draws > 0 && N > 0 && T > 0 && T <= MAX_T, "kp_aug_draw: bad arguments");
+    const int total = draws * N;
+    aug_draw_k<<<(total + 127) / 128, 128, 0, (cudaStream_t)stream>>>(seed, step_dev, draws, N, T, variance, max_rotate, theta,
+                                                                       ctrl, rot);
+    KP_LAUNCH_CHECK();
+    return KP_OK;
+}
+
+extern "C" int kp_zero(kp_stream stream, void* ptr, int64_t bytes) {
+    KP_CHECK_ARG(ptr && bytes >= 0, "kp_zero: bad arguments");
+    if (bytes) KP_CUDA(cudaMemsetAsync(ptr, 0, (size_t)bytes, (cudaStream_t)stream));
+    return KP_OK;
+}
 
 extern "C" int kp_tps_warp(kp_stream stream, const float* x, float* out, const float* theta, const float* ctrl, int N,
                            int C, int H, int W, int T, int reduced) {
-    KP_CHECK_ARG(x && out && theta && ctrl && x != out && N > 0 && C > 0 && H > 0 && W > 0 && T > 0 && T <= MAX_T &&
+    KP_CHECK_ARG(out && theta && ctrl && x != out && N > 0 && C > 0 && H > 0 && W > 0 && T > 0 && T <= MAX_T &&
                      (!reduced || T >= 2),
                  "kp_tps_warp: bad arguments");
     long long total = (long long)N * H * W;
@@ -115,7 +210,7 @@ extern "C" int kp_tps_warp(kp_stream stream, const float* x, float* out, const f
 
 extern "C" int kp_rotate_warp(kp_stream stream, const float* x, float* out, const float* rot, int N, int C, int H,
                               int W) {
-    KP_CHECK_ARG(x && out && rot && x != out && N > 0 && C > 0 && H > 0 && W > 0, "kp_rotate_warp: bad arguments");
+    KP_CHECK_ARG(out && rot && x != out && N > 0 && C > 0 && H > 0 && W > 0, "kp_rotate_warp: bad arguments");
     long long total = (long long)N * H * W;
     long long g = (total + 255) / 256;
     if (g > (long long)kp_sm_count() * 16) g = (long long)kp_sm_count() * 16;

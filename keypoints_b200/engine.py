@@ -191,7 +191,7 @@ def unit_forward(specs: List[ConvSpec], params: List[LayerParams], x_pad: torch.
     nstat = sum(2 * s.cout for s in specs if s.bn)
     stats_all = alloc(f'{tag}.stats', (max(nstat, 1),), torch.float64, dev)
     if nstat and training:
-        stats_all.zero_()
+        L.zero(stats_all)
     soff = 0
     cur, h, w = x_pad, H, W
     ctxs: List[LayerCtx] = []
@@ -250,17 +250,20 @@ def unit_forward(specs: List[ConvSpec], params: List[LayerParams], x_pad: torch.
 
 def unit_backward(specs: List[ConvSpec], params: List[LayerParams], grads: List[LayerGrads], ctxs: List[LayerCtx],
                   dout: torch.Tensor, dout_pad: int, precision: str, need_dx: bool,
-                  alloc: Callable = default_alloc, tag: str = 'u', defer_stg: Optional[List] = None) -> Optional[torch.Tensor]:
+                  alloc: Callable = default_alloc, tag: str = 'u', defer_stg: Optional[List] = None,
+                  after_wgrad: Optional[Callable] = None) -> Optional[torch.Tensor]:
     """Backward of one Unit.  ``dout``: gradient w.r.t. the last activation, indexed [n,y,x,c] (ptr at the
     padded origin when dout_pad=1).  Weight gradients are ACCUMULATED into ``grads`` (zero them per step);
-    BatchNorm / bias gradients are overwritten.  Returns d(padded input) [N][H+2][W+2][Cp] or None."""
+    BatchNorm / bias gradients are overwritten.  ``after_wgrad(i)`` (optional) is called once every gradient of layer i
+    (weight, bias, BatchNorm affine) has been issued on the current stream — the fused trainer starts the bucket-wise
+    gradient all-reduce from it.  Returns d(padded input) [N][H+2][W+2][Cp] or None."""
     dev = ctxs[0].x.device
     N = ctxs[0].x.shape[0]
     T = act_dtype(precision)
     st = L.stream()
     nsum = sum(2 * s.cout for s in specs)
     sums_all = alloc(f'{tag}.sums', (nsum,), torch.float64, dev)
-    sums_all.zero_()
+    L.zero(sums_all)
     soff = 0
     dx = None
     for i in range(len(specs) - 1, -1, -1):
@@ -314,6 +317,8 @@ def unit_backward(specs: List[ConvSpec], params: List[LayerParams], grads: List[
             else:
                 L.call('kp_conv_wgrad_tc', st, L.ptr(c.x), L.ptr(dyp), Q, s.cin, cinp, s.cout, len(sh), L.shifts_array(sh),
                        L.ptr(stg), dw_ptr, flops=2.0 * N * h * w * s.cin * s.cout * s.k * s.k, tag=f'{tag}{i} {s.cin}->{s.cout}@{h}x{w} k{s.k}')
+            if after_wgrad is not None:
+                after_wgrad(i)
             if want_dx:
                 dx = alloc(f'{tag}.dx{i}', (N, PH, PW, cinp), T, dev)
                 L.call('kp_conv_tc', st, L.ptr(dyp), Q, s.cout, L.ptr(c.pack['tc_d']), len(sh), L.shifts_array(sh), None,
@@ -322,6 +327,8 @@ def unit_backward(specs: List[ConvSpec], params: List[LayerParams], grads: List[
             src = c.x if s.k == 3 else c.x[:, 1:, 1:, :]
             L.call('kp_conv_wgrad_simt', st, L.view(src), L.view(dy_int), L.ptr(g.dw), N, h, w, s.cin, s.cout, s.k,
                    tag=f'{tag}{i} {s.cin}->{s.cout}@{h}x{w} k{s.k}')
+            if after_wgrad is not None:
+                after_wgrad(i)
             if want_dx:
                 dx = alloc(f'{tag}.dx{i}', (N, PH, PW, cinp), T, dev, zero=s.k == 1)
                 if s.k == 3:

@@ -64,6 +64,10 @@ SIGNATURES = {
     'kp_l2_loss': [_P, _P, _P, _P, _L, _F, _P, _P],
     'kp_tps_warp': [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I],
     'kp_rotate_warp': [_P, _P, _P, _P, _I, _I, _I, _I],
+    'kp_aug_draw': [_P, C.c_uint64, _P, _I, _I, _I, _F, _F, _P, _P, _P],
+    'kp_zero': [_P, _P, _L],
+    'kp_u8_to_f32': [_P, _P, _P, _I, _I, _I, _I, _F, _F],
+    'kp_loss_ring_push': [_P, _P, _D, _P, _P, _I],
     'kp_adam_step': [_P, _P, _P, _P, _P, _L, _D, _D, _D, _D, _I, _F, _P],
 }
 EXPORTS = sorted(list(SIGNATURES) + ['kp_last_error', 'kp_version'])
@@ -95,7 +99,7 @@ def load():
 timing = None         # when a list: (name, flops, start_event, end_event) per call (bench.py roofline leg)
 
 
-def call(name, *args, flops=0.0, tag=''):
+def call(name, *args, flops=0.0, tag='', count=True):
     global launches
     lib = load()
     if timing is not None:
@@ -107,7 +111,13 @@ def call(name, *args, flops=0.0, tag=''):
     if timing is not None:
         e1.record()
         timing.append((name, flops, e0, e1, tag))
-    launches += 1
+    if count:
+        launches += 1
+
+
+def zero(t):
+    """Zero a contiguous tensor with a memset node on the current stream (no ATen fill kernel inside the step)."""
+    call('kp_zero', stream(), ptr(t), t.numel() * t.element_size(), count=False)
 
 
 def device_info():

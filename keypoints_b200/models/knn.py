@@ -218,7 +218,9 @@ class Unit(nn.Module):
         for name, block in self._blocks().items():
             path = Path(f'{directory}/{name}.mdl')
             path.parent.mkdir(parents=True, exist_ok=True)
-            torch.save(block.state_dict(), str(path))
+            # detached copies: a parameter that aliases the fused trainer's flat bucket would otherwise drag the whole
+            # bucket's storage into every file (torch.save serialises the underlying storage of a view)
+            torch.save({k: v.detach().clone() for k, v in block.state_dict().items()}, str(path))
 
     def load(self, directory, in_block=True, core=True, out_block=True, map_device=None):
         wanted = {'in_block': in_block, 'core': core, 'out_block': out_block}

@@ -5,7 +5,10 @@ ops on CPU tensors, fp32 or fp64) of the reference algorithm.  It is the
 checker for the CUDA path, never the thing measured or shipped: only
 ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s ``cpu_baseline`` /
 ``--impl reference`` legs may import it.  Nothing under ``keypoints_b200/``
-imports it.
+imports it.  The functions follow their inputs' device (linspace rulers are computed on
+the CPU exactly as the reference does, then moved), so ``bench.py``'s
+``gpu_eager_baseline`` leg can also run this same graph in torch eager on cuda:0 —
+the reference's own GPU execution, the "kernel to beat" (SURVEY 8d).
 
 Parity pinning: the reference's own test-suite holds no golden vectors for this
 path, so the oracle is pinned against fixtures generated
@@ -130,8 +133,8 @@ def spatial_logsoftmax(heat: torch.Tensor) -> Tuple[torch.Tensor, Tuple[torch.Te
     n, k, h, w = heat.shape
     logp_h = F.log_softmax(heat.mean(dim=3), dim=2)
     logp_w = F.log_softmax(heat.mean(dim=2), dim=2)
-    ruler_h = torch.log(torch.linspace(0, 1, h)).to(heat.dtype)
-    ruler_w = torch.log(torch.linspace(0, 1, w)).to(heat.dtype)
+    ruler_h = torch.log(torch.linspace(0, 1, h)).to(heat)
+    ruler_w = torch.log(torch.linspace(0, 1, w)).to(heat)
     ky = torch.exp(logp_h + ruler_h).sum(dim=2)
     kx = torch.exp(logp_w + ruler_w).sum(dim=2)
     return torch.stack((ky, kx), dim=2), (torch.exp(logp_h), torch.exp(logp_w))
@@ -142,15 +145,15 @@ def spatial_softmax(heat: torch.Tensor) -> Tuple[torch.Tensor, Tuple[torch.Tenso
     n, k, h, w = heat.shape
     p_h = F.softmax(heat.mean(dim=3), dim=2)
     p_w = F.softmax(heat.mean(dim=2), dim=2)
-    ky = (p_h * torch.linspace(0, 1, h).to(heat.dtype)).sum(dim=2)
-    kx = (p_w * torch.linspace(0, 1, w).to(heat.dtype)).sum(dim=2)
+    ky = (p_h * torch.linspace(0, 1, h).to(heat)).sum(dim=2)
+    kx = (p_w * torch.linspace(0, 1, w).to(heat)).sum(dim=2)
     return torch.stack((ky, kx), dim=2), (p_h, p_w)
 
 
 def gaussian_like(kp: torch.Tensor, height: int, width: int, sigma: float = 0.1, eps: float = 1e-6) -> torch.Tensor:
     """``gaussian_like_function`` (functional.py:56-63): exp(-sqrt(dy^2+dx^2+eps)/(2 sigma^2))."""
-    ys = torch.linspace(0, 1, height).to(kp.dtype).view(1, 1, height, 1)
-    xs = torch.linspace(0, 1, width).to(kp.dtype).view(1, 1, 1, width)
+    ys = torch.linspace(0, 1, height).to(kp).view(1, 1, height, 1)
+    xs = torch.linspace(0, 1, width).to(kp).view(1, 1, 1, width)
     dy2 = (ys - kp[:, :, 0, None, None]) ** 2
     dx2 = (xs - kp[:, :, 1, None, None]) ** 2
     return torch.exp(-torch.sqrt(dy2 + dx2 + eps) / (2 * sigma ** 2))
@@ -288,8 +291,8 @@ def tps_grid(theta: torch.Tensor, ctrl: torch.Tensor, size: Tuple[int, int, int,
     U(d) = d^2 log(d + 1e-6); returns ((x,y) + z) * 2 - 1 as an (N,H,W,2) sampling grid.
     """
     N, _, H, W = size
-    xs = torch.linspace(0, 1, W).to(theta.dtype)
-    ys = torch.linspace(0, 1, H).to(theta.dtype)
+    xs = torch.linspace(0, 1, W).to(theta)
+    ys = torch.linspace(0, 1, H).to(theta)
     gx = xs.view(1, 1, W).expand(N, H, W)
     gy = ys.view(1, H, 1).expand(N, H, W)
     if ctrl.dim() == 2:
@@ -318,7 +321,7 @@ def tps_transform(x, theta, ctrl):
 def rotate_affine_grid_multi(x, theta):
     """``rotate_affine_grid_multi`` (tps.py:154-166)."""
     c, s = torch.cos(theta), torch.sin(theta)
-    A = torch.zeros(x.shape[0], 2, 3, dtype=x.dtype)
+    A = torch.zeros(x.shape[0], 2, 3, dtype=x.dtype, device=x.device)
     A[:, 0, 0], A[:, 0, 1], A[:, 1, 0], A[:, 1, 1] = c, s, -s, c
     grid = F.affine_grid(A, list(x.shape), align_corners=False)
     return F.grid_sample(x, grid, mode='bilinear', padding_mode='zeros', align_corners=False)

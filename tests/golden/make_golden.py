@@ -45,16 +45,8 @@ def npy(t):
     return t.detach().cpu().numpy()
 
 
-def synth_images(rng, n, c, h, w, lo=0.0, hi=1.0):
-    """Smooth noise + bright rectangles (SURVEY 8d synthetic inputs), numpy stream."""
-    base = torch.from_numpy(rng.random((n, c, max(h // 8, 2), max(w // 8, 2))).astype('float32'))
-    x = torch.nn.functional.interpolate(base, size=(h, w), mode='bilinear', align_corners=False)
-    for i in range(n):
-        for _ in range(3):
-            y0, x0 = int(rng.integers(0, h - 4)), int(rng.integers(0, w - 4))
-            hh, ww = int(rng.integers(2, max(h // 4, 3))), int(rng.integers(2, max(w // 4, 3)))
-            x[i, :, y0:y0 + hh, x0:x0 + ww] = torch.from_numpy(rng.random(c).astype('float32')).view(c, 1, 1) * 0.5 + 0.5
-    return (x * (hi - lo) + lo).contiguous()
+sys.path.insert(0, HERE)
+from synth import synth_images, sample  # noqa: E402  (shared with the tests: the full-size fixtures regenerate their inputs)
 
 
 def grad_summary(out, name, g):
@@ -261,8 +253,59 @@ def model_fixture(name, kind, model_type, cin, z, K, n, h, w, seed, lo, hi, with
     print(name, 'loss', float(loss), 'bytes', os.path.getsize(os.path.join(HERE, f'{name}.npz')))
 
 
+def full_size_fixture(name, kind, model_type, cin, z, K, n, h, w, seed):
+    """BASELINE configs 4 / 5 at their real shapes (Transporter F 128x128 K=30; KeyNet F 256x256 K=64), batch 2, fp32.
+    Inputs and weights regenerate from the seed (tests/golden/synth.py, oracle.init_state_dict), so the fixture holds
+    only the reference's outputs: small tensors in full, large ones as a strided sample (synth.sample)."""
+    torch.set_num_threads(8)                      # fp32 CPU convs; thread count does not change ATen's conv arithmetic order
+    rng = np.random.default_rng(seed)
+    if kind == 'transporter':
+        net = ref_transporter.make(model_type, cin, z, K, combine_mode='max')
+        ops = O.transporter_ops(model_type, cin, z, K)
+    else:
+        net = build_ref_keynet(model_type, cin, z, K)
+        ops = O.keynet_ops(model_type, cin, z, K)
+    net.load_state_dict(O.init_state_dict(ops, seed), strict=True)
+    a = synth_images(rng, n, cin, h, w, 0.0, 1.0)
+    b = synth_images(rng, n, cin, h, w, 0.0, 1.0)
+    mask = (torch.from_numpy(rng.random((n, cin, h, w)).astype('float32')) > 0.2).float()
+    out = {'meta': np.array([cin, z, K, n, h, w, seed]),
+           'in/check': np.array([float(a.double().sum()), float(b.double().sum()), float(mask.double().sum())])}
+    optim = torch.optim.Adam(net.parameters(), lr=1e-4)
+    optim.zero_grad()
+    res = net(a, b)
+    loss = ((res[0] - b) ** 2 * mask).mean()
+    loss.backward()
+    names = ['x_hat', 'phi', 'k', 'm', 'p', 'heat', 'mask_s', 'mask_t'] if kind == 'transporter' else \
+            ['x_hat', 'z', 'k', 'm', 'p', 'heat']
+    for nm, r in zip(names, res):
+        if nm == 'p':
+            out['out/p_h'], out['out/p_w'] = npy(r[0]), npy(r[1])
+        elif nm == 'k':
+            out['out/k'] = npy(r)
+        else:
+            out[f'outsample/{nm}'] = sample(npy(r))
+            out[f'outmax/{nm}'] = np.array(float(r.detach().abs().max()))
+    out['loss'] = npy(loss)
+    for pname, p in net.named_parameters():
+        grad_summary(out, pname, p.grad)
+        out[f'gradmax/{pname}'] = np.array(float(p.grad.abs().max()))
+    new_sd = net.state_dict()
+    for key in new_sd:
+        if 'running_' in key or 'num_batches' in key:
+            out[f'stat/{key}'] = npy(new_sd[key])
+    np.savez_compressed(os.path.join(HERE, f'{name}.npz'), **out)
+    print(name, 'loss', float(loss), 'bytes', os.path.getsize(os.path.join(HERE, f'{name}.npz')))
+    torch.set_num_threads(1)
+
+
 if __name__ == '__main__':
-    only = sys.argv[1:]          # e.g. `make_golden.py modes` regenerates only the SURVEY 8f fixtures
+    only = sys.argv[1:]
+    if 'full' in only:           # `make_golden.py full`: only the full-size config 4 / 5 fixtures
+        full_size_fixture('transporter_F_128_K30', 'transporter', 'F', 3, 64, 30, 2, 128, 128, 109)
+        full_size_fixture('keynet_F_256_K64', 'keynet', 'F', 3, 64, 64, 2, 256, 256, 110)
+        print('done')
+        sys.exit(0)          # e.g. `make_golden.py modes` regenerates only the SURVEY 8f fixtures
     if only:
         known_answers = functional_fixture = tps_fixture = lambda: None
         _mf = model_fixture
@@ -287,4 +330,7 @@ if __name__ == '__main__':
                       with_mask=False, combine_mode='sum_and_clamp')
         autoencoder_fixture('autoencoder_pong', 'VGG_PONG', 1, 8, 3, 24, 16, 107, -1.0, 1.0)
         eval_fixture('transporter_pong_eval', 'VGG_PONG', 1, 8, 3, 32, 24, 108)
+    if not only:
+        full_size_fixture('transporter_F_128_K30', 'transporter', 'F', 3, 64, 30, 2, 128, 128, 109)
+        full_size_fixture('keynet_F_256_K64', 'keynet', 'F', 3, 64, 64, 2, 256, 256, 110)
     print('done')

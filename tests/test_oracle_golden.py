@@ -127,6 +127,50 @@ def test_model_step(golden, name, kind, model_type):
                 close(sd[key[5:]], g[key], 0.02, key, scale=1e-4)      # within 2 % of one lr-sized step
 
 
+FULL = [('transporter_F_128_K30', 'transporter', 'F'), ('keynet_F_256_K64', 'keynet', 'F')]
+
+
+@pytest.mark.parametrize('name,kind,model_type', FULL)
+def test_model_step_full_size(golden, name, kind, model_type):
+    """BASELINE configs 4 / 5 at their real shapes (Transporter F 128x128 K=30, KeyNet F 256x256 K=64; batch 2): the oracle
+    against the reference's outputs; inputs and weights regenerate from the fixture's seed."""
+    import os, sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden'))
+    from synth import full_size_inputs, sample_like
+    torch.set_num_threads(min(8, os.cpu_count() or 1))
+    try:
+        g = golden(name)
+        cin, z, K, n, h, w, seed = (int(v) for v in g['meta'])
+        a, b, mask = full_size_inputs(g['meta'])
+        close(np.array([float(a.double().sum()), float(b.double().sum()), float(mask.double().sum())]), g['in/check'], 1e-9, 'inputs')
+        ops = O.transporter_ops(model_type, cin, z, K) if kind == 'transporter' else O.keynet_ops(model_type, cin, z, K)
+        sd = O.init_state_dict(ops, seed)
+        tr = O.OracleTrainer(kind, model_type, cin, z, K, sd)
+        loss, out = tr.step(a, b, mask)
+        names = ['x_hat', 'phi', 'k', 'm', 'p', 'heat', 'mask_s', 'mask_t'] if kind == 'transporter' else \
+                ['x_hat', 'z', 'k', 'm', 'p', 'heat']
+        tol = 5e-5        # multi-threaded fp32 convolutions may reduce in another order than the fixture's run
+        for nm, r in zip(names, out):
+            if nm == 'p':
+                close(r[0], g['out/p_h'], tol, 'p_h'); close(r[1], g['out/p_w'], tol, 'p_w')
+            elif nm == 'k':
+                close(r, g['out/k'], tol, 'k')
+            else:
+                ref = g[f'outsample/{nm}']
+                close(sample_like(r.detach().numpy(), len(ref)), ref, tol, nm, scale=float(g[f'outmax/{nm}']))
+        close(loss, g['loss'], tol, 'loss')
+        for key in g:
+            if key.startswith('grad/'):
+                sib = bn_sibling(key, g)
+                close(sd[key[5:]].grad, g[key], 5e-3, key, scale=float(g['gradmax/' + (sib or key)[5:]]))
+            elif key.startswith('gradsample/'):
+                close(sd[key[11:]].grad.reshape(-1)[::997], g[key], 5e-3, key, scale=float(g['gradmax/' + key[11:]]))
+            elif key.startswith('stat/'):
+                close(sd[key[5:]], g[key], tol, key)
+    finally:
+        torch.set_num_threads(1)
+
+
 # ---- SURVEY 8f widening: non-default combine modes, auto-encoder pre-training, checkpoint transfer ----------------
 def _check_step(g, sd, loss, outs, names, tol=2e-5):
     for nm, r in zip(names, outs):
