@@ -538,6 +538,21 @@ class Trainer:
         self.calls_per_step = L.launches - before
         self.graph_key = key
 
+    def _snapshot(self):
+        bufs = [b for _, bn in self._all_mods() if bn is not None for b in (bn.running_mean, bn.running_var, bn.num_batches_tracked)]
+        return ([t.clone() for t in (self.flat_p, self.flat_m, self.flat_v, self.step_dev)], [(b, b.clone()) for b in bufs])
+
+    def _restore(self, state):
+        flats, bufs = state
+        for dst, src in zip((self.flat_p, self.flat_m, self.flat_v, self.step_dev), flats):
+            dst.copy_(src)
+        for b, saved in bufs:
+            b.copy_(saved)
+
+    def _all_mods(self):
+        for u in self.units.values():
+            yield from u.mods
+
     # ------------------------------------------------------------------------------------------
     def loss(self) -> float:
         """Mean masked L2 loss of the last step (device -> host read)."""
