@@ -431,6 +431,7 @@ class Run:
 
     def close(self):
         import torch
+        self.tr.close()                        # the captured NCCL collectives must be gone before the process group is
         del self.tr
         torch.cuda.empty_cache()
 

@@ -538,6 +538,15 @@ class Trainer:
         self.calls_per_step = L.launches - before
         self.graph_key = key
 
+    def close(self):
+        """Drop the captured graph.  Data parallel: call before ``destroy_process_group`` — NCCL cannot tear down a
+        communicator while a live CUDA graph still holds its captured collectives (the destroy blocks forever)."""
+        import gc
+        torch.cuda.synchronize(self.device)
+        self.graph = None
+        self.graph_key = None
+        gc.collect()
+
     def _snapshot(self):
         bufs = [b for _, bn in self._all_mods() if bn is not None for b in (bn.running_mean, bn.running_var, bn.num_batches_tracked)]
         return ([t.clone() for t in (self.flat_p, self.flat_m, self.flat_v, self.step_dev)], [(b, b.clone()) for b in bufs])

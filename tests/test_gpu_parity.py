@@ -494,12 +494,12 @@ def _ddp_worker(rank, world, port, out, use_graph):
     tr3 = Trainer(keynet.build('F', 3, 64, 10), precision='bf16', use_graph=False, device=dev,
                   augment=dict(cntl_pts=4, variance=0.05, max_rotate=0.1))
     tr3.flat_p.copy_(p_start)
-    for (_, b1), (_, b2) in zip(tr2.net.named_buffers(), tr3.net.named_buffers()):
-        pass
     tr3.step(x)
     torch.cuda.synchronize()
     err = float((tr3.flat_g - total).abs().max() / total.abs().max())
     out[rank] = (err, tr.flat_p.cpu(), p_start.cpu(), losses, tr.aug_seed, getattr(tr, 'calls_per_step', None))
+    for t in (tr, tr2, tr3):
+        t.close()                                  # graphs holding captured collectives must go before the communicator
     dist.destroy_process_group()
 
 
