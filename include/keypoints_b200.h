@@ -253,6 +253,28 @@ int kp_adam_step(kp_stream stream, float* p, const float* g, float* m, float* v,
                  double lr, double beta1, double beta2, double eps, int step, float grad_scale,
                  int32_t* step_dev);
 
+/* Data-parallel optimiser step over NVLink peer memory (the reference has no distributed code).
+ * Gradient reduce-scatter + Adam + parameter all-gather in one kernel: rank r owns elements
+ * [r*ceil(n/4/world)*4, ...) of the flat bucket, sums that slice of every replica's gradient buffer (peer loads, or
+ * multimem.ld_reduce through the NVSwitch when use_multicast), updates its slice of m / v (Adam, same arithmetic as
+ * kp_adam_step with the device step counter) and writes the new parameters into EVERY replica's buffer (peer stores /
+ * multimem.st).  peers->g[j], p[j]: replica j's gradient / parameter buffers mapped into this process (symmetric
+ * memory); flag[j]: replica j's int32[KP_DP_MAX_WORLD] barrier flags (zero-initialised); mc_g / mc_p: multicast
+ * addresses of the two buffers (NULL without NVLS).  epoch_dev: device int32 barrier epoch (starts at 0, advanced by
+ * the call; every replica must make the same sequence of calls).  Bracketed by two flag barriers, so on return (in
+ * stream order) all replicas hold identical parameters and the gradient buffers may be overwritten. */
+#define KP_DP_MAX_WORLD 8
+typedef struct kp_dp_peers {
+    float*   g[KP_DP_MAX_WORLD];
+    float*   p[KP_DP_MAX_WORLD];
+    int32_t* flag[KP_DP_MAX_WORLD];
+    float*   mc_g;
+    float*   mc_p;
+} kp_dp_peers;
+int kp_dp_adam_step(kp_stream stream, const kp_dp_peers* peers, int rank, int world, int64_t n, float* m, float* v,
+                    double lr, double beta1, double beta2, double eps, float grad_scale, int32_t* step_dev,
+                    int32_t* epoch_dev, int use_multicast);
+
 /* Non-blocking loss log (replaces the per-step `loss.item()` host sync of ResultsLogger.log, utils.py:122-130):
  * ring[2*(s % slots)] = s, ring[2*(s % slots)+1] = *loss_sum * scale with s = *step_dev (0 if NULL); ring is
  * double[2*slots] in device memory.  The host copies the ring back every k steps on a side stream and reads the

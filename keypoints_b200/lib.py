@@ -31,6 +31,14 @@ class KpView(C.Structure):
                 ('dtype', C.c_int32), ('_pad', C.c_int32)]
 
 
+DP_MAX_WORLD = 8
+
+
+class KpDpPeers(C.Structure):
+    _fields_ = [('g', C.c_void_p * DP_MAX_WORLD), ('p', C.c_void_p * DP_MAX_WORLD), ('flag', C.c_void_p * DP_MAX_WORLD),
+                ('mc_g', C.c_void_p), ('mc_p', C.c_void_p)]
+
+
 _P = C.c_void_p
 _VP = C.POINTER(KpView)
 _I, _L, _F, _D = C.c_int, C.c_int64, C.c_float, C.c_double
@@ -68,6 +76,7 @@ SIGNATURES = {
     'kp_zero': [_P, _P, _L],
     'kp_u8_to_f32': [_P, _P, _P, _I, _I, _I, _I, _F, _F],
     'kp_loss_ring_push': [_P, _P, _D, _P, _P, _I],
+    'kp_dp_adam_step': [_P, C.POINTER(KpDpPeers), _I, _I, _L, _P, _P, _D, _D, _D, _D, _F, _P, _P, _I],
     'kp_adam_step': [_P, _P, _P, _P, _P, _L, _D, _D, _D, _D, _I, _F, _P],
 }
 EXPORTS = sorted(list(SIGNATURES) + ['kp_last_error', 'kp_version'])

@@ -50,3 +50,44 @@ def allreduce_buckets(flat: torch.Tensor, spans: Sequence[Tuple[int, int]], grou
 def wait_all(works) -> None:
     for w in works:
         w.wait()
+
+
+class PeerBuckets:
+    """The flat parameter and gradient buckets of a replica in SYMMETRIC memory (every replica's buffers mapped into every
+    process over NVLink; torch.distributed._symmetric_memory does the handle exchange) plus the barrier flags, and the
+    peer-pointer table ``kp_dp_adam_step`` takes.  Raises if the GPUs cannot map each other's memory."""
+
+    def __init__(self, n: int, device, group=None):
+        import torch.distributed._symmetric_memory as symm
+        from . import lib as L
+        group = group if group is not None else dist.group.WORLD
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        if self.world > L.DP_MAX_WORLD:
+            raise RuntimeError(f'peer-memory data parallelism supports up to {L.DP_MAX_WORLD} replicas')
+        try:
+            symm.enable_symm_mem_for_group(group.group_name)
+        except Exception:
+            pass                                  # newer torch enables groups implicitly
+        self.p = symm.empty(n, dtype=torch.float32, device=device)
+        self.g = symm.empty(n, dtype=torch.float32, device=device)
+        self.flags = symm.empty(64, dtype=torch.int32, device=device)
+        for t in (self.p, self.g, self.flags):
+            t.zero_()
+        self.handles = [symm.rendezvous(t, group=group) for t in (self.p, self.g, self.flags)]
+        hp, hg, hf = self.handles
+        self.peers = L.KpDpPeers()
+        for j in range(self.world):
+            self.peers.p[j], self.peers.g[j], self.peers.flag[j] = hp.buffer_ptrs[j], hg.buffer_ptrs[j], hf.buffer_ptrs[j]
+        self.multicast = bool(getattr(hp, 'has_multicast_support', False) and getattr(hg, 'has_multicast_support', False)
+                              and os.environ.get('KP_DP_MULTICAST', '1') != '0')
+        if self.multicast:
+            self.peers.mc_p, self.peers.mc_g = hp.multicast_ptr, hg.multicast_ptr
+        self.epoch = torch.zeros(1, dtype=torch.int32, device=device)
+        torch.cuda.synchronize(device)
+        dist.barrier(group=group)                 # every replica's flags are zero before anyone signals
+
+    def owned(self, n: int) -> Tuple[int, int]:
+        """Element range of the flat bucket whose Adam moments this rank holds (kp_dp_adam_step's slice)."""
+        n4 = n // 4
+        chunk4 = (n4 + self.world - 1) // self.world
+        return min(self.rank * chunk4, n4) * 4, min((self.rank + 1) * chunk4, n4) * 4

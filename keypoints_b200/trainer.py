@@ -86,6 +86,10 @@ class Trainer:
         elif process_group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()):
             self.world = torch.distributed.get_world_size(process_group)
         self.rank = torch.distributed.get_rank(self.pg) if self.world > 1 else 0
+        # gradient exchange: 'p2p' = reduce-scatter + Adam + all-gather fused in one kernel over NVLink peer memory
+        # (kp_dp_adam_step); 'nccl' = bucket-wise NCCL all-reduce overlapped with backward + replicated Adam
+        self.dp_mode = os.environ.get('KP_DP', 'p2p') if self.world > 1 else 'none'
+        self.peer = None
         # augmentation stream: base seed + rank, so the shards of a data-parallel job draw different perturbations
         self.aug_seed = (int(seed) * 1000003 + self.rank) & 0xFFFFFFFFFFFFFFFF
         first = net.feature if self.kind == 'transporter' else net.encoder
@@ -154,8 +158,23 @@ class Trainer:
                     off += (t.numel() + ALIGN - 1) // ALIGN * ALIGN
             u.span = (start, off)
         n = off
-        self.flat_p = torch.zeros(n, dtype=torch.float32, device=self.device)
-        self.flat_g = torch.zeros(n, dtype=torch.float32, device=self.device)
+        if self.dp_mode == 'p2p':
+            try:
+                self.peer = parallel.PeerBuckets(n, self.device, self.pg)
+            except Exception as e:                # no peer mapping between these GPUs: NCCL carries the gradients instead
+                import warnings
+                warnings.warn(f'keypoints_b200: peer-memory data parallelism unavailable ({type(e).__name__}: {e}); using NCCL')
+                self.dp_mode = 'nccl'
+            if self.world > 1:                    # all replicas must agree on the mode
+                ok = torch.tensor([1 if self.dp_mode == 'p2p' else 0], device=self.device)
+                torch.distributed.all_reduce(ok, op=torch.distributed.ReduceOp.MIN, group=self.pg)
+                if int(ok.item()) == 0:
+                    self.dp_mode, self.peer = 'nccl', None
+        if self.peer is not None:
+            self.flat_p, self.flat_g = self.peer.p, self.peer.g
+        else:
+            self.flat_p = torch.zeros(n, dtype=torch.float32, device=self.device)
+            self.flat_g = torch.zeros(n, dtype=torch.float32, device=self.device)
         self.flat_m = torch.zeros(n, dtype=torch.float32, device=self.device)
         self.flat_v = torch.zeros(n, dtype=torch.float32, device=self.device)
         gviews = {}
@@ -419,7 +438,7 @@ class Trainer:
                                     alloc=u.alloc, tag='b', defer_stg=self._stg.get(u.name), after_wgrad=hook)
 
     def _buckets(self):
-        if self.world == 1 or not self.overlap_allreduce:
+        if self.world == 1 or not self.overlap_allreduce or self.dp_mode != 'nccl':
             return None
         if getattr(self, '_bucket_plan', None) is None:
             plan = {}
@@ -461,7 +480,7 @@ class Trainer:
     def _allreduce(self):
         """Join the bucket all-reduces issued during backward (or, without overlap, run them now): NCCL over
         NVLink/NVSwitch on the GPUs."""
-        if self.world == 1:
+        if self.world == 1 or self.dp_mode != 'nccl':
             return
         if self._buckets() is None:
             self._works += parallel.allreduce_buckets(self.flat_g, [u.span for u in self.units.values()], self.pg)
@@ -472,14 +491,41 @@ class Trainer:
         L.call('kp_adam_step', L.stream(), L.ptr(self.flat_p), L.ptr(self.flat_g), L.ptr(self.flat_m), L.ptr(self.flat_v),
                self.n_params, self.lr, self.betas[0], self.betas[1], self.eps, 0, 1.0 / self.world, L.ptr(self.step_dev))
 
+    def _dp_adam(self):
+        """Gradient reduce-scatter + Adam + parameter all-gather over NVLink peer memory, one fused kernel between two flag
+        barriers (csrc/kp_dp.cu); replaces `_allreduce` + `_adam` when the replicas can map each other's buffers."""
+        import ctypes
+        pb = self.peer
+        L.call('kp_dp_adam_step', L.stream(), ctypes.byref(pb.peers), pb.rank, pb.world, self.n_params, L.ptr(self.flat_m),
+               L.ptr(self.flat_v), self.lr, self.betas[0], self.betas[1], self.eps, 1.0 / self.world, L.ptr(self.step_dev),
+               L.ptr(pb.epoch), 1 if pb.multicast else 0)
+
+    def _full_moments(self):
+        """Adam moments of the whole bucket.  In 'p2p' mode every rank only holds (and updates) its own slice; the rest of
+        its buffers is whatever was loaded / broadcast, so the slices are summed over the replicas (collective: every rank
+        must call)."""
+        if self.peer is None:
+            return self.flat_m, self.flat_v
+        lo, hi = self.peer.owned(self.n_params)
+        out = []
+        for t in (self.flat_m, self.flat_v):
+            own = torch.zeros_like(t)
+            own[lo:hi] = t[lo:hi]
+            torch.distributed.all_reduce(own, group=self.pg)
+            out.append(own)
+        return out
+
     def _whole(self, xa, xb, mask):
         if self.kind == 'autoencoder':
             xb = xa                              # the target is the input (autoencode.py:88-90)
         elif self.augment is not None:
             xa, xb, mask = self._augment(xa)
         self._forward_backward(xa, xb, mask)
-        self._allreduce()
-        self._adam()
+        if self.world > 1 and self.dp_mode == 'p2p':
+            self._dp_adam()
+        else:
+            self._allreduce()
+            self._adam()
 
     # ------------------------------------------------------------------------------------------
     def step(self, xa: torch.Tensor, xb: Optional[torch.Tensor] = None, mask: Optional[torch.Tensor] = None):
@@ -594,14 +640,15 @@ class Trainer:
         ``net.state_dict()``), the step count and the hyper-parameters."""
         names = {id(p): n for n, p in self.net.named_parameters()}
         m, v = {}, {}
+        flat_m, flat_v = self._full_moments()
         for u in self.units.values():
             for t in u.tensors():
                 o = t.data.data_ptr() - self.flat_p.data_ptr()
                 assert o % 4 == 0
                 o //= 4
                 k = t.numel()
-                m[names[id(t)]] = self.flat_m[o:o + k].view_as(t).clone()
-                v[names[id(t)]] = self.flat_v[o:o + k].view_as(t).clone()
+                m[names[id(t)]] = flat_m[o:o + k].view_as(t).clone()
+                v[names[id(t)]] = flat_v[o:o + k].view_as(t).clone()
         return {'exp_avg': m, 'exp_avg_sq': v, 'step': int(self.step_dev.item()), 'lr': self.lr, 'betas': tuple(self.betas),
                 'eps': self.eps, 'precision': self.precision}
 

@@ -24,7 +24,7 @@ mode = sys.argv[1] if len(sys.argv) > 1 else 'graph'
 torch.manual_seed(rank)
 net = keynet.build('F', 3, 64, 10)
 tr = Trainer(net, precision='bf16', use_graph=mode == 'graph', device=dev, augment=dict(cntl_pts=4, variance=0.05, max_rotate=0.1))
-mark(f'trainer built, overlap={tr.overlap_allreduce}')
+mark(f'trainer built, dp_mode={tr.dp_mode} overlap={tr.overlap_allreduce} multicast={getattr(tr.peer, "multicast", None)}')
 x = torch.rand(8, 3, 64, 64, device=dev)
 orig_capture = tr._capture
 
