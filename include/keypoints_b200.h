@@ -238,6 +238,18 @@ int kp_aug_draw(kp_stream stream, uint64_t seed, const int32_t* step_dev, int dr
 /* Input conversion on the device (transforms.ToTensor + Normalize, datasets.py:287-300): uint8 NHWC frames as the
  * loader ships them over PCIe -> fp32 NCHW, out = in * scale + bias (grey/color: scale 2/255, bias -1; celeba: 1/255, 0). */
 int kp_u8_to_f32(kp_stream stream, const uint8_t* in, float* out, int N, int H, int W, int C, float scale, float bias);
+/* Real-data ingestion (datasets.py:237-254 ImageFolder + celeba_transform :297-300), SURVEY.md 8f.4.
+ * kp_jpeg_*: nvJPEG decode of one host JPEG stream into an interleaved RGB uint8 device image (libnvjpeg is dlopen'ed at
+ * the first kp_jpeg_create; KP_ERR_UNSUPPORTED if it is absent).  A context is not thread-safe: one per decoding thread.
+ * kp_resize_to_f32: transforms.Resize((oh,ow)) of a PIL image (Pillow's antialiased BILINEAR: triangle filter of support
+ * max(scale,1), horizontal pass then vertical pass, 8-bit rounding after each) + ToTensor: uint8 [H][W][C] ->
+ * fp32 [C][oh][ow] in [0,1], i.e. straight into one slot of the NCHW batch.  tmp: uint8 [H][ow][C] scratch. */
+int kp_jpeg_create(void** ctx);
+int kp_jpeg_destroy(void* ctx);
+int kp_jpeg_info(void* ctx, const uint8_t* data, int64_t len, int* width, int* height, int* components);
+int kp_jpeg_decode(void* ctx, kp_stream stream, const uint8_t* data, int64_t len, uint8_t* out_rgb, int width, int height);
+int kp_resize_to_f32(kp_stream stream, const uint8_t* in_hwc, int in_h, int in_w, int channels, uint8_t* tmp,
+                     float* out_chw, int out_h, int out_w);
 /* cudaMemsetAsync(ptr, 0, bytes) on `stream` (gradient / statistics accumulators; graph-capturable). */
 int kp_zero(kp_stream stream, void* ptr, int64_t bytes);
 /* rotate_affine_grid_multi: affine_grid([[cos,sin,0],[-sin,cos,0]]) + grid_sample. rot: [N]. */

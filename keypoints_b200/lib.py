@@ -74,6 +74,11 @@ SIGNATURES = {
     'kp_rotate_warp': [_P, _P, _P, _P, _I, _I, _I, _I],
     'kp_aug_draw': [_P, C.c_uint64, _P, _I, _I, _I, _F, _F, _P, _P, _P],
     'kp_zero': [_P, _P, _L],
+    'kp_jpeg_create': [C.POINTER(C.c_void_p)],
+    'kp_jpeg_destroy': [_P],
+    'kp_jpeg_info': [_P, _P, _L, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)],
+    'kp_jpeg_decode': [_P, _P, _P, _L, _P, _I, _I],
+    'kp_resize_to_f32': [_P, _P, _I, _I, _I, _P, _P, _I, _I],
     'kp_u8_to_f32': [_P, _P, _P, _I, _I, _I, _I, _F, _F],
     'kp_loss_ring_push': [_P, _P, _D, _P, _P, _I],
     'kp_dp_adam_step': [_P, C.POINTER(KpDpPeers), _I, _I, _L, _P, _P, _D, _D, _D, _D, _F, _P, _P, _I],

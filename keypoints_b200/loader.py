@@ -187,3 +187,117 @@ def u8_pairs_to_float(mean: float = 0.5, std: float = 0.5):
             outs.append(o)
         return tuple(outs)
     return convert
+
+
+# ---- real images: ImageFolder of JPEGs -> nvJPEG decode -> Pillow-exact resize -> fp32 NCHW batch on the device ---------
+IMG_EXTENSIONS = ('.jpg', '.jpeg', '.png', '.ppm', '.bmp', '.pgm', '.tif', '.tiff', '.webp')
+
+
+def image_folder_files(root: str):
+    """The sample list of ``torchvision.datasets.ImageFolder(root)`` (datasets.py:248): classes = sorted sub-directories,
+    files of a class in sorted walk order; returns [(path, class_index)]."""
+    import os
+    classes = sorted(e.name for e in os.scandir(root) if e.is_dir())
+    if not classes:
+        raise FileNotFoundError(f"Couldn't find any class folder in {root}.")
+    out = []
+    for ci, cname in enumerate(classes):
+        for d, _, fnames in sorted(os.walk(os.path.join(root, cname), followlinks=True)):
+            for f in sorted(fnames):
+                if f.lower().endswith(IMG_EXTENSIONS):
+                    out.append((os.path.join(d, f), ci))
+    return out
+
+
+class JpegBatchDecoder:
+    """Decodes a batch of JPEG byte strings on the GPU and applies the reference's ``celeba_transform`` (datasets.py:297-300:
+    Resize((128,128)) + ToTensor) into an fp32 NCHW batch.  `threads` host threads each own an nvJPEG context, a CUDA stream
+    and scratch buffers (nvJPEG's Huffman stage runs on the host; ctypes releases the GIL during the calls)."""
+
+    def __init__(self, device, size=(128, 128), threads: int = 4):
+        import ctypes
+        from concurrent.futures import ThreadPoolExecutor
+        from . import lib as L
+        self.L, self.device, self.size = L, torch.device(device), tuple(size)
+        L.load()
+        self.workers = []
+        with torch.cuda.device(self.device):
+            for _ in range(threads):
+                ctx = ctypes.c_void_p()
+                L.call('kp_jpeg_create', ctypes.byref(ctx), count=False)
+                self.workers.append({'ctx': ctx, 'stream': torch.cuda.Stream(device=self.device), 'rgb': None, 'tmp': None,
+                                     'event': torch.cuda.Event()})
+        self.pool = ThreadPoolExecutor(max_workers=threads)
+        self.free: "queue.Queue[dict]" = queue.Queue()
+        for w in self.workers:
+            self.free.put(w)
+
+    def _one(self, data: bytes, out_slot: torch.Tensor):
+        import ctypes
+        L = self.L
+        w = self.free.get()
+        try:
+            with torch.cuda.device(self.device):
+                buf = (ctypes.c_uint8 * len(data)).from_buffer_copy(data)
+                wd, ht, nc = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+                L.call('kp_jpeg_info', w['ctx'], buf, len(data), ctypes.byref(wd), ctypes.byref(ht), ctypes.byref(nc), count=False)
+                W, H = wd.value, ht.value
+                oh, ow = self.size
+                if w['rgb'] is None or w['rgb'].numel() < H * W * 3:
+                    w['rgb'] = torch.empty(H * W * 3, dtype=torch.uint8, device=self.device)
+                if w['tmp'] is None or w['tmp'].numel() < H * ow * 3:
+                    w['tmp'] = torch.empty(H * ow * 3, dtype=torch.uint8, device=self.device)
+                st = ctypes.c_void_p(w['stream'].cuda_stream)
+                L.call('kp_jpeg_decode', w['ctx'], st, buf, len(data), L.ptr(w['rgb']), W, H)
+                L.call('kp_resize_to_f32', st, L.ptr(w['rgb']), H, W, 3, L.ptr(w['tmp']), L.ptr(out_slot), oh, ow)
+                w['event'].record(w['stream'])
+                w['event'].synchronize()          # scratch buffers and the host byte buffer are reused by the next image
+        finally:
+            self.free.put(w)
+
+    def decode(self, blobs: Sequence[bytes], out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """blobs: JPEG byte strings -> out [len(blobs)][3][oh][ow] fp32 in [0,1] on the device (complete on return)."""
+        oh, ow = self.size
+        if out is None:
+            out = torch.empty((len(blobs), 3, oh, ow), dtype=torch.float32, device=self.device)
+        futs = [self.pool.submit(self._one, b, out[i]) for i, b in enumerate(blobs)]
+        for f in futs:
+            f.result()
+        return out
+
+    def close(self):
+        self.pool.shutdown(wait=True)
+        for w in self.workers:
+            self.L.call('kp_jpeg_destroy', w['ctx'], count=False)
+        self.workers = []
+
+
+def jpeg_folder_batches(root: str, batch: int, device, size=(128, 128), shuffle_seed: Optional[int] = 0, epochs: int = 1,
+                        decode_threads: int = 4, read_threads: int = 4, drop_last: bool = True):
+    """Batches of an ImageFolder of JPEGs as fp32 NCHW device tensors (the CelebA datapack of the reference,
+    datasets.py:237-254,297-300 + DataLoader(shuffle=True), keypoints.py:36): files are read by a thread pool one batch
+    ahead of the decoder, decoded and resized on the GPU.  Feed the result to ``Trainer.step(x)`` with TpsAndRotate on."""
+    from concurrent.futures import ThreadPoolExecutor
+    files = [p for p, _ in image_folder_files(root)]
+    dec = JpegBatchDecoder(device, size, decode_threads)
+    readers = ThreadPoolExecutor(max_workers=read_threads)
+
+    def read(path):
+        with open(path, 'rb') as fh:
+            return fh.read()
+
+    try:
+        for ep in range(epochs):
+            order = np.arange(len(files))
+            if shuffle_seed is not None:
+                np.random.default_rng((shuffle_seed, ep)).shuffle(order)
+            starts = list(range(0, len(order) - (batch - 1 if drop_last else 0), batch))
+            pending = None
+            for s in starts + [None]:
+                nxt = None if s is None else [readers.submit(read, files[i]) for i in order[s:s + batch]]
+                if pending is not None:
+                    yield dec.decode([f.result() for f in pending])
+                pending = nxt
+    finally:
+        readers.shutdown(wait=False)
+        dec.close()

@@ -84,3 +84,86 @@ def test_prefetcher_feeds_the_trainer_from_uint8_frames():
         losses.append(tr.loss())
         count += 1
     assert count == nb and all(np.isfinite(losses))
+
+
+def _write_jpegs(root, n, seed=0, subsampling=0):
+    """A small ImageFolder of CelebA-sized (178x218) JPEGs: smooth gradients + rectangles, written with Pillow."""
+    import os
+    from PIL import Image
+    rng = np.random.default_rng(seed)
+    paths = []
+    for cls in ('a', 'b'):
+        os.makedirs(os.path.join(root, cls), exist_ok=True)
+    for i in range(n):
+        h, w = 218, 178
+        yy, xx = np.mgrid[0:h, 0:w].astype(np.float32)
+        img = np.stack([(np.sin(xx / rng.uniform(8, 30) + rng.uniform(0, 6)) * 0.5 + 0.5) * 255,
+                        (np.cos(yy / rng.uniform(8, 30)) * 0.5 + 0.5) * 255,
+                        ((xx + yy) / (h + w)) * 255], axis=-1)
+        for _ in range(3):
+            y0, x0 = rng.integers(0, h - 40), rng.integers(0, w - 40)
+            img[y0:y0 + rng.integers(8, 40), x0:x0 + rng.integers(8, 40)] = rng.integers(0, 256, size=3)
+        p = os.path.join(root, 'a' if i % 2 == 0 else 'b', f'img_{i:03d}.jpg')
+        Image.fromarray(img.astype(np.uint8)).save(p, quality=92, subsampling=subsampling)
+        paths.append(p)
+    return paths
+
+
+def test_image_folder_listing_matches_torchvision(tmp_path):
+    import torchvision as tv
+    from keypoints_b200.loader import image_folder_files
+    _write_jpegs(str(tmp_path), 7)
+    ours = image_folder_files(str(tmp_path))
+    ref = tv.datasets.ImageFolder(str(tmp_path)).samples
+    assert ours == [(p, c) for p, c in ref]
+
+
+@pytest.mark.gpu
+def test_jpeg_decode_and_resize_match_the_reference_transform(tmp_path):
+    """nvJPEG decode + the resize kernels against the reference's celeba_transform (datasets.py:297-300: Pillow decode,
+    transforms.Resize((128,128)), ToTensor).  The resize is checked tightly on identical decoded pixels (<= 1 grey level,
+    Pillow works in fixed point); decode + resize end to end within the IDCT tolerance between libjpeg and nvJPEG."""
+    import ctypes
+    import torchvision.transforms as T
+    from PIL import Image
+    from keypoints_b200 import lib as L
+    from keypoints_b200.loader import JpegBatchDecoder, jpeg_folder_batches
+    dev = torch.device('cuda:0')
+    paths = _write_jpegs(str(tmp_path), 6, seed=1, subsampling=0)
+    celeba_transform = T.Compose([T.Resize((128, 128)), T.ToTensor()])
+    # (a) resize kernels on Pillow-decoded pixels
+    for p in paths[:3]:
+        im = Image.open(p).convert('RGB')
+        arr = torch.from_numpy(np.asarray(im).copy()).to(dev)                    # [H][W][3] uint8
+        H, W = arr.shape[:2]
+        tmp = torch.empty(H * 128 * 3, dtype=torch.uint8, device=dev)
+        out = torch.empty(3, 128, 128, device=dev)
+        L.call('kp_resize_to_f32', L.stream(), L.ptr(arr), H, W, 3, L.ptr(tmp), L.ptr(out), 128, 128)
+        ref = celeba_transform(im)
+        d = (out.cpu() - ref).abs() * 255
+        assert float(d.max()) <= 1.01, float(d.max())
+        assert float((d > 0.5).float().mean()) < 0.02                             # almost every pixel identical
+    # (b) the whole pipeline
+    dec = JpegBatchDecoder(dev, (128, 128), threads=3)
+    blobs = [open(p, 'rb').read() for p in paths]
+    out = dec.decode(blobs)
+    dec.close()
+    for i, p in enumerate(paths):
+        ref = celeba_transform(Image.open(p).convert('RGB'))
+        d = (out[i].cpu() - ref).abs() * 255
+        assert float(d.mean()) < 0.6 and float(d.max()) <= 6.0, (p, float(d.mean()), float(d.max()))
+    # (c) batches of the folder in ImageFolder order feed the trainer
+    got = list(jpeg_folder_batches(str(tmp_path), 2, dev, shuffle_seed=None))
+    assert len(got) == 3 and got[0].shape == (2, 3, 128, 128)
+    from keypoints_b200.loader import image_folder_files
+    order = [p for p, _ in image_folder_files(str(tmp_path))]
+    ref0 = celeba_transform(Image.open(order[0]).convert('RGB'))
+    assert float((got[0][0].cpu() - ref0).abs().max()) * 255 <= 6.0
+    from keypoints_b200.models import keynet
+    from keypoints_b200.trainer import Trainer
+    torch.manual_seed(0)
+    tr = Trainer(keynet.build('VGG_PONG', 3, 8, 4), precision='bf16', use_graph=False, device=dev,
+                 augment=dict(cntl_pts=4, variance=0.05, max_rotate=0.1))
+    for x in got:
+        tr.step(x)
+        assert np.isfinite(tr.loss())
