@@ -1047,6 +1047,147 @@ wgrad_tc_persist_k(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     }
 }
 
+// Row-stacked weight gradient for the layers whose narrow side has 64 channels (64 <-> 128 at 128x128 / 256x256).  With one
+// tap per work item every staged byte feeds exactly one 128 x 64 x 16 MMA: 24 KB written by TMA + 24 KB read by the tensor
+// core per 128 clocks of MMA = 375 B/clk against the SM's ~128 B/clk of shared-memory bandwidth, so those launches ran at
+// 0.26 of the tensor peak (620 TFLOP/s).  Here a work item is a kernel ROW: the 128-channel operand (unshifted: dy for
+// 64 -> 128, x for 128 -> 64, where the shift moves to dy with the opposite sign) is staged ONCE and multiplied against the
+// three horizontally shifted tiles of the 64-channel operand laid side by side as one N = 192 operand (three MN-major
+// 64-channel atoms, LBO = one box) -> 80 KB of shared-memory traffic per 384 clocks = 208 B/clk.
+template <int STAGES>
+__global__ void __launch_bounds__(192, 1)
+wgrad_tc_rows_k(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const WgradTcParams p) {
+    constexpr int BOX_BYTES = 64 * 128;
+    constexpr int A_BYTES = 2 * BOX_BYTES;
+    constexpr int B_BYTES = 3 * BOX_BYTES;
+    constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+    constexpr int NACC = 256;                                  // TMEM column pitch of one accumulator buffer (192 used)
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* gen_base = smem_raw + (base - smem_u32(smem_raw));
+    const uint32_t bars = base + STAGES * STAGE_BYTES;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gen_base + STAGES * STAGE_BYTES + 8 * (2 * STAGES + 4));
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int num_m = p.Mtot / 128, num_n = p.Ntot / 64;
+    // work item = (split, kernel row, n tile, m tile)
+    const int total = num_m * num_n * 3 * p.splits;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmA);
+        tma_prefetch_desc(&tmB);
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(bars + 8 * s, 1);
+            mbar_init(bars + 8 * (STAGES + s), 1);
+        }
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(bars + 8 * (2 * STAGES + b), 1);
+            mbar_init(bars + 8 * (2 * STAGES + 2 + b), 1);
+        }
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(smem_u32(tmem_slot), 2 * NACC);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    auto decode = [&](int t, int& m0, int& n0, int& ty, long long& qbeg, int& nkb) {
+        int mt = t % num_m; t /= num_m;
+        int nt = t % num_n; t /= num_n;
+        ty = t % 3;
+        int split = t / 3;
+        m0 = mt * 128; n0 = nt * 64;
+        qbeg = (long long)split * p.kchunk;
+        long long qend = qbeg + p.kchunk;
+        if (qend > p.Q) qend = p.Q;
+        nkb = qend > qbeg ? (int)((qend - qbeg + 63) / 64) : 0;
+    };
+
+    if (warp == 0) {
+        if (elect_one()) {
+            int it = 0;
+            for (int t = blockIdx.x; t < total; t += gridDim.x) {
+                int m0, n0, ty, nkb;
+                long long qbeg;
+                decode(t, m0, n0, ty, qbeg, nkb);
+                for (int kb = 0; kb < nkb; ++kb, ++it) {
+                    const int s = it % STAGES, ph = (it / STAGES) & 1;
+                    mbar_wait(bars + 8 * (STAGES + s), ph ^ 1);
+                    const uint32_t full = bars + 8 * s;
+                    mbar_expect_tx(full, STAGE_BYTES);
+                    const long long q = qbeg + (long long)kb * 64;
+                    const uint32_t sa = base + s * STAGE_BYTES;
+#pragma unroll
+                    for (int b = 0; b < 2; ++b) tma_load_2d(sa + b * BOX_BYTES, &tmA, m0 + b * 64, (int)q, full);
+#pragma unroll
+                    for (int tx = 0; tx < 3; ++tx)
+                        tma_load_2d(sa + A_BYTES + tx * BOX_BYTES, &tmB, n0, (int)(q + p.shiftB[3 * ty + tx]), full);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (elect_one()) {
+            constexpr uint32_t idesc = make_idesc(192, 1, 1);
+            int it = 0, lt = 0;
+            for (int t = blockIdx.x; t < total; t += gridDim.x, ++lt) {
+                int m0, n0, ty, nkb;
+                long long qbeg;
+                decode(t, m0, n0, ty, qbeg, nkb);
+                const int buf = lt & 1;
+                mbar_wait(bars + 8 * (2 * STAGES + 2 + buf), ((lt >> 1) & 1) ^ 1);
+                tc_fence_after();
+                const uint32_t dcol = tmem_base + buf * NACC;
+                for (int kb = 0; kb < nkb; ++kb, ++it) {
+                    const int s = it % STAGES, ph = (it / STAGES) & 1;
+                    mbar_wait(bars + 8 * s, ph);
+                    tc_fence_after();
+                    const uint32_t sa = base + s * STAGE_BYTES;
+                    const uint64_t ad = make_desc(sa, BOX_BYTES, 1024), bd = make_desc(sa + A_BYTES, BOX_BYTES, 1024);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) umma_bf16(dcol, ad + 128 * k, bd + 128 * k, idesc, (kb | k) ? 1u : 0u);
+                    umma_commit(bars + 8 * (STAGES + s));
+                }
+                umma_commit(bars + 8 * (2 * STAGES + buf));
+            }
+        }
+    } else {
+        const int wq = warp & 3;
+        const int row = wq * 32 + lane;
+        const int et = threadIdx.x - 64;
+        int lt = 0;
+        for (int t = blockIdx.x; t < total; t += gridDim.x, ++lt) {
+            int m0, n0, ty, nkb;
+            long long qbeg;
+            decode(t, m0, n0, ty, qbeg, nkb);
+            const int buf = lt & 1;
+            mbar_wait(bars + 8 * (2 * STAGES + buf), (lt >> 1) & 1);
+            tc_fence_after();
+            if (nkb > 0) {
+#pragma unroll 1
+                for (int c = 0; c < 6; ++c) {                   // 192 columns = 3 taps x 64 channels, 32 at a time
+                    uint32_t r[32];
+                    tmem_ld32(tmem_base + ((uint32_t)(wq * 32) << 16) + buf * NACC + c * 32, r);
+                    float* dst = p.stg + ((long long)(3 * ty + (c >> 1)) * p.Mtot + m0 + row) * p.Ntot + n0 + (c & 1) * 32;
+#pragma unroll
+                    for (int g = 0; g < 8; ++g)
+                        red_add_v4(dst + g * 4, __uint_as_float(r[4 * g]), __uint_as_float(r[4 * g + 1]),
+                                   __uint_as_float(r[4 * g + 2]), __uint_as_float(r[4 * g + 3]));
+                }
+            }
+            tc_fence_before();
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            if (et == 0) mbar_arrive(bars + 8 * (2 * STAGES + 2 + buf));
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        __syncwarp();
+        tmem_dealloc(tmem_base, 2 * NACC);
+    }
+}
+
 // CTA-pair weight gradient: D[256 (M channels)][BN (N channels)], each CTA stages its 128 M-channels of one operand and
 // BN/2 N-channels of the other (MN-major boxes of 64 channels x 64 pixels); one M=256 MMA stream issued by the leader.
 template <int BN, int STAGES>
@@ -1366,6 +1507,21 @@ static int launch_wgrad_persist(cudaStream_t st, const CUtensorMap& a, const CUt
     return KP_OK;
 }
 
+template <int STAGES>
+static int launch_wgrad_rows(cudaStream_t st, const CUtensorMap& a, const CUtensorMap& b, const WgradTcParams& p) {
+    constexpr int smem = STAGES * (5 * 8192) + 8 * (2 * STAGES + 4) + 16 + 1024;
+    static_assert(smem <= 227 * 1024, "shared memory budget");
+    static KpOncePerDevice attr_done;
+    if (attr_done.first()) {
+        KP_CUDA(cudaFuncSetAttribute(wgrad_tc_rows_k<STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    }
+    long long total = (long long)(p.Mtot / 128) * (p.Ntot / 64) * 3 * p.splits;
+    int grid = (int)(total < kp_sm_count() ? total : kp_sm_count());
+    wgrad_tc_rows_k<STAGES><<<grid, 192, smem, st>>>(a, b, p);
+    KP_LAUNCH_CHECK();
+    return KP_OK;
+}
+
 }  // namespace
 
 // in: bf16 [Q][Cin]; wt: bf16 [taps][Cout][Cin]; out: bf16 [Q][Cout]; shifts: host int[taps];
@@ -1501,6 +1657,14 @@ static int wgrad_tc_impl(kp_stream stream, const void* x_bf16, const void* dy_bf
     const int tiles = (Mtot / 128) * (Ntot / BN) * taps;
     long long blocks64 = (Q + 63) / 64;
     choose_split(tiles, kp_sm_count(), blocks64, &p.kchunk, &p.splits);
+    static int rows_on = -1;
+    if (rows_on < 0) { const char* e = getenv("KP_WGRAD_ROWS"); rows_on = (e && e[0] == '0') ? 0 : 1; }
+    const bool rows = rows_on && !img && BN == 64 && taps == 9;
+    if (rows) {
+        // row-stacked form: the 128-channel operand is staged unshifted, the 64-channel one carries the (relative) shift
+        for (int i = 0; i < 9; ++i) { p.shiftB[i] = p.shiftB[i] - p.shiftA[i]; p.shiftA[i] = 0; }
+        choose_split((Mtot / 128) * (Ntot / 64) * 3, kp_sm_count(), blocks64, &p.kchunk, &p.splits);
+    }
     // dw_oihw == NULL: deferred mode — the caller zeroes its staging arena once per step and folds every layer with one
     // kp_wgrad_finalize_multi launch (saves a memset and a fold launch per layer)
     if (dw_oihw) KP_CUDA(cudaMemsetAsync(stg, 0, sizeof(float) * (size_t)taps * Mtot * Ntot, st));
@@ -1512,7 +1676,8 @@ static int wgrad_tc_impl(kp_stream stream, const void* x_bf16, const void* dy_bf
         choose_split(tiles2, kp_sm_count() / 2, blocks64, &p.kchunk, &p.splits);
         if (BN == 256) rc = launch_wgrad_pair<256, 6>(st, ta, tb, p, taps);
         else rc = launch_wgrad_pair<128, 8>(st, ta, tb, p, taps);
-    } else if (BN == 256) rc = launch_wgrad_persist<256, 4>(st, ta, tb, p, taps);
+    } else if (rows) rc = launch_wgrad_rows<5>(st, ta, tb, p);
+    else if (BN == 256) rc = launch_wgrad_persist<256, 4>(st, ta, tb, p, taps);
     else if (BN == 128) rc = launch_wgrad_persist<128, 6>(st, ta, tb, p, taps);
     else rc = launch_wgrad_persist<64, 8>(st, ta, tb, p, taps);
     if (rc) return rc;
