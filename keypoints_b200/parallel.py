@@ -64,10 +64,6 @@ class PeerBuckets:
         self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
         if self.world > L.DP_MAX_WORLD:
             raise RuntimeError(f'peer-memory data parallelism supports up to {L.DP_MAX_WORLD} replicas')
-        try:
-            symm.enable_symm_mem_for_group(group.group_name)
-        except Exception:
-            pass                                  # newer torch enables groups implicitly
         self.p = symm.empty(n, dtype=torch.float32, device=device)
         self.g = symm.empty(n, dtype=torch.float32, device=device)
         self.flags = symm.empty(64, dtype=torch.int32, device=device)
@@ -78,8 +74,12 @@ class PeerBuckets:
         self.peers = L.KpDpPeers()
         for j in range(self.world):
             self.peers.p[j], self.peers.g[j], self.peers.flag[j] = hp.buffer_ptrs[j], hg.buffer_ptrs[j], hf.buffer_ptrs[j]
-        self.multicast = bool(getattr(hp, 'has_multicast_support', False) and getattr(hg, 'has_multicast_support', False)
-                              and os.environ.get('KP_DP_MULTICAST', '1') != '0')
+        # NVSwitch multicast (multimem.ld_reduce / multimem.st): measured slower than plain peer loads/stores at 2 replicas
+        # (0.283 vs 0.186 ms for the 98 MB bucket, gpurun_out/r2_dp_micro_n2.log); KP_DP_MULTICAST=0/1 overrides
+        want = os.environ.get('KP_DP_MULTICAST')
+        want = (self.world >= 4) if want is None else want != '0'
+        self.multicast = bool(want and getattr(hp, 'has_multicast_support', False)
+                              and getattr(hg, 'has_multicast_support', False))
         if self.multicast:
             self.peers.mc_p, self.peers.mc_g = hp.multicast_ptr, hg.multicast_ptr
         self.epoch = torch.zeros(1, dtype=torch.int32, device=device)

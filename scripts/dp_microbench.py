@@ -38,7 +38,11 @@ def timed(fn, n=30):
 
 res = {}
 if tr.peer is not None:
-    for mc in ([1, 0] if tr.peer.multicast else [0]):
+    can_mc = bool(tr.peer.peers.mc_g) or tr.peer.multicast
+    if not tr.peer.multicast and getattr(tr.peer.handles[0], 'has_multicast_support', False):
+        tr.peer.peers.mc_p, tr.peer.peers.mc_g = tr.peer.handles[0].multicast_ptr, tr.peer.handles[1].multicast_ptr
+        can_mc = True
+    for mc in ([1, 0] if can_mc else [0]):
         tr.peer.multicast = bool(mc)
         res[f'fused p2p (multicast={mc})'] = timed(tr._dp_adam)
 res['adam alone (replicated)'] = timed(tr._adam)
