@@ -48,6 +48,22 @@ int kp_version(void);
 /* SM count, cc major/minor of the current device; fails loudly if there is no sm_100 GPU. */
 int kp_device_info(int* sm_count, int* cc_major, int* cc_minor);
 
+/* Optional per-device context.  kp_ctx_create binds to the CURRENT CUDA device (fails unless it is sm_100);
+ * kp_ctx_set_current makes it the calling thread's context for every later kp_* call (NULL = none).  A context holds
+ *  - the SM budget of the persistent kernels (kp_ctx_set_sm_limit: leave SMs free, e.g. for a concurrent collective;
+ *    0 = all), and
+ *  - a cache of encoded TMA tensor maps keyed by (buffer, shape, box): with the static buffers of a training loop the
+ *    tensor-core launchers encode each map once instead of on every call (kp_ctx_info reports hits / misses).
+ * Without a current context the calls behave as before (all SMs, maps encoded per call).  One context per thread/GPU;
+ * the context itself is internally locked, the entry points stay asynchronous on `stream`. */
+typedef struct kp_ctx kp_ctx;
+int kp_ctx_create(kp_ctx** ctx);
+int kp_ctx_destroy(kp_ctx* ctx);
+int kp_ctx_set_current(kp_ctx* ctx);
+int kp_ctx_set_sm_limit(kp_ctx* ctx, int sms);
+int kp_ctx_info(kp_ctx* ctx, int* device, int* sm_count, int* sm_limit, int64_t* map_hits, int64_t* map_misses,
+                int64_t* maps_cached);
+
 /* ---------------------------------------------------------------------------------------------
  * Convolution, direct fp32 (CUDA cores).  Parity-grade path and the path for thin layers
  * (Cin or Cout not a multiple of 64).

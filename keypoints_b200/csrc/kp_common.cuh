@@ -126,6 +126,17 @@ __device__ __forceinline__ float act_grad(float z, int act) {
 
 int kp_sm_count();
 
+// kp_ctx (kp_api.cu): per-device state a caller may bind to its thread - SM budget of the persistent kernels and a cache of
+// encoded TMA tensor maps.  The tensor-core launchers ask for maps through kp_ctx_map_{get,put}; without a current
+// context every call encodes its maps afresh (the behaviour before contexts existed).
+struct KpMapKey {
+    const void* ptr;
+    long long d0, d1, d2, d3;     // dims (2-D: rows, cols, box_rows, -1; 4-D: N, PH*65536+PW, C, bx*256+by)
+    bool operator==(const KpMapKey& o) const { return ptr == o.ptr && d0 == o.d0 && d1 == o.d1 && d2 == o.d2 && d3 == o.d3; }
+};
+bool kp_ctx_map_get(const KpMapKey& key, void* map128);        // true: the 128-byte CUtensorMap was copied out of the cache
+void kp_ctx_map_put(const KpMapKey& key, const void* map128);
+
 // per-device one-time setup guard (cudaFuncSetAttribute is per device; one process may drive several GPUs)
 struct KpOncePerDevice {
     unsigned long long mask = 0;

@@ -1397,6 +1397,9 @@ static EncodeTiledFn get_encode() {
 
 // 2-D bf16 matrix [rows][cols] (cols contiguous), box = 64 cols x box_rows, 128-byte swizzle
 static int make_map(CUtensorMap* tm, const void* ptr, long long rows, long long cols, int box_rows) {
+    static_assert(sizeof(CUtensorMap) == 128, "tensor map size");
+    const KpMapKey key{ptr, rows, cols, box_rows, -1};
+    if (kp_ctx_map_get(key, tm)) return KP_OK;
     EncodeTiledFn enc = get_encode();
     if (!enc) { kp_set_error("cuTensorMapEncodeTiled entry point not available"); return KP_ERR_CUDA; }
     cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
@@ -1407,11 +1410,14 @@ static int make_map(CUtensorMap* tm, const void* ptr, long long rows, long long 
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { kp_set_error("cuTensorMapEncodeTiled failed: %d (rows=%lld cols=%lld box=%d)", (int)r, rows, cols, box_rows); return KP_ERR_CUDA; }
+    kp_ctx_map_put(key, tm);
     return KP_OK;
 }
 
 // 4-D bf16 tensor [N][PH][PW][C] (C contiguous), box = 64 channels x bx x by x 1 image, 128-byte swizzle
 static int make_map4(CUtensorMap* tm, const void* ptr, int N, int PH, int PW, int C, int bx, int by) {
+    const KpMapKey key{ptr, N, (long long)PH * 65536 + PW, C, (long long)bx * 256 + by};
+    if (kp_ctx_map_get(key, tm)) return KP_OK;
     EncodeTiledFn enc = get_encode();
     if (!enc) { kp_set_error("cuTensorMapEncodeTiled entry point not available"); return KP_ERR_CUDA; }
     cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)PW, (cuuint64_t)PH, (cuuint64_t)N};
@@ -1422,6 +1428,7 @@ static int make_map4(CUtensorMap* tm, const void* ptr, int N, int PH, int PW, in
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { kp_set_error("cuTensorMapEncodeTiled(4d) failed: %d (N=%d PH=%d PW=%d C=%d box=%dx%d)", (int)r, N, PH, PW, C, bx, by); return KP_ERR_CUDA; }
+    kp_ctx_map_put(key, tm);
     return KP_OK;
 }
 

@@ -46,6 +46,12 @@ _I, _L, _F, _D = C.c_int, C.c_int64, C.c_float, C.c_double
 # name -> argtypes (restype is always int); mirrors include/keypoints_b200.h
 SIGNATURES = {
     'kp_device_info': [C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)],
+    'kp_ctx_create': [C.POINTER(C.c_void_p)],
+    'kp_ctx_destroy': [_P],
+    'kp_ctx_set_current': [_P],
+    'kp_ctx_set_sm_limit': [_P, _I],
+    'kp_ctx_info': [_P, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int64), C.POINTER(C.c_int64),
+                    C.POINTER(C.c_int64)],
     'kp_conv_simt': [_P, _VP, _P, _P, _VP, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I],
     'kp_conv_wgrad_simt': [_P, _VP, _VP, _P, _I, _I, _I, _I, _I, _I],
     'kp_conv_tc': [_P, _P, _L, _I, _P, _I, C.POINTER(C.c_int32), _P, _P, _I, _P, _I, _I, _I, _I],
@@ -127,6 +133,34 @@ def call(name, *args, flops=0.0, tag='', count=True):
         timing.append((name, flops, e0, e1, tag))
     if count:
         launches += 1
+
+
+class Context:
+    """kp_ctx: per-device SM budget + tensor-map cache (include/keypoints_b200.h).  `use()` binds it to the calling thread."""
+
+    def __init__(self):
+        self.handle = C.c_void_p()
+        call('kp_ctx_create', C.byref(self.handle), count=False)
+
+    def use(self):
+        call('kp_ctx_set_current', self.handle, count=False)
+
+    def set_sm_limit(self, sms: int):
+        call('kp_ctx_set_sm_limit', self.handle, int(sms), count=False)
+
+    def info(self):
+        dev, sm, lim = C.c_int(), C.c_int(), C.c_int()
+        hits, misses, cached = C.c_int64(), C.c_int64(), C.c_int64()
+        call('kp_ctx_info', self.handle, C.byref(dev), C.byref(sm), C.byref(lim), C.byref(hits), C.byref(misses), C.byref(cached),
+             count=False)
+        return {'device': dev.value, 'sm_count': sm.value, 'sm_limit': lim.value, 'map_hits': hits.value,
+                'map_misses': misses.value, 'maps_cached': cached.value}
+
+    def close(self):
+        if self.handle:
+            load().kp_ctx_set_current(None)
+            call('kp_ctx_destroy', self.handle, count=False)
+            self.handle = C.c_void_p()
 
 
 def zero(t):

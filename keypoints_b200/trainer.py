@@ -57,6 +57,7 @@ class Trainer:
             self.device = torch.device('cuda', torch.cuda.current_device())
         with torch.cuda.device(self.device):
             L.device_info()                   # fails loudly on a non-sm_100 device
+            self.ctx = L.Context()            # SM budget + tensor-map cache of this trainer's device
         self.net = net.to(self.device)
         if isinstance(net, KeyNet):
             self.kind = 'keynet'
@@ -533,6 +534,7 @@ class Trainer:
         (x, x_, loss_mask) triple is produced by the TPS+rotate kernels.  Returns the device scalar holding
         sum((xhat-x_)^2 mask); ``loss()`` converts it."""
         with torch.cuda.device(self.device):
+            self.ctx.use()
             xa = xa.to(self.device, torch.float32).contiguous()
             paired = self.augment is None and self.kind != 'autoencoder'
             if paired:

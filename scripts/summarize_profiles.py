@@ -14,7 +14,10 @@ METRICS = ['gpu__time_duration.sum', 'launch__grid_size', 'launch__block_size', 
            'sm__throughput.avg.pct_of_peak_sustained_elapsed', 'gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed',
            'dram__bytes_read.sum', 'dram__bytes_write.sum', 'lts__throughput.avg.pct_of_peak_sustained_elapsed',
            'l1tex__throughput.avg.pct_of_peak_sustained_elapsed', 'sm__warps_active.avg.pct_of_peak_sustained_active',
-           'smsp__issue_active.avg.pct_of_peak_sustained_active']
+           'smsp__issue_active.avg.pct_of_peak_sustained_active',
+           # shared-memory side (round 2: the 64/128-channel tcgen05 variants are bounded by it)
+           'l1tex__data_bank_reads.avg.pct_of_peak_sustained_elapsed', 'l1tex__data_bank_writes.avg.pct_of_peak_sustained_elapsed',
+           'l1tex__data_pipe_lsu_wavefronts_mem_shared.sum', 'sm__cycles_elapsed.max']
 
 
 def launches():
@@ -42,13 +45,15 @@ def launches():
     with open(os.path.join(OUT, f'{TAG}_launches_one_step.md'), 'w') as fh:
         fh.write(f'# One graph-replayed training step, per-kernel device time ({TAG})\n\n')
         fh.write('Command: `ncu --metrics gpu__time_duration.sum --clock-control none --csv python bench.py --steps 2 --warmup 3 '
-                 '--no-cpu-baseline --no-kernel-timing` (KeyNet F 128x128 K=10, batch 64, bf16).  Launches between the last two '
+                 '--no-cpu-baseline --no-kernel-timing [--no-eager-baseline --no-module-api --no-other-workloads]` (KeyNet F 128x128 K=10, batch 64, bf16).  Launches between the last two '
                  '`adam_k` launches = one step.  ncu serialises kernels and runs them cold: compare SHARES, not absolutes.\n\n')
         fh.write(f'{b - a} kernel launches, sum {tot:.3f} ms\n\n| ms | share | launches | kernel |\n|---:|---:|---:|---|\n')
         for k, d in sorted(agg.items(), key=lambda kv: -kv[1][1]):
             fh.write(f'| {d[1]:.3f} | {100 * d[1] / tot:.1f}% | {d[0]} | `{k}` |\n')
         tc = sum(d[1] for k, d in agg.items() if 'tc_' in k)
+        bn = sum(d[1] for k, d in agg.items() if k.startswith('bn_'))
         fh.write(f'\ntcgen05 conv family share of the step: {100 * tc / tot:.1f}%\n')
+        fh.write(f'\nBatchNorm pass family (bn_*) share of the step: {100 * bn / tot:.1f}%\n')
     with open(os.path.join(OUT, f'{TAG}_launches_one_step.csv'), 'w') as fh:
         fh.write('kernel,ms\n')
         for n, v in zip(names[a:b], vals[a:b]):
@@ -176,7 +181,7 @@ def sass():
     txt = subprocess.run(['cuobjdump', '-sass', so], capture_output=True, text=True).stdout
     c = collections.Counter()
     import re
-    for m in re.finditer(r'\b(UTCHMMA[.A-Z0-9]*|UTMALDG[.A-Z0-9_]*|UTMAPF[.A-Z0-9_]*|UTCBAR[.A-Z0-9_]*|LDTM[.A-Z0-9_]*|HMMA[.A-Z0-9_]*|REDG[.A-Z0-9_]*|SYNCS[.A-Z0-9_]*|UBLKCP[.A-Z0-9_]*|FFMA2[.A-Z0-9_]*|UTMASTG[.A-Z0-9_]*)', txt):
+    for m in re.finditer(r'\b(LDGMC[.A-Z0-9_]*|UTCHMMA[.A-Z0-9]*|UTMALDG[.A-Z0-9_]*|UTMAPF[.A-Z0-9_]*|UTCBAR[.A-Z0-9_]*|LDTM[.A-Z0-9_]*|HMMA[.A-Z0-9_]*|REDG[.A-Z0-9_]*|SYNCS[.A-Z0-9_]*|UBLKCP[.A-Z0-9_]*|FFMA2[.A-Z0-9_]*|UTMASTG[.A-Z0-9_]*)', txt):
         c[m.group(1)] += 1
     with open(os.path.join(OUT, f'{TAG}_sass_evidence.md'), 'w') as fh:
         fh.write(f'# SASS mnemonics in libkeypoints_b200.so ({TAG})\n\n`cuobjdump -sass keypoints_b200/lib/libkeypoints_b200.so`\n\n| mnemonic | count |\n|---|---:|\n')
@@ -184,7 +189,9 @@ def sass():
             fh.write(f'| {k} | {v} |\n')
         fh.write('\nUTCHMMA = tcgen05.mma (`.2CTA` = cta_group::2), UTMALDG = cp.async.bulk.tensor (TMA), LDTM = tcgen05.ld, '
                  'UTCBAR = tcgen05.commit, UTMASTG = TMA store (conv epilogue), UBLKCP = cp.async.bulk (BatchNorm streaming kernels), '
-                 'FFMA2 = packed fp32x2 math; HMMA (mma.sync) only in the first-layer Cin<=3 kernels (kp_conv_thin_mma.cu).\n')
+                 'FFMA2 = packed fp32x2 math; LDGMC / STG...MC = multimem.ld_reduce / multimem.st (kp_dp.cu); HMMA (mma.sync) in the kernels '
+                 'for shapes a 64-channel tcgen05 k-block cannot fill: first-layer Cin<=3 and narrow 1x1 heads (kp_conv_thin_mma.cu: '
+                 'thin_mma_*, head_mma_*) and the 16/32-channel VGG_PONG layers (kp_conv_small_mma.cu: small_mma_*).\n')
 
 
 if __name__ == '__main__':

@@ -299,3 +299,40 @@ def test_loss_ring_and_plateau_scheduler(dev):
     assert tr.graph is None
     tr.step(xa, xb)
     assert tr.graph is not None
+
+
+def test_ctx_tensor_map_cache_and_sm_limit(dev):
+    """kp_ctx: with a current context the tensor-core launchers take their TMA tensor maps from the cache on the
+    second call (same buffers) and produce bit-identical results; the SM limit shrinks the persistent grids without
+    changing the result beyond the order of the split-K atomics."""
+    from keypoints_b200 import engine, lib as L
+    from keypoints_b200.engine import ConvSpec, LayerParams
+    torch.manual_seed(0)
+    n, cin, cout, h = 2, 64, 128, 32
+    spec = ConvSpec(k=3, cin=cin, cout=cout, bn=False, act='none')
+    p = LayerParams(w=(torch.randn(cout, cin, 3, 3, device=dev) / 24), b=torch.zeros(cout, device=dev))
+    x = torch.randn(n, cin, h, h, device=dev)
+    alloc = engine.CachedAlloc('ctxtest')
+    ctx = L.Context()
+    try:
+        L.load().kp_ctx_set_current(None)
+        xp = engine.to_padded(x, 'bf16', alloc, 'x')
+        out0 = torch.empty(n, h, h, cout, device=dev)
+        engine.unit_forward([spec], [p], xp, h, h, 'bf16', out0, 0, alloc=alloc)          # no context: encode per call
+        ctx.use()
+        outs = []
+        for _ in range(2):
+            o = torch.empty(n, h, h, cout, device=dev)
+            engine.unit_forward([spec], [p], xp, h, h, 'bf16', o, 0, alloc=alloc)
+            outs.append(o)
+        info = ctx.info()
+        assert info['map_misses'] > 0 and info['map_hits'] >= info['map_misses'], info
+        assert torch.equal(outs[0], out0) and torch.equal(outs[1], out0)
+        ctx.set_sm_limit(64)
+        assert ctx.info()['sm_limit'] == 64
+        o = torch.empty(n, h, h, cout, device=dev)
+        engine.unit_forward([spec], [p], xp, h, h, 'bf16', o, 0, alloc=alloc)
+        assert torch.equal(o, out0)                                                        # fprop has no atomics: identical
+        ctx.set_sm_limit(0)
+    finally:
+        ctx.close()
