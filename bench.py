@@ -394,22 +394,42 @@ class Run:
         batches = ((self.x_host,) if aug else (self.x_host, self.x2_host))
         pf = DevicePrefetcher(iter(lambda: batches, None), self.dev)
 
+        # the loss of every step is read back on the host inside the timed region, one step late: the 8-byte D2H copy of
+        # step i is queued behind it and consumed after step i+1 has been launched, so the host never drains the queue
+        # (what runlog.LossRing does for a training loop; the reference's per-step loss.item() stalls here)
+        pinned = [torch.zeros(1, dtype=torch.float64).pin_memory() for _ in range(2)]
+        evs = [torch.cuda.Event(), torch.cuda.Event()]
+        state = {'i': 0, 'loss': 0.0}
+
         def e2e_step():
             cur = pf.next()
             tr.step(*cur)
             pf.release()                                       # step() has copied its inputs into the static graph buffers
-            return tr.loss()                                   # device -> host read of the step's loss
+            k = state['i'] & 1
+            pinned[k].copy_(tr.loss_sum, non_blocking=True)    # device -> host read of this step's loss
+            evs[k].record()
+            if state['i'] > 0:
+                evs[k ^ 1].synchronize()
+                state['loss'] = float(pinned[k ^ 1]) / tr.numel
+            state['i'] += 1
+
+        def drain():
+            k = (state['i'] - 1) & 1
+            evs[k].synchronize()
+            state['loss'] = float(pinned[k]) / tr.numel
 
         for _ in range(2):                                     # untimed: first use of the staging tensors / pinned copies
             e2e_step()
+        drain()
         self.sync()
         f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         f0.record()
-        loss_val = 0.0
         for _ in range(steps):
-            loss_val = e2e_step()
+            e2e_step()
+        drain()
         f1.record()
         self.sync()
+        loss_val = state['loss']
         h2d = self.x_host.numel() * 4 * (1 if aug else 2)
         return f0.elapsed_time(f1), h2d, loss_val
 

@@ -126,6 +126,15 @@ __device__ __forceinline__ float act_grad(float z, int act) {
 
 int kp_sm_count();
 
+// Experiment switches (A/B of kernel generations on the GPU box): compiled in only with `make EXPERIMENTS=1`
+// (-DKP_EXPERIMENTS).  The product library never reads the environment: every switch takes its default.
+#ifdef KP_EXPERIMENTS
+#include <stdlib.h>
+static inline const char* kp_env(const char* name) { return getenv(name); }
+#else
+static inline const char* kp_env(const char*) { return nullptr; }
+#endif
+
 // kp_ctx (kp_api.cu): per-device state a caller may bind to its thread - SM budget of the persistent kernels and a cache of
 // encoded TMA tensor maps.  The tensor-core launchers ask for maps through kp_ctx_map_{get,put}; without a current
 // context every call encodes its maps afresh (the behaviour before contexts existed).

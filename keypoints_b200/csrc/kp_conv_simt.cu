@@ -443,7 +443,7 @@ thin_out_fprop_k(View<TI> in, const float* __restrict__ wk /*[Cin][Cout]*/, cons
 static bool thin_fast_enabled() {
     static int v = -1;
     if (v < 0) {
-        const char* e = getenv("KP_SIMT_FAST");
+        const char* e = kp_env("KP_SIMT_FAST");
         v = (e && e[0] == '0') ? 0 : 1;
     }
     return v == 1;
@@ -451,7 +451,7 @@ static bool thin_fast_enabled() {
 static bool thin_mma_enabled() {
     static int v = -1;
     if (v < 0) {
-        const char* e = getenv("KP_THIN_MMA");
+        const char* e = kp_env("KP_THIN_MMA");
         v = (e && e[0] == '0') ? 0 : 1;
     }
     return v == 1;

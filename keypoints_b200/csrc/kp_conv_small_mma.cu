@@ -644,7 +644,7 @@ int kp_small_mma_conv(cudaStream_t st, const kp_view* in, const float* wk, const
     if (blocks > cap) blocks = cap;
     const bool check = ks == 3 && !(off >= 0 && OH + off + 2 <= IH && OW + off + 2 <= IW);
     static int pipe = -1;
-    if (pipe < 0) { const char* e = getenv("KP_SMALL_CONV_PIPE"); pipe = e ? atoi(e) : 1; }
+    if (pipe < 0) { const char* e = kp_env("KP_SMALL_CONV_PIPE"); pipe = e ? atoi(e) : 1; }
     if (pipe && ks == 3 && (((uintptr_t)in->ptr) % 16) == 0 && in->sx % 8 == 0 && in->sy % 8 == 0 && in->sn % 8 == 0) {
         long long pb = (tiles + SM_WARPS - 1) / SM_WARPS;
         const long long pcap = (long long)kp_sm_count() * 2;
@@ -701,12 +701,12 @@ int kp_small_mma_wgrad(cudaStream_t st, const kp_view* x, const kp_view* dy, flo
     const long long tiles = (long long)N * H * ((W + 15) / 16);
     long long blocks = tiles;
     static int mult = -1;
-    if (mult < 0) { const char* e = getenv("KP_SMALL_WGRAD_MULT"); mult = e ? atoi(e) : 2; if (mult < 1) mult = 1; }
+    if (mult < 0) { const char* e = kp_env("KP_SMALL_WGRAD_MULT"); mult = e ? atoi(e) : 2; if (mult < 1) mult = 1; }
     const long long cap = (long long)kp_sm_count() * mult;
     if (blocks > cap) blocks = cap;
     const dim3 grid((unsigned)blocks);
     static int pipe = -1;
-    if (pipe < 0) { const char* e = getenv("KP_SMALL_WGRAD_PIPE"); pipe = e ? atoi(e) : 1; }
+    if (pipe < 0) { const char* e = kp_env("KP_SMALL_WGRAD_PIPE"); pipe = e ? atoi(e) : 1; }
     if (pipe && ks == 3 && (((uintptr_t)x->ptr) % 16) == 0 && (((uintptr_t)dy->ptr) % 16) == 0 && x->sx % 8 == 0 && x->sy % 8 == 0 &&
         x->sn % 8 == 0 && dy->sx % 8 == 0 && dy->sy % 8 == 0 && dy->sn % 8 == 0) {
 #define KP_SWP(CI, CO)                                                                                                   \
@@ -764,7 +764,7 @@ bool kp_c1_wgrad_ok(const kp_view* x, const kp_view* dy, int Cin, int Cout, int 
 int kp_c1_wgrad(cudaStream_t st, const kp_view* x, const kp_view* dy, float* dw, int N, int H, int W, int Cout) {
     long long rows = (long long)N * H;
     static int mult = -1;
-    if (mult < 0) { const char* e = getenv("KP_C1_WGRAD_MULT"); mult = e ? atoi(e) : 2; if (mult < 1) mult = 1; }
+    if (mult < 0) { const char* e = kp_env("KP_C1_WGRAD_MULT"); mult = e ? atoi(e) : 2; if (mult < 1) mult = 1; }
     const long long cap = (long long)kp_sm_count() * mult;
     const int grid = (int)(rows < cap ? rows : cap);
 #define KP_C1W(GV) c1_wgrad_k<GV><<<grid, 256, 0, st>>>(make_view<bf16>(x), make_view<bf16>(dy), dw, N, H, W)

@@ -1547,7 +1547,7 @@ extern "C" int kp_conv_tc(kp_stream stream, const void* in_bf16, int64_t Q, int 
         const long long mt = (Q + 255) / 256, workers = kp_sm_count() / 2;
         auto eff = [&](long long tiles) { return (double)tiles / (double)(((tiles + workers - 1) / workers) * workers); };
         static int q_on = -1;
-        if (q_on < 0) { const char* e = getenv("KP_TC_QUANT"); q_on = (e && e[0] == '0') ? 0 : 1; }
+        if (q_on < 0) { const char* e = kp_env("KP_TC_QUANT"); q_on = (e && e[0] == '0') ? 0 : 1; }
         if (q_on && eff(mt * (Cout / 256)) < 0.8 && eff(mt * (Cout / 128)) > eff(mt * (Cout / 256)) + 0.08) BN = 128;
     }
     CUtensorMap ta, tb;
@@ -1564,13 +1564,13 @@ extern "C" int kp_conv_tc(kp_stream stream, const void* in_bf16, int64_t Q, int 
     rc = make_map(&to, out_bf16, Q, Cout, 128);
     if (rc) return rc;
     static int pair_on = -1;
-    if (pair_on < 0) { const char* e = getenv("KP_TC_PAIR"); pair_on = (e && e[0] == '0') ? 0 : 1; }
+    if (pair_on < 0) { const char* e = kp_env("KP_TC_PAIR"); pair_on = (e && e[0] == '0') ? 0 : 1; }
     if (pair_on && Q >= 256) {
         CUtensorMap tbh;                                       // each CTA of the pair loads half of the weight tile
         rc = make_map(&tbh, wt_bf16, (long long)taps * Cout, Cin, BN / 2);
         if (rc) return rc;
         static int halo_on = -1;
-        if (halo_on < 0) { const char* e = getenv("KP_TC_HALO"); halo_on = (e && e[0] == '0') ? 0 : 1; }
+        if (halo_on < 0) { const char* e = kp_env("KP_TC_HALO"); halo_on = (e && e[0] == '0') ? 0 : 1; }
         bool regular = taps == 9;                              // shift[3 ty + tx] = shift[3 ty] + tx
         for (int t = 0; regular && t < 9; ++t) regular = shifts[t] == shifts[3 * (t / 3)] + (t % 3);
         if (halo_on && regular) {
@@ -1665,7 +1665,7 @@ static int wgrad_tc_impl(kp_stream stream, const void* x_bf16, const void* dy_bf
     long long blocks64 = (Q + 63) / 64;
     choose_split(tiles, kp_sm_count(), blocks64, &p.kchunk, &p.splits);
     static int rows_on = -1;
-    if (rows_on < 0) { const char* e = getenv("KP_WGRAD_ROWS"); rows_on = (e && e[0] == '0') ? 0 : 1; }
+    if (rows_on < 0) { const char* e = kp_env("KP_WGRAD_ROWS"); rows_on = (e && e[0] == '0') ? 0 : 1; }
     const bool rows = rows_on && !img && BN == 64 && taps == 9;
     if (rows) {
         // row-stacked form: the 128-channel operand is staged unshifted, the 64-channel one carries the (relative) shift
@@ -1676,7 +1676,7 @@ static int wgrad_tc_impl(kp_stream stream, const void* x_bf16, const void* dy_bf
     // kp_wgrad_finalize_multi launch (saves a memset and a fold launch per layer)
     if (dw_oihw) KP_CUDA(cudaMemsetAsync(stg, 0, sizeof(float) * (size_t)taps * Mtot * Ntot, st));
     static int wpair_on = -1;
-    if (wpair_on < 0) { const char* e = getenv("KP_TC_PAIR"); wpair_on = (e && e[0] == '0') ? 0 : 1; }
+    if (wpair_on < 0) { const char* e = kp_env("KP_TC_PAIR"); wpair_on = (e && e[0] == '0') ? 0 : 1; }
     if (wpair_on && Mtot % 256 == 0 && BN >= 128) {
         // recompute the split for 256-row tiles
         const int tiles2 = (Mtot / 256) * (Ntot / BN) * taps;

@@ -527,7 +527,7 @@ int kp_head1x1_wgrad(cudaStream_t st, const kp_view* x, const kp_view* dy, float
 
 bool kp_head_mma_fprop_ok(const kp_view* in, const kp_view* out, int N, int H, int W, int Cw, int Ct) {
     static int on = -1;
-    if (on < 0) { const char* e = getenv("KP_HEAD_MMA"); on = e ? atoi(e) : 1; }
+    if (on < 0) { const char* e = kp_env("KP_HEAD_MMA"); on = e ? atoi(e) : 1; }
     return on && in->dtype == KP_BF16 && in->sc == 1 && (((uintptr_t)in->ptr) % 4) == 0 && in->sx % 2 == 0 && in->sy % 2 == 0 &&
            in->sn % 2 == 0 && Cw % 16 == 0 && Cw >= 16 && Cw <= 512 && Ct >= 1 && Ct <= 32 &&
            (out->dtype == KP_BF16 || out->dtype == KP_F32) && (long long)N * H * W < (1LL << 31) - 16;

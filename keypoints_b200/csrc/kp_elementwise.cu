@@ -952,18 +952,18 @@ static bool fast_ok(int C, long long rows_px) {
 }
 static bool lean_enabled() {
     static int v = -1;
-    if (v < 0) { const char* e = getenv("KP_BN_LEAN"); v = (e && e[0] == '0') ? 0 : 1; }
+    if (v < 0) { const char* e = kp_env("KP_BN_LEAN"); v = (e && e[0] == '0') ? 0 : 1; }
     return v == 1;
 }
 static bool pipe_enabled() {
     static int v = -1;
-    if (v < 0) { const char* e = getenv("KP_BN_PIPE"); v = (e && e[0] == '0') ? 0 : 1; }
+    if (v < 0) { const char* e = kp_env("KP_BN_PIPE"); v = (e && e[0] == '0') ? 0 : 1; }
     return v == 1;
 }
 // dense bf16 NHWC rows the bulk-async kernels can stream: pixel stride == C, 512-item chunks
 static bool pipe_up_enabled() {
     static int v = -1;
-    if (v < 0) { const char* e = getenv("KP_BN_PIPE_UP"); v = (e && e[0] == '0') ? 0 : 1; }
+    if (v < 0) { const char* e = kp_env("KP_BN_PIPE_UP"); v = (e && e[0] == '0') ? 0 : 1; }
     return v == 1;
 }
 static bool pipe_view_ok(const kp_view* v, int C) { return v->dtype == KP_BF16 && v->sx == C && view_vec8_ok(v, C); }
@@ -993,7 +993,7 @@ static int ilog2(int v) { int s = 0; while ((1 << s) < v) ++s; return s; }
 // pass 2 comes back over the same (dout, y) tail; the convs that follow sweep forward again.  KP_BN_REV overrides the mask.
 static int bn_rev(int role, int N) {
     static int mask = -1;
-    if (mask < 0) { const char* e = getenv("KP_BN_REV"); mask = e ? atoi(e) : 5; }
+    if (mask < 0) { const char* e = kp_env("KP_BN_REV"); mask = e ? atoi(e) : 5; }
     return (mask & role) ? N : 0;
 }
 

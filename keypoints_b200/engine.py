@@ -251,12 +251,14 @@ def unit_forward(specs: List[ConvSpec], params: List[LayerParams], x_pad: torch.
 def unit_backward(specs: List[ConvSpec], params: List[LayerParams], grads: List[LayerGrads], ctxs: List[LayerCtx],
                   dout: torch.Tensor, dout_pad: int, precision: str, need_dx: bool,
                   alloc: Callable = default_alloc, tag: str = 'u', defer_stg: Optional[List] = None,
-                  after_wgrad: Optional[Callable] = None) -> Optional[torch.Tensor]:
+                  after_wgrad: Optional[Callable] = None, wgrad_stream=None) -> Optional[torch.Tensor]:
     """Backward of one Unit.  ``dout``: gradient w.r.t. the last activation, indexed [n,y,x,c] (ptr at the
     padded origin when dout_pad=1).  Weight gradients are ACCUMULATED into ``grads`` (zero them per step);
     BatchNorm / bias gradients are overwritten.  ``after_wgrad(i)`` (optional) is called once every gradient of layer i
     (weight, bias, BatchNorm affine) has been issued on the current stream — the fused trainer starts the bucket-wise
-    gradient all-reduce from it.  Returns d(padded input) [N][H+2][W+2][Cp] or None."""
+    gradient all-reduce from it.  ``wgrad_stream`` (optional, deferred-staging mode only): the weight-gradient kernels are
+    issued on that stream, off the dgrad -> BatchNorm-backward chain that the next layer waits for; joined before returning.
+    Returns d(padded input) [N][H+2][W+2][Cp] or None."""
     dev = ctxs[0].x.device
     N = ctxs[0].x.shape[0]
     T = act_dtype(precision)
@@ -266,6 +268,16 @@ def unit_backward(specs: List[ConvSpec], params: List[LayerParams], grads: List[
     L.zero(sums_all)
     soff = 0
     dx = None
+    if defer_stg is None or after_wgrad is not None:
+        wgrad_stream = None
+
+    def wgrad_call(name, *args, **kw):
+        """Launch a weight-gradient kernel (args after the stream) on the wgrad stream if there is one."""
+        if wgrad_stream is None:
+            return L.call(name, L.stream(), *args, **kw)
+        wgrad_stream.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(wgrad_stream):
+            L.call(name, L.stream(), *args, **kw)
     for i in range(len(specs) - 1, -1, -1):
         s, p, g, c = specs[i], params[i], grads[i], ctxs[i]
         h, w = c.h, c.w
@@ -312,10 +324,10 @@ def unit_backward(specs: List[ConvSpec], params: List[LayerParams], grads: List[
             if (WGRAD_IMG and w >= 16 and w & (w - 1) == 0 and (w >= 64 or h % (64 // w) == 0)
                     and (w <= 32 or min(cinp, s.cout) >= 256)):
                 # contraction over the valid pixels only (no MMA work on the pad / zero border)
-                L.call('kp_conv_wgrad_tc_img', st, L.ptr(c.x), L.ptr(dyp), N, h, w, s.cin, cinp, s.cout, s.k, L.ptr(stg),
+                wgrad_call('kp_conv_wgrad_tc_img', L.ptr(c.x), L.ptr(dyp), N, h, w, s.cin, cinp, s.cout, s.k, L.ptr(stg),
                        dw_ptr, flops=2.0 * N * h * w * s.cin * s.cout * s.k * s.k, tag=f'{tag}{i} {s.cin}->{s.cout}@{h}x{w} k{s.k}')
             else:
-                L.call('kp_conv_wgrad_tc', st, L.ptr(c.x), L.ptr(dyp), Q, s.cin, cinp, s.cout, len(sh), L.shifts_array(sh),
+                wgrad_call('kp_conv_wgrad_tc', L.ptr(c.x), L.ptr(dyp), Q, s.cin, cinp, s.cout, len(sh), L.shifts_array(sh),
                        L.ptr(stg), dw_ptr, flops=2.0 * N * h * w * s.cin * s.cout * s.k * s.k, tag=f'{tag}{i} {s.cin}->{s.cout}@{h}x{w} k{s.k}')
             if after_wgrad is not None:
                 after_wgrad(i)
@@ -325,7 +337,7 @@ def unit_backward(specs: List[ConvSpec], params: List[LayerParams], grads: List[
                        L.ptr(dx), cinp, None, PH, PW, PH, PW, flops=2.0 * N * h * w * s.cin * s.cout * s.k * s.k, tag=f'{tag}{i} {s.cin}->{s.cout}@{h}x{w} k{s.k}')
         else:
             src = c.x if s.k == 3 else c.x[:, 1:, 1:, :]
-            L.call('kp_conv_wgrad_simt', st, L.view(src), L.view(dy_int), L.ptr(g.dw), N, h, w, s.cin, s.cout, s.k,
+            wgrad_call('kp_conv_wgrad_simt', L.view(src), L.view(dy_int), L.ptr(g.dw), N, h, w, s.cin, s.cout, s.k,
                    tag=f'{tag}{i} {s.cin}->{s.cout}@{h}x{w} k{s.k}')
             if after_wgrad is not None:
                 after_wgrad(i)
@@ -340,6 +352,8 @@ def unit_backward(specs: List[ConvSpec], params: List[LayerParams], grads: List[
                            tag=f'{tag}{i} dgrad {s.cin}->{s.cout}@{h}x{w} k{s.k}')
         if want_dx and i > 0:
             dout, dout_pad = dx[..., :specs[i - 1].cout], 1
+    if wgrad_stream is not None:
+        torch.cuda.current_stream().wait_stream(wgrad_stream)
     return dx if need_dx else None
 
 

@@ -107,6 +107,9 @@ class Trainer:
             self.loss_sum = torch.zeros(1, dtype=torch.float64, device=self.device)
             self.loss_ring = None             # see LossRing / attach_loss_ring
         self.two_streams = os.environ.get('KP_TWO_STREAMS', '1') != '0'
+        # weight-gradient kernels on their own stream per unit (off the dgrad -> BatchNorm-backward chain)
+        self.wgrad_streams = os.environ.get('KP_WGRAD_STREAM', '0') != '0'
+        self._wg_side = {}
         self.graph = None
         self.graph_key = None
         self.steps_done = 0
@@ -435,8 +438,14 @@ class Trainer:
             def hook(i):
                 if i in ends:
                     self._bucket_ready(u, *ends[i])
+        ws = None
+        if self.wgrad_streams and hook is None:
+            ws = self._wg_side.get(u.name)
+            if ws is None:
+                ws = self._wg_side[u.name] = torch.cuda.Stream(device=self.device)
         return engine.unit_backward(u.specs, u.params, u.grads, u.ctxs, dout, dout_pad, self.precision, need_dx,
-                                    alloc=u.alloc, tag='b', defer_stg=self._stg.get(u.name), after_wgrad=hook)
+                                    alloc=u.alloc, tag='b', defer_stg=self._stg.get(u.name), after_wgrad=hook,
+                                    wgrad_stream=ws)
 
     def _buckets(self):
         if self.world == 1 or not self.overlap_allreduce or self.dp_mode != 'nccl':
