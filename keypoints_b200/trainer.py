@@ -107,8 +107,9 @@ class Trainer:
             self.loss_sum = torch.zeros(1, dtype=torch.float64, device=self.device)
             self.loss_ring = None             # see LossRing / attach_loss_ring
         self.two_streams = os.environ.get('KP_TWO_STREAMS', '1') != '0'
-        # weight-gradient kernels on their own stream per unit (off the dgrad -> BatchNorm-backward chain)
-        self.wgrad_streams = os.environ.get('KP_WGRAD_STREAM', '0') != '0'
+        # weight-gradient kernels on their own stream per unit, off the dgrad -> BatchNorm-backward chain the next layer waits
+        # for: their tails fill with the other kernels (measured A/B/A/B: 14.29 -> 14.16 ms/step, 256x256: 26.40 -> 26.11)
+        self.wgrad_streams = os.environ.get('KP_WGRAD_STREAM', '1') != '0'
         self._wg_side = {}
         self.graph = None
         self.graph_key = None
