@@ -460,7 +460,12 @@ def test_reference_script_loop_through_dropin(dev):
 def _ddp_worker(rank, world, port, out, use_graph, dp_mode):
     import os
     os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank),
-                      KP_DP=dp_mode)
+                      KP_DP=dp_mode.split('+')[0])
+    if dp_mode == 'p2p+multicast':
+        os.environ['KP_DP_MULTICAST'] = '1'        # multimem.ld_reduce / multimem.st through the NVSwitch (default from 4 replicas up)
+    elif dp_mode == 'p2p':
+        os.environ['KP_DP_MULTICAST'] = '0'        # plain peer loads / stores
+    dp_mode = dp_mode.split('+')[0]
     import torch.distributed as dist
     from oracle import keypoints_oracle as O
     from keypoints_b200 import parallel
@@ -473,6 +478,10 @@ def _ddp_worker(rank, world, port, out, use_graph, dp_mode):
     net = keynet.build('F', 3, 64, 10)             # large enough that the NCCL gradient buckets split (deep / shallow layers)
     tr = Trainer(net, precision='bf16', use_graph=use_graph, device=dev, augment=aug)
     assert tr.dp_mode == dp_mode, tr.dp_mode
+    if os.environ.get('KP_DP_MULTICAST') == '1' and not tr.peer.multicast:
+        out[rank] = 'no multicast support'
+        dist.destroy_process_group()
+        return
     p_start = tr.flat_p.clone()
     g = torch.Generator().manual_seed(200 + rank)
     x = torch.rand(4, 3, 64, 64, generator=g).to(dev)
@@ -504,7 +513,7 @@ def _ddp_worker(rank, world, port, out, use_graph, dp_mode):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize('dp_mode,use_graph', [('p2p', True), ('p2p', False), ('nccl', True), ('nccl', False)])
+@pytest.mark.parametrize('dp_mode,use_graph', [('p2p', True), ('p2p', False), ('p2p+multicast', True), ('nccl', True), ('nccl', False)])
 def test_ddp_two_gpus_replicas_stay_identical(dev, dp_mode, use_graph):
     """World-size-2 run of the fused trainer, eager and as ONE captured graph (what the scaling benchmark times), with both
     gradient exchanges: 'p2p' (reduce-scatter + Adam + all-gather fused in one kernel over NVLink peer memory) and 'nccl'
@@ -519,6 +528,8 @@ def test_ddp_two_gpus_replicas_stay_identical(dev, dp_mode, use_graph):
     s = socket.socket(); s.bind(('127.0.0.1', 0)); port = s.getsockname()[1]; s.close()
     out = mp.Manager().dict()
     mp.spawn(_ddp_worker, args=(2, port, out, use_graph, dp_mode), nprocs=2, join=True)
+    if out[0] == 'no multicast support':
+        pytest.skip('the GPUs of this box have no NVSwitch multicast mapping')
     assert torch.equal(out[0][2], out[1][2]), 'constructor broadcast did not equalise the replicas'
     assert out[0][0] < 0.05 and out[1][0] < 0.05, (out[0][0], out[1][0])
     assert torch.equal(out[0][1], out[1][1]), 'replicas diverged'
