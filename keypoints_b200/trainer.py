@@ -677,10 +677,15 @@ class Trainer:
         self.graph = None                      # lr / betas are baked into the captured Adam launch
 
     def save(self, directory):
-        """Module weights in the reference's layout (loadable by the reference's ``net.load``) + ``trainer.pt``."""
+        """Module weights in the reference's layout (loadable by the reference's ``net.load``) + ``trainer.pt``.
+        Data parallel: call on EVERY rank (gathering the sharded Adam moments is a collective); rank 0 writes."""
         import os as _os
-        self.net.save(directory)
-        torch.save(self.state_dict(), _os.path.join(directory, 'trainer.pt'))
+        sd = self.state_dict()
+        if self.rank == 0:
+            self.net.save(directory)
+            torch.save(sd, _os.path.join(directory, 'trainer.pt'))
+        if self.world > 1:
+            torch.distributed.barrier(group=self.pg)
 
     def load(self, directory, map_device=None):
         import os as _os
