@@ -1578,6 +1578,12 @@ extern "C" int kp_conv_tc(kp_stream stream, const void* in_bf16, int64_t Q, int 
             rc = make_map(&ta3, in_bf16, Q, Cin, A3_ROWS);
             if (rc) return rc;
             if (BN == 256) return launch_conv_pair3<256, 3, 6>(st, ta3, tbh, to, p);
+#ifdef KP_EXPERIMENTS
+            static int deep = -1;
+            if (deep < 0) { const char* e = kp_env("KP_TC_DEEP"); deep = (e && e[0] == '1') ? 1 : 0; }
+            if (deep && BN == 128) return launch_conv_pair3<128, 5, 9>(st, ta3, tbh, to, p);
+            if (deep && BN == 64) return launch_conv_pair3<64, 6, 12>(st, ta3, tbh, to, p);
+#endif
             if (BN == 128) return launch_conv_pair3<128, 4, 8>(st, ta3, tbh, to, p);
             return launch_conv_pair3<64, 4, 9>(st, ta3, tbh, to, p);
         }
