@@ -35,6 +35,9 @@ enum kp_status { KP_OK = 0, KP_ERR_ARG = -1, KP_ERR_CUDA = -2, KP_ERR_UNSUPPORTE
 enum kp_dtype  { KP_F32 = 0, KP_BF16 = 1 };
 enum kp_act    { KP_ACT_NONE = 0, KP_ACT_LEAKY = 1, KP_ACT_RELU = 2 };   /* LeakyReLU slope 0.01 */
 enum kp_post   { KP_POST_NONE = 0, KP_POST_POOL = 1, KP_POST_UP = 2 };   /* MaxPool2x2 / bilinear x2 */
+/* OR-ed into `post` of the forward BatchNorm passes: the caller runs this pass on one stream while tensor-core convolutions
+ * run on another, so the small-shared-memory variant that can share an SM with a persistent conv CTA is preferred. */
+#define KP_POST_CORESIDENT 0x100
 
 typedef struct kp_view {
     void*   ptr;                         /* element (n=0,y=0,x=0,c=0) */

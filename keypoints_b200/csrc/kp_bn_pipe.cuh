@@ -126,7 +126,7 @@ constexpr int PIPE_APPLY_STAGE = 2 * pipe::CHUNK_BYTES, PIPE_APPLY_STAGES = 4;
 // forward, post = none: out[py][px] = act(scale * y[clamp(py - pad)][clamp(px - pad)] + shift)
 // unit = (output row, chunk of the source row); edge pixels also write their replicate-border copies
 // ------------------------------------------------------------------------------------------------
-template <int ACT>
+template <int ACT, int STAGES = PIPE_FWD_STAGES>
 __global__ void __launch_bounds__(pipe::THREADS, 2)
 bn_fwd_none_pipe_k(Rows<const bf16> y, Rows<bf16> out, const float* __restrict__ scale, const float* __restrict__ shift,
                    int pad, int N, int H, int W, int C, int cg_shift, int cpr, const BnFuse fuse, int rev) {
@@ -179,7 +179,7 @@ bn_fwd_none_pipe_k(Rows<const bf16> y, Rows<bf16> out, const float* __restrict__
             }
         }
     };
-    pipe_run<PIPE_FWD_STAGE, PIPE_FWD_STAGES>(smem, units, PH, cpr, rev, issue, body);
+    pipe_run<PIPE_FWD_STAGE, STAGES>(smem, units, PH, cpr, rev, issue, body);
 }
 
 // ------------------------------------------------------------------------------------------------

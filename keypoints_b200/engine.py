@@ -181,9 +181,12 @@ def to_padded(x_nchw: torch.Tensor, precision: str, alloc=default_alloc, name='x
 
 def unit_forward(specs: List[ConvSpec], params: List[LayerParams], x_pad: torch.Tensor, H: int, W: int,
                  precision: str, out: torch.Tensor, out_pad: int, alloc: Callable = default_alloc,
-                 training: bool = True, packs: Optional[List[dict]] = None, tag: str = 'u') -> List[LayerCtx]:
+                 training: bool = True, packs: Optional[List[dict]] = None, tag: str = 'u',
+                 coresident: bool = False) -> List[LayerCtx]:
     """Forward of one Unit.  ``x_pad``: [N][H+2][W+2][Cp].  ``out``: tensor indexed [n,y,x,c] receiving the
-    activation of the last conv (ptr at the padded origin when out_pad=1)."""
+    activation of the last conv (ptr at the padded origin when out_pad=1).  ``coresident``: another Unit's convolutions
+    run concurrently on another stream (the BatchNorm passes then use their small-footprint variants)."""
+    co = L.POST_CORESIDENT if coresident else 0
     dev = x_pad.device
     N = x_pad.shape[0]
     T = act_dtype(precision)
@@ -233,7 +236,7 @@ def unit_forward(specs: List[ConvSpec], params: List[LayerParams], x_pad: torch.
                 c.invstd = alloc(f'{tag}.invstd{i}', (s.cout,), torch.float32, dev)
                 L.call('kp_bn_finalize_act_fwd', st, L.ptr(stats), float(N * h * w), L.ptr(p.gamma), L.ptr(p.beta),
                        BN_EPS, BN_MOMENTUM, L.ptr(p.rmean), L.ptr(p.rvar), L.ptr(p.nbt), L.ptr(c.scale), L.ptr(c.shift),
-                       L.ptr(c.mean), L.ptr(c.invstd), L.view(y[:, :h, :w, :]), L.view(dst), L.ACTS[s.act], L.POSTS[s.post],
+                       L.ptr(c.mean), L.ptr(c.invstd), L.view(y[:, :h, :w, :]), L.view(dst), L.ACTS[s.act], L.POSTS[s.post] | co,
                        pad, N, h, w, s.cout, tag=ltag)
             else:   # eval: running statistics (host-side plumbing on [C] vectors)
                 inv = torch.rsqrt(p.rvar + BN_EPS)

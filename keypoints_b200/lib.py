@@ -17,6 +17,7 @@ LIB_PATH = os.environ.get('KP_LIB') or os.path.join(_HERE, 'lib', 'libkeypoints_
 F32, BF16 = 0, 1
 ACT_NONE, ACT_LEAKY, ACT_RELU = 0, 1, 2
 POST_NONE, POST_POOL, POST_UP = 0, 1, 2
+POST_CORESIDENT = 0x100        # hint for the forward BatchNorm passes: tensor-core convs run concurrently on another stream
 ACTS = {None: ACT_NONE, 'none': ACT_NONE, 'leaky': ACT_LEAKY, 'relu': ACT_RELU}
 COMBINE = {'max': 0, 'sum_and_clamp': 1, 'loop': 2}
 POSTS = {None: POST_NONE, 'none': POST_NONE, 'pool': POST_POOL, 'up': POST_UP}

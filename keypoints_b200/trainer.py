@@ -221,8 +221,10 @@ class Trainer:
         return out
 
     def _fwd_unit(self, u: _UnitState, x_pad, H, W, out, out_pad):
+        # encoder and keypoint stacks run side by side on two streams: their BatchNorm passes share SMs with the other's convs
+        co = self.two_streams and self.kind != 'autoencoder' and u.name != 'decoder'
         u.ctxs = engine.unit_forward(u.specs, u.params, x_pad, H, W, self.precision, out, out_pad, alloc=u.alloc,
-                                     training=True, packs=u.packs, tag='f')
+                                     training=True, packs=u.packs, tag='f', coresident=co)
 
     def _staging(self, shapes):
         """One fp32 arena for the tensor-core weight-gradient staging of every layer (zeroed once per step) and the
