@@ -109,6 +109,16 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
         : "memory");
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
 __device__ __forceinline__ bool elect_one() {
     uint32_t pred;
     asm volatile(
@@ -674,14 +684,40 @@ constexpr int A3_ROWS = 136;
 constexpr int A3_BYTES = A3_ROWS * 128;        // 17408 bytes landed by TMA
 constexpr int A3_SLOT = 18432;                 // slot pitch (multiple of 1024)
 
-template <int BN, int AS, int BS>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(320, 1)
+// Sum over the 32 lanes of a warp of 32 per-lane values, transposed: lane l ends with the total of x[l] (returned).
+// Five exchange steps of 16, 8, 4, 2, 1 values: 31 shuffles for 32 columns.
+__device__ __forceinline__ float warp_transpose_sum32(float* x, int lane) {
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) {
+        const bool up = (lane & off) != 0;
+#pragma unroll
+        for (int j = 0; j < off; ++j) {
+            const float send = up ? x[j] : x[j + off];
+            const float keep = up ? x[j + off] : x[j];
+            x[j] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+        }
+    }
+    return x[0];
+}
+
+// RB ("resident B"): the layer's whole weight tile set (9 taps x Cin/64 chunks, this CTA's half of the BN rows) fits the B
+// ring exactly (BS == 9 * Cin / 64, Cout == BN): it is loaded once, on the first tile, and never released - the 64 <-> 128
+// channel layers at 128x128 otherwise re-stage 72 KB of weights for every 54 KB of activations.
+// BN <= 128: the BatchNorm statistics are accumulated per thread in registers across the tiles of a CTA (one row, BN/2
+// columns per thread) and reduced over rows once per CTA with warp shuffles; the BN = 256 tiles keep the per-tile
+// shared-memory transposes (256 accumulators per thread do not fit the register file).
+template <int BN, int AS, int BS, bool RB>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(BN <= 128 ? 384 : 320, 1)
 conv_tc_pair3_k(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmO, const ConvTcParams p) {
+    constexpr bool RS = BN <= 128;                             // register-resident statistics
+    constexpr int EW0 = RS ? 4 : 2;                            // first epilogue warp (RS: warpgroups 1 and 2)
+    constexpr int NCH = BN / 64;                               // 32-column chunks per epilogue thread
     constexpr int B_BYTES = (BN / 2) * 128;                    // this CTA's half of the weight tile
     constexpr int RING_BYTES = AS * A3_SLOT + BS * B_BYTES;
     constexpr int NBAR = 2 * AS + 2 * BS + 4;                  // a_full, a_empty, b_full, b_empty, tfull[2], tempty[2]
     constexpr int AFULL = 0, AEMPTY = AS, BFULL = 2 * AS, BEMPTY = 2 * AS + BS, TFULL = 2 * AS + 2 * BS, TEMPTY = TFULL + 2;
-    constexpr int EPI_FLOATS = 8 * 32 * 17 + 4 * 2 * BN;   // per-warp 32x16 transpose tiles, per-lane-group running column sums
+    constexpr int TILE_FLOATS = RS ? 0 : 8 * 32 * 17;          // per-warp 32x16 transpose tiles (BN = 256 only)
+    constexpr int EPI_FLOATS = TILE_FLOATS + 4 * 2 * BN;       // + per-lane-group running column sums
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* gen_base = smem_raw + (base - smem_u32(smem_raw));
@@ -695,7 +731,6 @@ conv_tc_pair3_k(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     const uint32_t rank = cluster_ctarank();
     const bool leader = rank == 0;
     const int kchunks = p.Cin / 64;
-    const int num_kb = p.taps * kchunks;
     const int num_m = (int)((p.Q + 255) / 256);                 // pair tiles of 256 pixels
     const int total = num_m * (p.Cout / BN);
 
@@ -711,9 +746,9 @@ conv_tc_pair3_k(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(2 * BN) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
     }
-    if (threadIdx.x >= 64) {
-        float* wsum0 = epi + 8 * 32 * 17;
-        for (int i = threadIdx.x - 64; i < 4 * 2 * BN; i += 256) wsum0[i] = 0.f;
+    if (threadIdx.x >= EW0 * 32) {
+        float* wsum0 = epi + TILE_FLOATS;
+        for (int i = threadIdx.x - EW0 * 32; i < 4 * 2 * BN; i += 256) wsum0[i] = 0.f;
     }
     tc_fence_before();
     __syncthreads();
@@ -722,6 +757,12 @@ conv_tc_pair3_k(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     const uint32_t tmem_base = *tmem_slot;
     const int nclusters = gridDim.x >> 1, cid = blockIdx.x >> 1;
 
+    // BN <= 128: three warpgroups, 0 = TMA producer (warp 0) + MMA issuer (warp 1) + two idle warps, 1 and 2 = epilogue.
+    // The epilogue's per-thread BatchNorm accumulators need more than the 168 registers a 384-thread CTA gets evenly, so
+    // warpgroup 0 hands most of its share to the other two (setmaxnreg).  BN = 256: 320 threads, warps 2-9 = epilogue
+    // (113 registers: leaves room for a co-resident BatchNorm CTA of the other stream).
+    if (warp < EW0) {
+    if constexpr (RS) asm volatile("setmaxnreg.dec.sync.aligned.u32 72;" ::: "memory");
     if (warp == 0) {
         if (elect_one()) {
             int ia = 0, ib = 0;
@@ -729,6 +770,7 @@ conv_tc_pair3_k(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 const int n_t = t / num_m, m_t = t - n_t * num_m;
                 const long long q0 = (long long)m_t * 256 + rank * 128;
                 const int n0 = n_t * BN + rank * (BN / 2);
+                const bool load_b = !RB || t == cid;
                 for (int ty = 0; ty < 3; ++ty)
                     for (int kc = 0; kc < kchunks; ++kc) {
                         const int sa_i = ia % AS, pa = (ia / AS) & 1;
@@ -737,13 +779,15 @@ conv_tc_pair3_k(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                         const uint32_t afull = bars + 8 * (AFULL + sa_i);
                         if (leader) mbar_expect_tx(afull, 2 * A3_BYTES);
                         tma_load_2d_pair(base + sa_i * A3_SLOT, &tmA, kc * 64, (int)(q0 + p.shift[3 * ty]), afull);
-                        for (int tx = 0; tx < 3; ++tx) {
-                            const int sb_i = ib % BS, pb = (ib / BS) & 1;
-                            ++ib;
-                            mbar_wait(bars + 8 * (BEMPTY + sb_i), pb ^ 1);
-                            const uint32_t bfull = bars + 8 * (BFULL + sb_i);
-                            if (leader) mbar_expect_tx(bfull, 2 * B_BYTES);
-                            tma_load_2d_pair(base + AS * A3_SLOT + sb_i * B_BYTES, &tmB, kc * 64, (3 * ty + tx) * p.Cout + n0, bfull);
+                        if (load_b) {
+                            for (int tx = 0; tx < 3; ++tx) {
+                                const int sb_i = ib % BS, pb = (ib / BS) & 1;
+                                ++ib;
+                                mbar_wait(bars + 8 * (BEMPTY + sb_i), pb ^ 1);
+                                const uint32_t bfull = bars + 8 * (BFULL + sb_i);
+                                if (leader) mbar_expect_tx(bfull, 2 * B_BYTES);
+                                tma_load_2d_pair(base + AS * A3_SLOT + sb_i * B_BYTES, &tmB, kc * 64, (3 * ty + tx) * p.Cout + n0, bfull);
+                            }
                         }
                     }
             }
@@ -758,6 +802,7 @@ conv_tc_pair3_k(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 tc_fence_after();
                 const uint32_t dcol = tmem_base + buf * BN;
                 uint32_t first = 1;
+                if (RB) ib = 0;
                 for (int ty = 0; ty < 3; ++ty)
                     for (int kc = 0; kc < kchunks; ++kc) {
                         const int sa_i = ia % AS, pa = (ia / AS) & 1;
@@ -767,30 +812,48 @@ conv_tc_pair3_k(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                         for (int tx = 0; tx < 3; ++tx) {
                             const int sb_i = ib % BS, pb = (ib / BS) & 1;
                             ++ib;
-                            mbar_wait(bars + 8 * (BFULL + sb_i), pb);
+                            if (!RB || lt == 0) mbar_wait(bars + 8 * (BFULL + sb_i), pb);
                             tc_fence_after();
                             const uint64_t ad = make_desc(sa + tx * 128, 16, 1024);
                             const uint64_t bd = make_desc(base + AS * A3_SLOT + sb_i * B_BYTES, 16, 1024);
 #pragma unroll
                             for (int k = 0; k < 4; ++k) umma_bf16_pair(dcol, ad + 2 * k, bd + 2 * k, idesc, (first && k == 0) ? 0u : 1u);
                             first = 0;
-                            umma_commit_pair(bars + 8 * (BEMPTY + sb_i));
+                            if (!RB) umma_commit_pair(bars + 8 * (BEMPTY + sb_i));
                         }
                         umma_commit_pair(bars + 8 * (AEMPTY + sa_i));
                     }
                 umma_commit_pair(bars + 8 * (TFULL + buf));
             }
         }
+    }
     } else {
+        if constexpr (RS) asm volatile("setmaxnreg.inc.sync.aligned.u32 208;" ::: "memory");
         const int wq = warp & 3;
         const int row = wq * 32 + lane;
-        const int et = threadIdx.x - 64;                       // 0..255: 8 epilogue warps, 2 per TMEM lane group
-        const int half = (warp - 2) >> 2;                      // which interleaved set of 32-column chunks
-        float* tile = epi + (warp - 2) * (32 * 17);
-        float* wsum_all = epi + 8 * 32 * 17;                   // [4 lane groups][2*BN] running column sums of this CTA
+        const int et = threadIdx.x - EW0 * 32;                 // 0..255: 8 epilogue warps, 2 per TMEM lane group
+        const int half = (warp - EW0) >> 2;                    // which interleaved set of 32-column chunks
+        float* tile = epi + (warp - EW0) * (32 * 17);          // BN = 256 only
+        float* wsum_all = epi + TILE_FLOATS;                   // [4 lane groups][2*BN] running column sums of this CTA
         float* wsum = wsum_all + wq * (2 * BN);
+        float a1[RS ? NCH * 32 : 1], a2[RS ? NCH * 32 : 1];    // per-thread running sums (one row, this warp's columns)
+        if constexpr (RS) {
+#pragma unroll
+            for (int j = 0; j < NCH * 32; ++j) { a1[j] = 0.f; a2[j] = 0.f; }
+        }
         int lt = 0, cur_n = -1, slabs = 0;
-        auto flush = [&](int n_tile) {                         // all 128 epilogue threads
+        auto flush = [&](int n_tile) {                         // all 256 epilogue threads
+            if constexpr (RS) {
+#pragma unroll
+                for (int i = 0; i < NCH; ++i) {
+                    const float s1 = warp_transpose_sum32(a1 + i * 32, lane);     // in place: the accumulators restart at zero
+                    const float s2 = warp_transpose_sum32(a2 + i * 32, lane);
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) { a1[i * 32 + j] = 0.f; a2[i * 32 + j] = 0.f; }
+                    wsum[(half + 2 * i) * 32 + lane] = s1;
+                    wsum[BN + (half + 2 * i) * 32 + lane] = s2;
+                }
+            }
             asm volatile("bar.sync 1, 256;" ::: "memory");
             for (int ch = et; ch < BN; ch += 256) {
                 float s1 = 0.f, s2 = 0.f;
@@ -822,8 +885,51 @@ conv_tc_pair3_k(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             }
             mbar_wait(bars + 8 * (TFULL + buf), (lt >> 1) & 1);
             tc_fence_after();
-#pragma unroll 1
-            for (int c = half; c < BN / 32; c += 2) {
+            auto chunk_rs = [&](const int c, const int ci) {   // BN <= 128: two 16-column halves keep the live registers low
+                const int sb = slabs & 1;
+                if (et == 0) bulk_wait_read<1>();              // the store that last read this slab buffer is done with it
+                asm volatile("bar.sync 1, 256;" ::: "memory");
+                uint8_t* drow = slab_gen + sb * SLAB_BYTES + row * 128;
+                const bool bias_v = p.bias && ((reinterpret_cast<uintptr_t>(p.bias) & 15) == 0);
+#pragma unroll
+                for (int hc = 0; hc < 2; ++hc) {
+                    uint32_t r[16];
+                    tmem_ld16(tmem_base + ((uint32_t)(wq * 32) << 16) + buf * BN + c * 32 + hc * 16, r);
+                    float v[16];
+                    if (bias_v) {
+                        const float4* bp = reinterpret_cast<const float4*>(p.bias + n0 + c * 32 + hc * 16);
+#pragma unroll
+                        for (int g = 0; g < 4; ++g) {
+                            const float4 bv = bp[g];
+                            v[4 * g] = __uint_as_float(r[4 * g]) + bv.x; v[4 * g + 1] = __uint_as_float(r[4 * g + 1]) + bv.y;
+                            v[4 * g + 2] = __uint_as_float(r[4 * g + 2]) + bv.z; v[4 * g + 3] = __uint_as_float(r[4 * g + 3]) + bv.w;
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]) + (p.bias ? p.bias[n0 + c * 32 + hc * 16 + j] : 0.f);
+                    }
+#pragma unroll
+                    for (int g = 0; g < 2; ++g) {
+                        uint4 u;
+                        __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) h[e] = __floats2bfloat162_rn(v[g * 8 + 2 * e], v[g * 8 + 2 * e + 1]);
+                        *reinterpret_cast<uint4*>(drow + (((half * 4 + hc * 2 + g) ^ (row & 7)) << 4)) = u;
+                    }
+                    if (p.stats && valid) {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) {
+                            a1[ci * 32 + hc * 16 + j] += v[j];
+                            a2[ci * 32 + hc * 16 + j] = fmaf(v[j], v[j], a2[ci * 32 + hc * 16 + j]);
+                        }
+                    }
+                }
+                fence_async_smem();
+                asm volatile("bar.sync 1, 256;" ::: "memory");
+                if (et == 0) tma_store_2d(&tmO, slab + sb * SLAB_BYTES, n0 + (c >> 1) * 64, (int)q_tile);
+                ++slabs;
+            };
+            auto chunk = [&](const int c, const int ci) {      // c: 32-column chunk of the tile, ci: its index among this thread's chunks
                 uint32_t r[32];
                 tmem_ld32(tmem_base + ((uint32_t)(wq * 32) << 16) + buf * BN + c * 32, r);
                 float v[32];
@@ -883,6 +989,13 @@ conv_tc_pair3_k(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                         __syncwarp();
                     }
                 }
+            };
+            if constexpr (RS) {
+#pragma unroll
+                for (int i = 0; i < NCH; ++i) chunk_rs(half + 2 * i, i);
+            } else {
+#pragma unroll 1
+                for (int c = half; c < BN / 32; c += 2) chunk(c, 0);
             }
             // every epilogue thread has drained its TMEM rows: release the accumulator buffer to the MMA warp
             tc_fence_before();
@@ -1466,20 +1579,20 @@ static int launch_conv_pair(cudaStream_t st, const CUtensorMap& a, const CUtenso
     return KP_OK;
 }
 
-template <int BN, int AS, int BS>
+template <int BN, int AS, int BS, bool RB>
 static int launch_conv_pair3(cudaStream_t st, const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& o, const ConvTcParams& p) {
-    constexpr int smem = AS * A3_SLOT + BS * (BN / 2) * 128 + 2 * SLAB_BYTES + (8 * 32 * 17 + 4 * 2 * BN) * 4 +
+    constexpr int smem = AS * A3_SLOT + BS * (BN / 2) * 128 + 2 * SLAB_BYTES + ((BN <= 128 ? 0 : 8 * 32 * 17) + 4 * 2 * BN) * 4 +
                          8 * (2 * AS + 2 * BS + 4) + 16 + 1024;
     static_assert(smem <= 227 * 1024, "shared memory budget");
     static KpOncePerDevice attr_done;
     if (attr_done.first()) {
-        KP_CUDA(cudaFuncSetAttribute(conv_tc_pair3_k<BN, AS, BS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        KP_CUDA(cudaFuncSetAttribute(conv_tc_pair3_k<BN, AS, BS, RB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     }
     long long total = ((p.Q + 255) / 256) * (p.Cout / BN);
     int clusters = kp_sm_count() / 2;
     if (clusters > total) clusters = (int)total;
     if (clusters < 1) clusters = 1;
-    conv_tc_pair3_k<BN, AS, BS><<<2 * clusters, 320, smem, st>>>(a, b, o, p);
+    conv_tc_pair3_k<BN, AS, BS, RB><<<2 * clusters, BN <= 128 ? 384 : 320, smem, st>>>(a, b, o, p);
     KP_LAUNCH_CHECK();
     return KP_OK;
 }
@@ -1577,15 +1690,17 @@ extern "C" int kp_conv_tc(kp_stream stream, const void* in_bf16, int64_t Q, int 
             CUtensorMap ta3;                                   // 128 + 2 pixel rows (padded to 136) per kernel row
             rc = make_map(&ta3, in_bf16, Q, Cin, A3_ROWS);
             if (rc) return rc;
-            if (BN == 256) return launch_conv_pair3<256, 3, 6>(st, ta3, tbh, to, p);
-#ifdef KP_EXPERIMENTS
-            static int deep = -1;
-            if (deep < 0) { const char* e = kp_env("KP_TC_DEEP"); deep = (e && e[0] == '1') ? 1 : 0; }
-            if (deep && BN == 128) return launch_conv_pair3<128, 5, 9>(st, ta3, tbh, to, p);
-            if (deep && BN == 64) return launch_conv_pair3<64, 6, 12>(st, ta3, tbh, to, p);
-#endif
-            if (BN == 128) return launch_conv_pair3<128, 4, 8>(st, ta3, tbh, to, p);
-            return launch_conv_pair3<64, 4, 9>(st, ta3, tbh, to, p);
+            if (BN == 256) return launch_conv_pair3<256, 3, 6, false>(st, ta3, tbh, to, p);
+            // small weight sets stay resident in shared memory (loaded once per CTA): 64 -> 128 and 128 -> 64 (and their
+            // dgrads), 72 KB per CTA; the activation ring takes the rest but leaves 16 KB for a co-resident BatchNorm CTA
+            static int rb_on = -1;
+            if (rb_on < 0) { const char* e = kp_env("KP_TC_RESB"); rb_on = (e && e[0] == '0') ? 0 : 1; }
+            if (rb_on && Cout == BN) {
+                if (BN == 128 && Cin == 64) return launch_conv_pair3<128, 5, 9, true>(st, ta3, tbh, to, p);
+                if (BN == 64 && Cin == 128) return launch_conv_pair3<64, 5, 18, true>(st, ta3, tbh, to, p);
+            }
+            if (BN == 128) return launch_conv_pair3<128, 4, 8, false>(st, ta3, tbh, to, p);
+            return launch_conv_pair3<64, 5, 12, false>(st, ta3, tbh, to, p);
         }
         if (BN == 256) return launch_conv_pair<256, 5>(st, ta, tbh, to, p);
         if (BN == 128) return launch_conv_pair<128, 7>(st, ta, tbh, to, p);

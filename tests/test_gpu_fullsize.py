@@ -240,6 +240,38 @@ def test_tcgen05_conv_full_size_vs_fp64(dev, cin, cout, k, H):
     R.finish()
 
 
+@pytest.mark.parametrize('cin,cout,H,n', [(64, 128, 128, 4), (128, 64, 128, 4), (256, 128, 128, 2),
+                                          (512, 512, 16, 64), (256, 256, 64, 4)])
+def test_tcgen05_batchnorm_statistics_full_size_vs_fp64(dev, cin, cout, H, n):
+    """Train-mode BatchNorm statistics of the tensor-core fprop epilogue (per-thread register accumulators for the <= 128
+    wide tiles, shared-memory transposes for the 256 wide ones; several channel tiles per CTA at 16x16) against an fp64
+    reference on the same bf16-rounded operands: batch mean / biased variance through the running buffers to 1e-4."""
+    from keypoints_b200 import engine
+    from keypoints_b200.engine import ConvSpec, LayerParams
+    torch.manual_seed(cin + 3 * cout + H)
+    spec = ConvSpec(k=3, cin=cin, cout=cout, bn=True, act='none')
+    x = (torch.randn(n, cin, H, H, device=dev) + 0.3).bfloat16().float()
+    wt = (torch.randn(cout, cin, 3, 3, device=dev) / (cin * 9) ** 0.5).bfloat16().float()
+    bias = torch.randn(cout, device=dev) * 0.5
+    p = LayerParams(w=wt, b=bias, gamma=torch.ones(cout, device=dev), beta=torch.zeros(cout, device=dev),
+                    rmean=torch.zeros(cout, device=dev), rvar=torch.zeros(cout, device=dev),
+                    nbt=torch.zeros((), dtype=torch.long, device=dev))
+    xp = engine.to_padded(x, 'bf16', cp=cin)
+    assert engine.uses_tc(spec, cin, 'bf16')
+    out = torch.empty(n, H, H, cout, device=dev)
+    engine.unit_forward([spec], [p], xp, H, H, 'bf16', out, 0)
+    ref = torch.nn.functional.conv2d(torch.nn.functional.pad(x.double(), (1, 1, 1, 1), mode='replicate'), wt.double(), bias.double())
+    mean = ref.mean(dim=(0, 2, 3))
+    var_unbiased = ref.var(dim=(0, 2, 3), unbiased=True)
+    R = Report()
+    R.close(p.rmean, 0.1 * mean, 1e-4, 'running_mean (0.1 * batch mean)')
+    R.close(p.rvar, 0.1 * var_unbiased, 1e-4, 'running_var (0.1 * unbiased batch variance)')
+    # the normalised output itself (bf16 y re-read by the BatchNorm pass): zero mean / unit variance per channel
+    R.add('normalised mean', float(out.double().mean(dim=(0, 1, 2)).abs().max()), 5e-3)
+    R.add('normalised var', float((out.double().var(dim=(0, 1, 2), unbiased=False) - 1).abs().max()), 1e-2)
+    R.finish()
+
+
 # ------------------------------------------------------------------------------------------------
 def test_bf16_and_fp32_training_runs_converge_together(dev):
     """(c) 200 Adam steps of KeyNet F (128x128x3, K=10, batch 8) on one fixed pair of batches, from identical weights, once
