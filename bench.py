@@ -558,9 +558,8 @@ def main():
         if tc_n and step_roof['bound'] == 'tensor':
             ach = tc_fl / (tc_ms / 1e3) / 1e12 if tc_ms > 0 else 0.0
             traffic, traffic_note = None, None
-            tpath = os.path.join(ROOT, 'profiles', 'r2_tc_traffic.json')
-            if not os.path.exists(tpath):
-                tpath = os.path.join(ROOT, 'profiles', 'r1_tc_traffic.json')
+            tpath = next((q for q in (os.path.join(ROOT, 'profiles', f'{t}_tc_traffic.json') for t in ('r2b', 'r2', 'r1'))
+                          if os.path.exists(q)), '')
             if wl == 'keynet_F_128_K10' and B == 64 and os.path.exists(tpath):
                 tj = json.load(open(tpath))
                 traffic = tj['bytes_per_launch']
