@@ -481,6 +481,7 @@ def main():
     ap.add_argument('--no-kernel-timing', action='store_true')
     ap.add_argument('--no-eager-baseline', action='store_true')
     ap.add_argument('--no-other-workloads', action='store_true')
+    ap.add_argument('--no-batch-sweep', action='store_true')
     ap.add_argument('--no-module-api', action='store_true')
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
@@ -599,6 +600,24 @@ def main():
             r2.close()
             others.append(entry)
 
+    # ---- batch sweep of the headline workload (SURVEY 8 cfg 3: 16 = the reference's default batch, 64, 256), rank 0 only ----
+    sweep = None
+    if not (args.no_batch_sweep or args.no_other_workloads) and args.precision == 'bf16' and world == 1 and wl == 'keynet_F_128_K10':
+        sweep = []
+        for sb in (16, 128, 256):
+            if sb == B:
+                continue
+            r3 = Run(args, wl, sb, dev, rank, world)
+            ssteps = 10
+            sms = r3.timed(ssteps, 3)
+            sval = ssteps * sb / (sms / 1e3)
+            sweep.append({'per_gpu_batch': sb, 'value': sval, 'unit': 'pairs/s', 'ms_per_step': sms / ssteps, 'steps': ssteps,
+                          'warmup': 3, 'step_frac_of_roofline': step_roofline(wl, sval, pk)['frac']})
+            r3.close()
+        sweep.append({'per_gpu_batch': B, 'value': value, 'unit': 'pairs/s', 'ms_per_step': ms / args.steps, 'steps': args.steps,
+                      'warmup': args.warmup, 'step_frac_of_roofline': step_roofline(wl, value, pk)['frac']})
+        sweep.sort(key=lambda e: e['per_gpu_batch'])
+
     cpu = None
     parity = None
     eager = None
@@ -632,7 +651,7 @@ def main():
                 'gpu_launches': (launches if launches is not None else (calls_per_step or 0) * args.steps),
                 'gpu_launches_note': 'C-ABI kernel-launching calls inside the timed region (each >= 1 kernel; replayed from a CUDA graph)',
                 'clocks': clocks, 'roofline': roof, 'cpu_baseline': cpu, 'parity': parity, 'gpu_eager_baseline': eager,
-                'module_api': module_api, 'other_workloads': others or None, 'loss': loss_val,
+                'module_api': module_api, 'other_workloads': others or None, 'batch_sweep': sweep, 'loss': loss_val,
                 'activation_bytes': activation_bytes, 'params': n_params}
         print(json.dumps(line))
     if world > 1:

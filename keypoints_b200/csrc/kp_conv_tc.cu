@@ -317,8 +317,9 @@ conv_tc_persist_k(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             const long long q = q_tile + row;
             bool valid = q < p.Q;
             if (valid && p.stats) {
-                int x = (int)(q % p.PW);
-                int y = (int)((q / p.PW) % p.PH);
+                const unsigned qu = (unsigned)q, row_i = qu / (unsigned)p.PW;       // Q < 2^31 (checked by the launcher): 32-bit divisions
+                int x = (int)(qu - row_i * (unsigned)p.PW);
+                int y = (int)(row_i % (unsigned)p.PH);
                 valid = x < p.VW && y < p.VH;
             }
             mbar_wait(bars + 8 * (2 * STAGES + buf), (lt >> 1) & 1);
@@ -585,8 +586,9 @@ conv_tc_pair_k(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const long long q = q_tile + row;
             bool valid = q < p.Q;
             if (valid && p.stats) {
-                int x = (int)(q % p.PW);
-                int y = (int)((q / p.PW) % p.PH);
+                const unsigned qu = (unsigned)q, row_i = qu / (unsigned)p.PW;       // Q < 2^31 (checked by the launcher): 32-bit divisions
+                int x = (int)(qu - row_i * (unsigned)p.PW);
+                int y = (int)(row_i % (unsigned)p.PH);
                 valid = x < p.VW && y < p.VH;
             }
             mbar_wait(bars + 8 * (2 * STAGES + buf), (lt >> 1) & 1);
@@ -879,8 +881,9 @@ conv_tc_pair3_k(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             const long long q = q_tile + row;
             bool valid = q < p.Q;
             if (valid && p.stats) {
-                int x = (int)(q % p.PW);
-                int y = (int)((q / p.PW) % p.PH);
+                const unsigned qu = (unsigned)q, row_i = qu / (unsigned)p.PW;       // Q < 2^31 (checked by the launcher): 32-bit divisions
+                int x = (int)(qu - row_i * (unsigned)p.PW);
+                int y = (int)(row_i % (unsigned)p.PH);
                 valid = x < p.VW && y < p.VH;
             }
             mbar_wait(bars + 8 * (TFULL + buf), (lt >> 1) & 1);

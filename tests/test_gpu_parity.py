@@ -261,7 +261,8 @@ def _conv_ref(x, w, b):
 
 
 @pytest.mark.parametrize('cin,cout,k,n,h,w', [(64, 128, 3, 2, 8, 8), (128, 64, 3, 3, 12, 20), (256, 256, 3, 1, 16, 16),
-                                                (512, 64, 1, 2, 4, 4), (128, 512, 3, 2, 6, 5)])
+                                                (512, 64, 1, 2, 4, 4), (128, 512, 3, 2, 6, 5),
+                                                (64, 128, 3, 2, 16, 16), (256, 128, 3, 2, 12, 12)])   # register-statistics tiles
 def test_tensor_core_conv_vs_fp32(dev, cin, cout, k, n, h, w):
     """tcgen05 fprop / dgrad / wgrad against an fp32 reference fed the same bf16-rounded operands."""
     from keypoints_b200 import engine, lib as L
