@@ -438,15 +438,17 @@ class Run:
         import torch
         from keypoints_b200 import lib as L
         tr = self.tr
-        was = tr.use_graph, tr.two_streams, tr.world
-        tr.use_graph, tr.two_streams, tr.world = False, False, 1
+        # one stream: with the side streams on (encoder beside keypoint branch, weight gradients beside the dgrad chain) a
+        # kernel's event pair also spans the time it waits for SMs held by the kernel running next to it
+        was = tr.use_graph, tr.two_streams, tr.wgrad_streams, tr.world
+        tr.use_graph, tr.two_streams, tr.wgrad_streams, tr.world = False, False, False, 1
         self.one_step()
         torch.cuda.synchronize()
         L.timing = []
         self.one_step()
         torch.cuda.synchronize()
         rec, L.timing = L.timing, None
-        tr.use_graph, tr.two_streams, tr.world = was
+        tr.use_graph, tr.two_streams, tr.wgrad_streams, tr.world = was
         return rec
 
     def close(self):
