@@ -748,7 +748,11 @@ bool kp_c1_conv_ok(const kp_view* in, const kp_view* out, int OH, int OW, int IH
 int kp_c1_fprop(cudaStream_t st, const kp_view* in, const float* wk, const float* bias, const kp_view* out, double* stats, int N,
                 int OH, int OW, int Cout) {
     long long rows = (long long)N * OH;
-    const long long cap = (long long)kp_sm_count() * 8;
+    static int mult = -1;
+    // 2 blocks per SM: every block ends with 2 * Cout double atomics on the same statistics words; at 8 blocks per SM their
+    // serialisation in the L2 cost more than the extra row passes per block (33 -> 26 us at 84x84, 128 images)
+    if (mult < 0) { const char* e = kp_env("KP_C1_FPROP_MULT"); mult = e ? atoi(e) : 2; if (mult < 1) mult = 1; }
+    const long long cap = (long long)kp_sm_count() * mult;
     const int grid = (int)(rows < cap ? rows : cap);
 #define KP_C1(GV) c1_fprop_k<GV><<<grid, 256, 0, st>>>(make_view<bf16>(in), wk, bias, make_view<bf16>(out), stats, N, OH, OW)
     if (Cout == 8) KP_C1(1); else if (Cout == 16) KP_C1(2); else if (Cout == 32) KP_C1(4); else KP_C1(8);
