@@ -221,8 +221,11 @@ class Trainer:
         return out
 
     def _fwd_unit(self, u: _UnitState, x_pad, H, W, out, out_pad):
-        # encoder and keypoint stacks run side by side on two streams: their BatchNorm passes share SMs with the other's convs
-        co = self.two_streams and self.kind != 'autoencoder' and u.name != 'decoder'
+        # encoder and keypoint stacks run side by side on two streams: their BatchNorm passes share SMs with the other's convs.
+        # Measured on one box, 4 interleaved runs each (gpurun_out/r3_co*): KeyNet F 4479 -> 4503 pairs/s with the hint,
+        # Transporter F 3584 -> 3553 (its source-frame passes already fill the gaps) - so KeyNet only.
+        co = (self.two_streams and self.kind == 'keynet' and u.name != 'decoder'
+              and os.environ.get('KP_BN_CORESIDENT', '1') != '0')
         u.ctxs = engine.unit_forward(u.specs, u.params, x_pad, H, W, self.precision, out, out_pad, alloc=u.alloc,
                                      training=True, packs=u.packs, tag='f', coresident=co)
 
