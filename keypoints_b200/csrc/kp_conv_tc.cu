@@ -119,6 +119,19 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
         : "memory");
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+// 16 TMEM lanes x 32 columns in the mma C-fragment layout (probed on B200, scripts/exp_tmem_ld_shapes.cu): with g = lane / 4,
+// q = lane % 4, r[4x + 0..1] = (row g, columns 8x + 2q, 8x + 2q + 1), r[4x + 2..3] = (row g + 8, same columns), x = 0..3.
+// No wait inside: the caller issues its loads back to back and waits once.
+__device__ __forceinline__ void tmem_ld_16x256b_x4(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.16x256b.x4.b32 "
+        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ bool elect_one() {
     uint32_t pred;
     asm volatile(
@@ -708,17 +721,17 @@ __device__ __forceinline__ float warp_transpose_sum32(float* x, int lane) {
 // BN <= 128: the BatchNorm statistics are accumulated per thread in registers across the tiles of a CTA (one row, BN/2
 // columns per thread) and reduced over rows once per CTA with warp shuffles; the BN = 256 tiles keep the per-tile
 // shared-memory transposes (256 accumulators per thread do not fit the register file).
-template <int BN, int AS, int BS, bool RB>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(BN <= 128 ? 384 : 320, 1)
+template <int BN, int AS, int BS, bool RB, bool FE>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__((BN <= 128 && !FE) ? 384 : 320, 1)
 conv_tc_pair3_k(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmO, const ConvTcParams p) {
-    constexpr bool RS = BN <= 128;                             // register-resident statistics
+    constexpr bool RS = BN <= 128 && !FE;                      // register-resident statistics, one row per thread
     constexpr int EW0 = RS ? 4 : 2;                            // first epilogue warp (RS: warpgroups 1 and 2)
     constexpr int NCH = BN / 64;                               // 32-column chunks per epilogue thread
     constexpr int B_BYTES = (BN / 2) * 128;                    // this CTA's half of the weight tile
     constexpr int RING_BYTES = AS * A3_SLOT + BS * B_BYTES;
     constexpr int NBAR = 2 * AS + 2 * BS + 4;                  // a_full, a_empty, b_full, b_empty, tfull[2], tempty[2]
     constexpr int AFULL = 0, AEMPTY = AS, BFULL = 2 * AS, BEMPTY = 2 * AS + BS, TFULL = 2 * AS + 2 * BS, TEMPTY = TFULL + 2;
-    constexpr int TILE_FLOATS = RS ? 0 : 8 * 32 * 17;          // per-warp 32x16 transpose tiles (BN = 256 only)
+    constexpr int TILE_FLOATS = (RS || FE) ? 0 : 8 * 32 * 17;  // per-warp 32x16 transpose tiles (BN = 256 without FE only)
     constexpr int EPI_FLOATS = TILE_FLOATS + 4 * 2 * BN;       // + per-lane-group running column sums
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -831,6 +844,123 @@ conv_tc_pair3_k(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     }
     } else {
         if constexpr (RS) asm volatile("setmaxnreg.inc.sync.aligned.u32 208;" ::: "memory");
+        if constexpr (FE) {
+            // Fragment epilogue: the accumulator is read in the mma C-fragment layout (tcgen05.ld.16x256b), so a thread holds
+            // 4 rows x 2 adjacent columns of every 8-column group instead of one row x 32 columns: its BatchNorm column sums
+            // need BN / 4 accumulators (64 at BN = 256) and stay in registers across all tiles of the CTA for every tile width.
+            constexpr int NCF = BN / 64;                        // 32-column chunks per thread
+            const int wq = warp & 3, g = lane >> 2, q4 = lane & 3;
+            const int et = threadIdx.x - EW0 * 32;
+            const int half = (warp - EW0) >> 2;
+            float* wsum_all = epi + TILE_FLOATS;
+            float* wsum = wsum_all + wq * (2 * BN);
+            float a1[NCF * 8], a2[NCF * 8];
+#pragma unroll
+            for (int j = 0; j < NCF * 8; ++j) { a1[j] = 0.f; a2[j] = 0.f; }
+            int lt = 0, cur_n = -1, slabs = 0;
+            auto flush = [&](int n_tile) {                      // all 256 epilogue threads
+#pragma unroll
+                for (int j = 0; j < NCF * 8; ++j) {
+                    float s1 = a1[j], s2 = a2[j];
+#pragma unroll
+                    for (int o = 4; o < 32; o <<= 1) { s1 += __shfl_xor_sync(0xffffffffu, s1, o); s2 += __shfl_xor_sync(0xffffffffu, s2, o); }
+                    if (g == 0) {
+                        const int col = (half + 2 * (j >> 3)) * 32 + 8 * ((j & 7) >> 1) + 2 * q4 + (j & 1);
+                        wsum[col] = s1;
+                        wsum[BN + col] = s2;
+                    }
+                    a1[j] = 0.f; a2[j] = 0.f;
+                }
+                asm volatile("bar.sync 1, 256;" ::: "memory");
+                for (int ch = et; ch < BN; ch += 256) {
+                    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+                    for (int w = 0; w < 4; ++w) {
+                        s1 += wsum_all[w * 2 * BN + ch];
+                        s2 += wsum_all[w * 2 * BN + BN + ch];
+                        wsum_all[w * 2 * BN + ch] = 0.f;
+                        wsum_all[w * 2 * BN + BN + ch] = 0.f;
+                    }
+                    atomicAdd(&p.stats[n_tile * BN + ch], (double)s1);
+                    atomicAdd(&p.stats[p.Cout + n_tile * BN + ch], (double)s2);
+                }
+                asm volatile("bar.sync 1, 256;" ::: "memory");
+            };
+            const bool bias_v = p.bias && ((reinterpret_cast<uintptr_t>(p.bias) & 7) == 0);
+            for (int t = cid; t < total; t += nclusters, ++lt) {
+                const int n_t = t / num_m, m_t = t - n_t * num_m;
+                const int n0 = n_t * BN;
+                const int buf = lt & 1;
+                if (p.stats && cur_n >= 0 && cur_n != n_t) flush(cur_n);
+                cur_n = n_t;
+                const long long q_tile = (long long)m_t * 256 + rank * 128;
+                float vm[4] = {0.f, 0.f, 0.f, 0.f};             // rows wq * 32 + g + 8 k of the tile: 1 = counts in the statistics
+                if (p.stats) {
+#pragma unroll
+                    for (int kq = 0; kq < 4; ++kq) {
+                        const long long qq = q_tile + wq * 32 + g + 8 * kq;
+                        if (qq < p.Q) {
+                            const unsigned qu = (unsigned)qq, row_i = qu / (unsigned)p.PW;
+                            const int x = (int)(qu - row_i * (unsigned)p.PW), y = (int)(row_i % (unsigned)p.PH);
+                            vm[kq] = (x < p.VW && y < p.VH) ? 1.f : 0.f;
+                        }
+                    }
+                }
+                mbar_wait(bars + 8 * (TFULL + buf), (lt >> 1) & 1);
+                tc_fence_after();
+#pragma unroll
+                for (int i = 0; i < NCF; ++i) {
+                    const int c = half + 2 * i;
+                    const int sb = slabs & 1;
+                    uint32_t r0[16], r1[16];
+                    const uint32_t tcol = tmem_base + buf * BN + c * 32;
+                    tmem_ld_16x256b_x4(tcol + ((uint32_t)(wq * 32) << 16), r0);
+                    tmem_ld_16x256b_x4(tcol + ((uint32_t)(wq * 32 + 16) << 16), r1);
+                    float2 bv[4];
+#pragma unroll
+                    for (int x = 0; x < 4; ++x) {
+                        const float* bp = p.bias + n0 + c * 32 + 8 * x + 2 * q4;
+                        bv[x] = bias_v ? *reinterpret_cast<const float2*>(bp) : (p.bias ? make_float2(bp[0], bp[1]) : make_float2(0.f, 0.f));
+                    }
+                    if (et == 0) bulk_wait_read<1>();           // the store that last read this slab buffer is done with it
+                    asm volatile("bar.sync 1, 256;" ::: "memory");
+                    tmem_ld_wait();
+                    uint8_t* dbase = slab_gen + sb * SLAB_BYTES + (wq * 32 + g) * 128 + q4 * 4;
+#pragma unroll
+                    for (int sbk = 0; sbk < 2; ++sbk) {
+#pragma unroll
+                        for (int x = 0; x < 4; ++x) {
+                            const uint32_t* rr = sbk ? r1 : r0;
+                            const float v00 = __uint_as_float(rr[4 * x]) + bv[x].x, v01 = __uint_as_float(rr[4 * x + 1]) + bv[x].y;
+                            const float v10 = __uint_as_float(rr[4 * x + 2]) + bv[x].x, v11 = __uint_as_float(rr[4 * x + 3]) + bv[x].y;
+                            // slab row R = wq * 32 + 16 sbk + 8 e + g (R & 7 == g), 16-byte chunk (c & 1) * 4 + x, swizzled by the row
+                            const int ch16 = ((((c & 1) << 2) + x) ^ g) << 4;
+                            __nv_bfloat162 h0 = __floats2bfloat162_rn(v00, v01), h1 = __floats2bfloat162_rn(v10, v11);
+                            *reinterpret_cast<__nv_bfloat162*>(dbase + (sbk * 16) * 128 + ch16) = h0;
+                            *reinterpret_cast<__nv_bfloat162*>(dbase + (sbk * 16 + 8) * 128 + ch16) = h1;
+                            if (p.stats) {
+                                const float m0 = vm[2 * sbk], m1 = vm[2 * sbk + 1];
+                                const float w00 = m0 * v00, w01 = m0 * v01, w10 = m1 * v10, w11 = m1 * v11;
+                                a1[i * 8 + 2 * x] += w00 + w10;
+                                a1[i * 8 + 2 * x + 1] += w01 + w11;
+                                a2[i * 8 + 2 * x] = fmaf(w00, v00, fmaf(w10, v10, a2[i * 8 + 2 * x]));
+                                a2[i * 8 + 2 * x + 1] = fmaf(w01, v01, fmaf(w11, v11, a2[i * 8 + 2 * x + 1]));
+                            }
+                        }
+                    }
+                    fence_async_smem();
+                    asm volatile("bar.sync 1, 256;" ::: "memory");
+                    if (et == 0) tma_store_2d(&tmO, slab + sb * SLAB_BYTES, n0 + (c >> 1) * 64, (int)q_tile);
+                    ++slabs;
+                }
+                // every epilogue thread has drained its TMEM rows: release the accumulator buffer to the MMA warp
+                tc_fence_before();
+                asm volatile("bar.sync 1, 256;" ::: "memory");
+                if (et == 0) mbar_arrive_leader(bars + 8 * (TEMPTY + buf));
+            }
+            if (p.stats && cur_n >= 0) flush(cur_n);
+            if (et == 0) bulk_wait_all();                       // every TMA store has completed before the CTA exits
+        } else {
         const int wq = warp & 3;
         const int row = wq * 32 + lane;
         const int et = threadIdx.x - EW0 * 32;                 // 0..255: 8 epilogue warps, 2 per TMEM lane group
@@ -1007,6 +1137,7 @@ conv_tc_pair3_k(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         }
         if (p.stats && cur_n >= 0) flush(cur_n);
         if (et == 0) bulk_wait_all();                          // every TMA store has completed before the CTA exits
+        }
     }
     tc_fence_before();
     __syncthreads();
@@ -1582,20 +1713,20 @@ static int launch_conv_pair(cudaStream_t st, const CUtensorMap& a, const CUtenso
     return KP_OK;
 }
 
-template <int BN, int AS, int BS, bool RB>
+template <int BN, int AS, int BS, bool RB, bool FE>
 static int launch_conv_pair3(cudaStream_t st, const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& o, const ConvTcParams& p) {
-    constexpr int smem = AS * A3_SLOT + BS * (BN / 2) * 128 + 2 * SLAB_BYTES + ((BN <= 128 ? 0 : 8 * 32 * 17) + 4 * 2 * BN) * 4 +
+    constexpr int smem = AS * A3_SLOT + BS * (BN / 2) * 128 + 2 * SLAB_BYTES + (((BN <= 128 || FE) ? 0 : 8 * 32 * 17) + 4 * 2 * BN) * 4 +
                          8 * (2 * AS + 2 * BS + 4) + 16 + 1024;
     static_assert(smem <= 227 * 1024, "shared memory budget");
     static KpOncePerDevice attr_done;
     if (attr_done.first()) {
-        KP_CUDA(cudaFuncSetAttribute(conv_tc_pair3_k<BN, AS, BS, RB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        KP_CUDA(cudaFuncSetAttribute(conv_tc_pair3_k<BN, AS, BS, RB, FE>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     }
     long long total = ((p.Q + 255) / 256) * (p.Cout / BN);
     int clusters = kp_sm_count() / 2;
     if (clusters > total) clusters = (int)total;
     if (clusters < 1) clusters = 1;
-    conv_tc_pair3_k<BN, AS, BS, RB><<<2 * clusters, BN <= 128 ? 384 : 320, smem, st>>>(a, b, o, p);
+    conv_tc_pair3_k<BN, AS, BS, RB, FE><<<2 * clusters, (BN <= 128 && !FE) ? 384 : 320, smem, st>>>(a, b, o, p);
     KP_LAUNCH_CHECK();
     return KP_OK;
 }
@@ -1693,17 +1824,31 @@ extern "C" int kp_conv_tc(kp_stream stream, const void* in_bf16, int64_t Q, int 
             CUtensorMap ta3;                                   // 128 + 2 pixel rows (padded to 136) per kernel row
             rc = make_map(&ta3, in_bf16, Q, Cin, A3_ROWS);
             if (rc) return rc;
-            if (BN == 256) return launch_conv_pair3<256, 3, 6, false>(st, ta3, tbh, to, p);
+            // Fragment epilogue (tcgen05.ld.16x256b, 4-byte slab stores) for the launches WITHOUT BatchNorm statistics, i.e. the
+            // dgrads: 1-5 % faster there on every layer (3.37 -> 3.27 ms over the 23 dgrad launches of a step,
+            // gpurun_out/r3_calls_fe{0,1}.txt).  With statistics its four rows per thread need four validity tests and masked
+            // sums per tile: equal on the 256-wide tiles, 24 % slower on the short 64 -> 128 tiles - fprop keeps the
+            // row-per-thread epilogues.  Experiments build: KP_TC_FE=0 never, =2 always.
+            static int fe_mode = -1;
+            if (fe_mode < 0) { const char* e = kp_env("KP_TC_FE"); fe_mode = e ? atoi(e) : 1; }
+            const bool fe_on = fe_mode == 2 || (fe_mode == 1 && stats == nullptr);
             // small weight sets stay resident in shared memory (loaded once per CTA): 64 -> 128 and 128 -> 64 (and their
             // dgrads), 72 KB per CTA; the activation ring takes the rest but leaves 16 KB for a co-resident BatchNorm CTA
             static int rb_on = -1;
             if (rb_on < 0) { const char* e = kp_env("KP_TC_RESB"); rb_on = (e && e[0] == '0') ? 0 : 1; }
-            if (rb_on && Cout == BN) {
-                if (BN == 128 && Cin == 64) return launch_conv_pair3<128, 5, 9, true>(st, ta3, tbh, to, p);
-                if (BN == 64 && Cin == 128) return launch_conv_pair3<64, 5, 18, true>(st, ta3, tbh, to, p);
+            const bool rb = rb_on && Cout == BN;
+            if (fe_on) {
+                if (BN == 256) return launch_conv_pair3<256, 3, 6, false, true>(st, ta3, tbh, to, p);
+                if (rb && BN == 128 && Cin == 64) return launch_conv_pair3<128, 5, 9, true, true>(st, ta3, tbh, to, p);
+                if (rb && BN == 64 && Cin == 128) return launch_conv_pair3<64, 5, 18, true, true>(st, ta3, tbh, to, p);
+                if (BN == 128) return launch_conv_pair3<128, 4, 8, false, true>(st, ta3, tbh, to, p);
+                return launch_conv_pair3<64, 5, 12, false, true>(st, ta3, tbh, to, p);
             }
-            if (BN == 128) return launch_conv_pair3<128, 4, 8, false>(st, ta3, tbh, to, p);
-            return launch_conv_pair3<64, 5, 12, false>(st, ta3, tbh, to, p);
+            if (BN == 256) return launch_conv_pair3<256, 3, 6, false, false>(st, ta3, tbh, to, p);
+            if (rb && BN == 128 && Cin == 64) return launch_conv_pair3<128, 5, 9, true, false>(st, ta3, tbh, to, p);
+            if (rb && BN == 64 && Cin == 128) return launch_conv_pair3<64, 5, 18, true, false>(st, ta3, tbh, to, p);
+            if (BN == 128) return launch_conv_pair3<128, 4, 8, false, false>(st, ta3, tbh, to, p);
+            return launch_conv_pair3<64, 5, 12, false, false>(st, ta3, tbh, to, p);
         }
         if (BN == 256) return launch_conv_pair<256, 5>(st, ta, tbh, to, p);
         if (BN == 128) return launch_conv_pair<128, 7>(st, ta, tbh, to, p);
