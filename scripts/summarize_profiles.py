@@ -181,14 +181,14 @@ def sass():
     txt = subprocess.run(['cuobjdump', '-sass', so], capture_output=True, text=True).stdout
     c = collections.Counter()
     import re
-    for m in re.finditer(r'\b(LDGMC[.A-Z0-9_]*|UTCHMMA[.A-Z0-9]*|UTMALDG[.A-Z0-9_]*|UTMAPF[.A-Z0-9_]*|UTCBAR[.A-Z0-9_]*|LDTM[.A-Z0-9_]*|HMMA[.A-Z0-9_]*|REDG[.A-Z0-9_]*|SYNCS[.A-Z0-9_]*|UBLKCP[.A-Z0-9_]*|FFMA2[.A-Z0-9_]*|UTMASTG[.A-Z0-9_]*)', txt):
+    for m in re.finditer(r'\b(LDGMC[.A-Z0-9_]*|UTCHMMA[.A-Z0-9]*|UTMALDG[.A-Z0-9_]*|UTMAPF[.A-Z0-9_]*|UTCBAR[.A-Z0-9_]*|LDTM[.A-Za-z0-9_]*|USETMAXREG[.A-Z0-9_]*|HMMA[.A-Z0-9_]*|REDG[.A-Z0-9_]*|SYNCS[.A-Z0-9_]*|UBLKCP[.A-Z0-9_]*|FFMA2[.A-Z0-9_]*|UTMASTG[.A-Z0-9_]*)', txt):
         c[m.group(1)] += 1
     with open(os.path.join(OUT, f'{TAG}_sass_evidence.md'), 'w') as fh:
         fh.write(f'# SASS mnemonics in libkeypoints_b200.so ({TAG})\n\n`cuobjdump -sass keypoints_b200/lib/libkeypoints_b200.so`\n\n| mnemonic | count |\n|---|---:|\n')
         for k, v in sorted(c.items()):
             fh.write(f'| {k} | {v} |\n')
         fh.write('\nUTCHMMA = tcgen05.mma (`.2CTA` = cta_group::2), UTMALDG = cp.async.bulk.tensor (TMA), LDTM = tcgen05.ld, '
-                 'UTCBAR = tcgen05.commit, UTMASTG = TMA store (conv epilogue), UBLKCP = cp.async.bulk (BatchNorm streaming kernels), '
+                 '(LDTM.x16 / .x32 = 32x32b row-per-thread loads, LDTM.16dp256bit = 16x256b fragment loads of the dgrad epilogue), USETMAXREG = setmaxnreg (register hand-over between the warpgroups of the register-statistics conv tiles), UTCBAR = tcgen05.commit, UTMASTG = TMA store (conv epilogue), UBLKCP = cp.async.bulk (BatchNorm streaming kernels), '
                  'FFMA2 = packed fp32x2 math; LDGMC / STG...MC = multimem.ld_reduce / multimem.st (kp_dp.cu); HMMA (mma.sync) in the kernels '
                  'for shapes a 64-channel tcgen05 k-block cannot fill: first-layer Cin<=3 and narrow 1x1 heads (kp_conv_thin_mma.cu: '
                  'thin_mma_*, head_mma_*) and the 16/32-channel VGG_PONG layers (kp_conv_small_mma.cu: small_mma_*).\n')
