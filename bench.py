@@ -444,11 +444,20 @@ class Run:
         tr.use_graph, tr.two_streams, tr.wgrad_streams, tr.world = False, False, False, 1
         self.one_step()
         torch.cuda.synchronize()
-        L.timing = []
-        self.one_step()
-        torch.cuda.synchronize()
-        rec, L.timing = L.timing, None
+        runs = []
+        for _ in range(3):                       # three timed steps: the per-call durations are averaged call by call
+            L.timing = []
+            self.one_step()
+            torch.cuda.synchronize()
+            runs.append(L.timing)
+        L.timing = None
         tr.use_graph, tr.two_streams, tr.wgrad_streams, tr.world = was
+        assert all(len(r) == len(runs[0]) for r in runs)
+        rec = []
+        for calls in zip(*runs):
+            name, fl, _, _, tg = calls[0]
+            ms = sum(a.elapsed_time(b) for _, _, a, b, _ in calls) / len(calls)
+            rec.append((name, fl, ms, tg))
         return rec
 
     def close(self):
@@ -542,9 +551,8 @@ def main():
         rec = run.kernel_timing()
         agg = {}
         calls = []
-        for name, fl, a, b, tg in rec:
+        for name, fl, t_ms, tg in rec:
             d = agg.setdefault(name, [0, 0.0, 0.0])
-            t_ms = a.elapsed_time(b)
             d[0] += 1; d[1] += t_ms; d[2] += fl
             calls.append((t_ms, name, tg, fl))
         if os.environ.get('KP_BENCH_CALLS'):

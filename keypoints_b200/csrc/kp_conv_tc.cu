@@ -895,16 +895,18 @@ conv_tc_pair3_k(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 cur_n = n_t;
                 const long long q_tile = (long long)m_t * 256 + rank * 128;
                 float vm[4] = {0.f, 0.f, 0.f, 0.f};             // rows wq * 32 + g + 8 k of the tile: 1 = counts in the statistics
+                bool allv = false;                              // every row of this WARP counts: unmasked sums
                 if (p.stats) {
+                    const long long q0r = q_tile + wq * 32 + g;
+                    const unsigned qu = (unsigned)q0r, row_i = qu / (unsigned)p.PW;     // one division pair, then +8 pixels per step
+                    int x = (int)(qu - row_i * (unsigned)p.PW), y = (int)(row_i % (unsigned)p.PH);
 #pragma unroll
                     for (int kq = 0; kq < 4; ++kq) {
-                        const long long qq = q_tile + wq * 32 + g + 8 * kq;
-                        if (qq < p.Q) {
-                            const unsigned qu = (unsigned)qq, row_i = qu / (unsigned)p.PW;
-                            const int x = (int)(qu - row_i * (unsigned)p.PW), y = (int)(row_i % (unsigned)p.PH);
-                            vm[kq] = (x < p.VW && y < p.VH) ? 1.f : 0.f;
-                        }
+                        vm[kq] = (q0r + 8 * kq < p.Q && x < p.VW && y < p.VH) ? 1.f : 0.f;
+                        x += 8;
+                        if (x >= p.PW) { x -= p.PW; if (++y >= p.PH) y = 0; }
                     }
+                    allv = __all_sync(0xffffffffu, vm[0] + vm[1] + vm[2] + vm[3] == 4.f);
                 }
                 mbar_wait(bars + 8 * (TFULL + buf), (lt >> 1) & 1);
                 tc_fence_after();
@@ -938,7 +940,12 @@ conv_tc_pair3_k(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                             __nv_bfloat162 h0 = __floats2bfloat162_rn(v00, v01), h1 = __floats2bfloat162_rn(v10, v11);
                             *reinterpret_cast<__nv_bfloat162*>(dbase + (sbk * 16) * 128 + ch16) = h0;
                             *reinterpret_cast<__nv_bfloat162*>(dbase + (sbk * 16 + 8) * 128 + ch16) = h1;
-                            if (p.stats) {
+                            if (allv) {
+                                a1[i * 8 + 2 * x] += v00 + v10;
+                                a1[i * 8 + 2 * x + 1] += v01 + v11;
+                                a2[i * 8 + 2 * x] = fmaf(v00, v00, fmaf(v10, v10, a2[i * 8 + 2 * x]));
+                                a2[i * 8 + 2 * x + 1] = fmaf(v01, v01, fmaf(v11, v11, a2[i * 8 + 2 * x + 1]));
+                            } else if (p.stats) {
                                 const float m0 = vm[2 * sbk], m1 = vm[2 * sbk + 1];
                                 const float w00 = m0 * v00, w01 = m0 * v01, w10 = m1 * v10, w11 = m1 * v11;
                                 a1[i * 8 + 2 * x] += w00 + w10;
@@ -1824,16 +1831,17 @@ extern "C" int kp_conv_tc(kp_stream stream, const void* in_bf16, int64_t Q, int 
             CUtensorMap ta3;                                   // 128 + 2 pixel rows (padded to 136) per kernel row
             rc = make_map(&ta3, in_bf16, Q, Cin, A3_ROWS);
             if (rc) return rc;
-            // Fragment epilogue (tcgen05.ld.16x256b, 4-byte slab stores) for the launches WITHOUT BatchNorm statistics, i.e. the
-            // dgrads: 1-5 % faster there on every layer (3.37 -> 3.27 ms over the 23 dgrad launches of a step,
-            // gpurun_out/r3_calls_fe{0,1}.txt).  With statistics its four rows per thread need four validity tests and masked
-            // sums per tile: equal on the 256-wide tiles, 24 % slower on the short 64 -> 128 tiles - fprop keeps the
-            // row-per-thread epilogues.  Experiments build: KP_TC_FE=0 never, =2 always.
+            // Fragment epilogue (tcgen05.ld.16x256b, 4-byte slab stores, statistics in BN / 4 registers per thread) everywhere
+            // except the one launch type it loses on: fprop of the 64 -> 128 layers, whose 9-k-block tiles leave the epilogue
+            // 2304 clocks and are 10 % faster with one row (one validity test) per thread.  Per launch the fragment form is
+            // 1-5 % faster on the dgrads and 2-4 % on the other fprops (gpurun_out/r3_calls_fe*.txt, r3_calls_fex*.txt).
+            // Experiments build: KP_TC_FE = 0 never, 1 dgrad only, 2 always, 3 (default) as described.
             static int fe_mode = -1;
-            if (fe_mode < 0) { const char* e = kp_env("KP_TC_FE"); fe_mode = e ? atoi(e) : 1; }
-            const bool fe_on = fe_mode == 2 || (fe_mode == 1 && stats == nullptr);
+            if (fe_mode < 0) { const char* e = kp_env("KP_TC_FE"); fe_mode = e ? atoi(e) : 3; }
+            const bool short_stats = stats != nullptr && BN == 128 && Cin == 64;
+            const bool fe_on = fe_mode == 2 || (fe_mode == 3 && !short_stats) || (fe_mode == 1 && stats == nullptr);
             // small weight sets stay resident in shared memory (loaded once per CTA): 64 -> 128 and 128 -> 64 (and their
-            // dgrads), 72 KB per CTA; the activation ring takes the rest but leaves 16 KB for a co-resident BatchNorm CTA
+            // dgrads), 72 KB per CTA; the activation ring takes the rest
             static int rb_on = -1;
             if (rb_on < 0) { const char* e = kp_env("KP_TC_RESB"); rb_on = (e && e[0] == '0') ? 0 : 1; }
             const bool rb = rb_on && Cout == BN;
@@ -1844,11 +1852,16 @@ extern "C" int kp_conv_tc(kp_stream stream, const void* in_bf16, int64_t Q, int 
                 if (BN == 128) return launch_conv_pair3<128, 4, 8, false, true>(st, ta3, tbh, to, p);
                 return launch_conv_pair3<64, 5, 12, false, true>(st, ta3, tbh, to, p);
             }
-            if (BN == 256) return launch_conv_pair3<256, 3, 6, false, false>(st, ta3, tbh, to, p);
             if (rb && BN == 128 && Cin == 64) return launch_conv_pair3<128, 5, 9, true, false>(st, ta3, tbh, to, p);
+#ifdef KP_EXPERIMENTS
+            if (BN == 256) return launch_conv_pair3<256, 3, 6, false, false>(st, ta3, tbh, to, p);
             if (rb && BN == 64 && Cin == 128) return launch_conv_pair3<64, 5, 18, true, false>(st, ta3, tbh, to, p);
             if (BN == 128) return launch_conv_pair3<128, 4, 8, false, false>(st, ta3, tbh, to, p);
             return launch_conv_pair3<64, 5, 12, false, false>(st, ta3, tbh, to, p);
+#else
+            if (BN == 128) return launch_conv_pair3<128, 4, 8, false, false>(st, ta3, tbh, to, p);   // KP_TC_RESB off only
+            return launch_conv_pair3<64, 5, 12, false, true>(st, ta3, tbh, to, p);
+#endif
         }
         if (BN == 256) return launch_conv_pair<256, 5>(st, ta, tbh, to, p);
         if (BN == 128) return launch_conv_pair<128, 7>(st, ta, tbh, to, p);
