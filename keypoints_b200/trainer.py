@@ -221,11 +221,12 @@ class Trainer:
         return out
 
     def _fwd_unit(self, u: _UnitState, x_pad, H, W, out, out_pad):
-        # encoder and keypoint stacks run side by side on two streams: their BatchNorm passes share SMs with the other's convs.
-        # Measured on one box, 4 interleaved runs each (gpurun_out/r3_co*): KeyNet F 4479 -> 4503 pairs/s with the hint,
-        # Transporter F 3584 -> 3553 (its source-frame passes already fill the gaps) - so KeyNet only.
+        # Co-resident BatchNorm hint (small-footprint forward passes that fit beside the other stream's persistent conv CTAs):
+        # off by default since the fragment epilogue - the 256-wide conv tiles now hold 162 registers per thread, so a
+        # 288-thread BatchNorm CTA no longer fits next to them, and with or without the hint the step measures the same
+        # (4503 vs 4501 pairs/s, 4 interleaved runs each, gpurun_out/r3_b_f3c{1,0}_*.log).  KP_BN_CORESIDENT=1 turns it on.
         co = (self.two_streams and self.kind == 'keynet' and u.name != 'decoder'
-              and os.environ.get('KP_BN_CORESIDENT', '1') != '0')
+              and os.environ.get('KP_BN_CORESIDENT', '0') == '1')
         u.ctxs = engine.unit_forward(u.specs, u.params, x_pad, H, W, self.precision, out, out_pad, alloc=u.alloc,
                                      training=True, packs=u.packs, tag='f', coresident=co)
 
