@@ -2,6 +2,7 @@
 # A/B of the conv_tc_pair3_k epilogue / resident-weight variants (round 2, second session): parity tests first, then
 # per-call timings (single stream, eager) and the graph-replayed step of the product library and of the experiments build
 # with the resident-B path switched off.
+# needs the experiments build: make -C keypoints_b200/csrc EXPERIMENTS=1 OUT=../lib/libkeypoints_b200_exp.so BUILD=../_build_exp
 mkdir -p gpurun_out
 python -m pytest tests/test_gpu_fullsize.py -x -q -k "tcgen05" > gpurun_out/r3_test_tc.log 2>&1
 tail -3 gpurun_out/r3_test_tc.log

@@ -1,6 +1,7 @@
 #!/bin/bash
 # Fragment epilogue: KP_TC_FE = 3 (default: everywhere but the 64 -> 128 fprop) vs 1 (dgrad only), with and without the
 # co-resident BatchNorm hint (the 256-wide fragment tiles use 162 registers: a 288-thread BatchNorm CTA no longer fits beside them).
+# needs the experiments build: make -C keypoints_b200/csrc EXPERIMENTS=1 OUT=../lib/libkeypoints_b200_exp.so BUILD=../_build_exp
 mkdir -p gpurun_out
 python -m pytest tests/test_gpu_fullsize.py tests/test_gpu_parity.py -x -q -k "tcgen05 or tensor_core or fused_trainer or normalised" > gpurun_out/r3_test_fe.log 2>&1; tail -3 gpurun_out/r3_test_fe.log
 B="python bench.py --steps 30 --warmup 3 --no-cpu-baseline --no-eager-baseline --no-module-api --no-other-workloads --no-kernel-timing"
